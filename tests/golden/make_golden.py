@@ -1,0 +1,83 @@
+"""tests/golden/make_golden.py -- regenerate the golden fixtures from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):   make -C oracle && python tests/golden/make_golden.py
+Every array in tests/golden/*.npz is an input to, or an output of, the reference C++ itself
+(oracle/_ref/libmarius_ref.so = the reference's TUs compiled in place + oracle/ref_driver.cpp):
+  InMemory::indexRead/indexAdd, PartitionBuffer::{indexRead,indexAdd,getGlobalToLocalMap,getNextAdmit,getNextEvict},
+  map_tensors, Model::forward_lp, Model::train_batch.
+The fixtures travel to the GPU box; /root/reference does not.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import marius_oracle as O  # noqa: E402
+from oracle import ref_lib as R  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def train_case(name, kind, B, C, N, d, num_nodes, num_rel, reduction, seed, lr=0.1, emb_scale=0.5):
+    rng = np.random.default_rng(seed)
+    uniq, edges, dn, sn = O.make_batch(rng, num_nodes, num_rel, B, C, N)
+    U = len(uniq)
+    emb = rng.uniform(-emb_scale, emb_scale, (U, d)).astype(np.float32)
+    state = rng.uniform(0, 0.1, (U, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (num_rel, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (num_rel, d)).astype(np.float32)
+    ref = R.train_batch(kind, emb, state, edges, rel, inv_rel, dn, sn, lr, reduction)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind=kind, B=B, C=C, N=N, d=d, lr=np.float32(lr), reduction=reduction, uniq=uniq, edges=edges,
+                        dst_negs=dn, src_negs=sn, emb=emb, state=state, rel=rel, inv_rel=inv_rel, **{"ref_" + k: v for k, v in ref.items()})
+    print(name, "U", U)
+
+
+def storage_case():
+    rng = np.random.default_rng(7)
+    table = rng.standard_normal((257, 24)).astype(np.float32)
+    idx = rng.integers(0, 257, size=100, dtype=np.int64)          # duplicates allowed for reads
+    read = R.index_read(table, idx)
+    uidx = rng.permutation(257)[:90].astype(np.int64)             # unique for adds (buffer.cpp:459)
+    vals = rng.standard_normal((90, 24)).astype(np.float32)
+    after = table.copy()
+    R.index_add(after, uidx, vals)
+    throws = R.index_read_bad_rank_throws(table)
+    all_ids = rng.integers(0, 50, size=200, dtype=np.int64)
+    uniq, mapped = R.map_tensors(all_ids)
+    np.savez_compressed(os.path.join(OUT, "storage.npz"), table=table, idx=idx, read=read, uidx=uidx, vals=vals, after=after, bad_rank_throws=throws,
+                        all_ids=all_ids, uniq=uniq, mapped=mapped)
+    print("storage ok, bad rank throws:", throws)
+
+
+def buffer_case():
+    # test/cpp/unit/test_buffer.cpp:20-75 : 45 rows, 5 partitions of 10 (last has 5), capacity 2, and the
+    # 10-state ordering of TestPartitionBufferOrdering (:241-259); embedding_size reduced 10000 -> 16.
+    rng = np.random.default_rng(11)
+    total, nparts, psize, d, cap = 45, 5, 10, 16, 2
+    table = rng.standard_normal((total, d)).astype(np.float32)
+    states = np.array([[0, 1], [0, 2], [0, 3], [0, 4], [1, 4], [1, 3], [1, 2], [3, 2], [4, 2], [4, 3]], dtype=np.int64)
+    with tempfile.TemporaryDirectory() as td:
+        fn = os.path.join(td, "emb.bin")
+        table.tofile(fn)
+        idx = rng.permutation(20)[:12].astype(np.int64)           # buffer-local ids, unique
+        vals = rng.standard_normal((12, d)).astype(np.float32)
+        res = R.partition_buffer_exercise(fn, cap, nparts, psize, d, total, states, idx, vals)
+        file_after = np.fromfile(fn, dtype=np.float32).reshape(total, d)
+    np.savez_compressed(os.path.join(OUT, "partition_buffer.npz"), table=table, states=states, idx=idx, vals=vals, file_after=file_after,
+                        total=total, nparts=nparts, psize=psize, d=d, cap=cap, **res)
+    print("buffer admits", res["admits"], "evicts", res["evicts"])
+
+
+if __name__ == "__main__":
+    assert R.available(), "build oracle/_ref first: make -C oracle"
+    storage_case()
+    buffer_case()
+    train_case("train_distmult_pad", O.DISTMULT, 7, 3, 5, 8, 40, 3, O.REDUCTION_SUM, 1)
+    train_case("train_complex_pad", O.COMPLEX, 7, 3, 5, 8, 40, 3, O.REDUCTION_SUM, 2)
+    train_case("train_distmult_mean", O.DISTMULT, 64, 2, 32, 16, 300, 5, O.REDUCTION_MEAN, 3)
+    train_case("train_complex_mid", O.COMPLEX, 96, 3, 64, 48, 2000, 7, O.REDUCTION_SUM, 4)
+    train_case("train_distmult_dup", O.DISTMULT, 128, 4, 64, 32, 60, 4, O.REDUCTION_SUM, 5)   # heavy id collisions
+    train_case("train_complex_d100", O.COMPLEX, 200, 2, 100, 100, 14541, 237, O.REDUCTION_SUM, 6, emb_scale=0.1)  # FB15k-237-sized
