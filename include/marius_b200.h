@@ -1,0 +1,174 @@
+/* marius_b200.h -- C ABI of the B200-native Marius embedding hot path.
+ *
+ * One shared library (marius_b200/lib/libmarius_b200.so, hand-written sm_100a CUDA) behind plain
+ * pointers and sizes: no torch types, no C++ types, no exceptions.  Every entry point returns an
+ * mb_status; mb_last_error() gives the message for the calling thread.
+ *
+ * The reference (marius-team/marius) has no plugin/FFI ABI; its seam is a set of C++ virtual
+ * interfaces that pass torch::Tensor.  Each entry point below names the reference
+ * call site(s) it replaces (paths relative to /root/reference/src/cpp).  The C++/libtorch adapters
+ * that keep the reference's class surface (Storage, PartitionBuffer, EdgeDecoder, Batch, Model) live
+ * in marius_b200/csrc/host/ and only ever call this header.  INTEGRATION.md shows the binding a
+ * Marius maintainer would add.
+ *
+ * Conventions
+ *   - ids are int64, values fp32, matrices row-major with an explicit leading dimension (elements).
+ *   - every device pointer must belong to the device the context was created on.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless stated.  Calls are re-entrant across contexts; one context = one in-flight batch.
+ *   - "unique ids within one call" is the only exclusivity the update kernels assume
+ *     (storage/buffer.cpp:459), exactly as the reference.
+ */
+#ifndef MARIUS_B200_H_
+#define MARIUS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_VERSION 100
+
+typedef enum mb_status {
+    MB_OK = 0,
+    MB_ERR_INVALID = 1,     /* bad shapes / null pointers: the reference throws std::runtime_error (storage.cpp:607-610,652-655) */
+    MB_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed */
+    MB_ERR_UNSUPPORTED = 3, /* valid in the reference, not implemented here (documented in DESIGN.md) */
+    MB_ERR_NOMEM = 4
+} mb_status;
+
+/* decoder kinds: the DotCompare family of include/configuration/options.h:60 */
+typedef enum mb_decoder {
+    MB_DECODER_DOT = 0,      /* 2-column edges, no relation operator  (decoder_methods.cpp:99-101, comparators.cpp:62-72) */
+    MB_DECODER_DISTMULT = 1, /* HadamardOperator        + DotCompare  (distmult.cpp:7-19, relation_operators.cpp:7-12)  */
+    MB_DECODER_COMPLEX = 2   /* ComplexHadamardOperator + DotCompare  (complex.cpp:7-19,  relation_operators.cpp:14-35) */
+} mb_decoder;
+
+typedef enum mb_reduction { MB_REDUCTION_MEAN = 0, MB_REDUCTION_SUM = 1 } mb_reduction; /* options.h:24 */
+
+/* arithmetic of the dense (batch x dim).(neg x dim)^T contractions (comparators.cpp:69-72 and their autograd) */
+typedef enum mb_precision {
+    MB_PREC_FP32 = 0,   /* fp32 FFMA on the SIMT pipes: reference-exact arithmetic, any d                          */
+    MB_PREC_BF16X3 = 1, /* tcgen05 kind::f16, operands split hi+lo in bf16, 3 products, fp32 TMEM accumulation:
+                           |err| <= ~2^-16 relative per product -- meets the 1e-4 parity bar   */
+    MB_PREC_BF16 = 2    /* single bf16 product (fast, does NOT meet the parity bar; never the default)           */
+} mb_precision;
+
+typedef struct mb_context mb_context; /* device, SM count, workspace arena, TMA descriptors, sort scratch */
+
+/* ---- context ----------------------------------------------------------------------------------------- */
+mb_status mb_create(int device, mb_context** out);
+void mb_destroy(mb_context* ctx);
+const char* mb_last_error(void);
+int mb_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches counter) */
+uint64_t mb_launch_count(void);
+/* name of the largest tensor-core path compiled in ("tcgen05" when built for sm_100a) */
+const char* mb_build_info(void);
+
+/* ---- storage: gather / scatter-add ---------------------------------------------------------------------
+ * mb_gather_rows        InMemory::indexRead CUDA branch  storage/storage.cpp:613-614 (data_.index_select)
+ *                       PartitionBuffer::indexRead       storage/buffer.cpp:441-455 (HBM-resident slab)
+ * mb_scatter_add_rows   InMemory::indexAdd CUDA branch   storage/storage.cpp:656-657 (data_.index_add_)
+ *                       PartitionBuffer::indexAdd        storage/buffer.cpp:459-480
+ * mb_scatter_put_rows   InMemory::indexPut               storage/storage.cpp:675-690
+ * ids must be in [0, num_rows); this is checked on the device only when `check` != 0 (the reference
+ * does not check either); a violation makes the call return MB_ERR_INVALID after a stream sync.        */
+mb_status mb_gather_rows(const float* table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n, float* out, int64_t out_ld,
+                         void* stream);
+mb_status mb_scatter_add_rows(float* table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n, const float* vals,
+                              int64_t vals_ld, void* stream);
+mb_status mb_scatter_put_rows(float* table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n, const float* vals,
+                              int64_t vals_ld, void* stream);
+/* PartitionBuffer::getGlobalToLocalMap (buffer.cpp:581-633): map[g] = slot*partition_size + (g - p*partition_size) for every
+ * resident partition p (given as parallel arrays partition id -> buffer slot, host memory), -1 elsewhere.  `map` is device memory. */
+mb_status mb_global_to_local_map(int64_t* map, int64_t total_rows, int64_t partition_size, const int32_t* partition_ids,
+                                 const int32_t* buffer_slots, int n_resident, void* stream);
+
+/* ---- sparse Adagrad ------------------------------------------------------------------------------------
+ * mb_adagrad_deltas       Batch::accumulateGradients  data/batch.cpp:62-79 (returns delta_e, delta_s; op-for-op fp32)
+ * mb_adagrad_update_rows  = accumulateGradients + DataLoader::updateEmbeddings (dataloader.cpp:550-564 ->
+ *                           graph_storage.cpp:289,319-323 -> Storage::indexAdd x2) fused: one read-modify-write
+ *                           of each unique row of the table and of the state table.                     */
+mb_status mb_adagrad_deltas(const float* grad, const float* state, int64_t n, int64_t d, int64_t ld, float lr, float* delta_e, float* delta_s,
+                            void* stream);
+mb_status mb_adagrad_update_rows(float* table, float* state_table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n,
+                                 const float* grad, int64_t grad_ld, float lr, void* stream);
+
+/* ---- unique-id mapping ----------------------------------------------------------------------------------
+ * mb_map_tensors  map_tensors  common/util.cpp:180-205 (cat + torch::_unique2(sorted, inverse)), as used by
+ *                 DataLoader::edgeSample (dataloader.cpp:399-409,447-461).  `all_ids` [n] global ids ->
+ *                 `unique_out` [<= n] sorted unique ids, `mapped_out` [n] position of each input id, *num_unique
+ *                 (device int64).  Stable LSD radix sort on the device; bit-identical to the reference.   */
+mb_status mb_map_tensors(mb_context* ctx, const int64_t* all_ids, int64_t n, int64_t max_id, int64_t* unique_out, int64_t* mapped_out,
+                         int64_t* num_unique_dev, void* stream);
+
+/* ---- decoder + training step ---------------------------------------------------------------------------
+ * Batch-local problem, exactly the tensors the reference Batch carries (data/batch.h:49-75):
+ *   emb   [U,d]  node_embeddings_            edges [B,3] (or [B,2] when kind == DOT): local src, rel, local dst
+ *   dst_negs / src_negs [C,N]  dst_neg_indices_mapping_ / src_neg_indices_mapping_ (local ids)
+ *   rel / inv_rel [R,d]  EdgeDecoder::relations_ / inverse_relations_ (edge_decoder.h:17-18); inv_rel == NULL or
+ *   src_negs == NULL -> use_inverse_relations_ = false.
+ * Bp = C * ceil(B / C): rows are zero-padded like pad_and_reshape (comparators.cpp:7-20) and pos scores are
+ * zero-padded to Bp (decoder_methods.cpp:103-111).                                                          */
+typedef struct mb_batch {
+    int decoder;      /* mb_decoder */
+    int64_t U, d, B, R;
+    int C, N;
+    const int64_t* edges;    /* [B,3] or [B,2] */
+    int edge_cols;           /* 3 or 2 */
+    const int64_t* dst_negs; /* [C,N] */
+    const int64_t* src_negs; /* [C,N] or NULL */
+    const float* rel;        /* [R,d] or NULL */
+    const float* inv_rel;    /* [R,d] or NULL */
+} mb_batch;
+
+/* Model::forward_lp -> node_corrupt_forward (nn/model.cpp:252-288, decoders/edge/decoder_methods.cpp:57-114):
+ * pos [Bp], neg [Bp,N], inv_pos [Bp], inv_neg [Bp,N] (inverse outputs may be NULL).                       */
+mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, float* pos, float* neg,
+                             float* inv_pos, float* inv_neg, void* stream);
+
+/* Model::train_batch for link prediction (nn/model.cpp:290-333) on batch-local tensors: forward_lp, SoftmaxCrossEntropy on
+ * both sides (nn/loss.cpp:50-67, model.cpp:309-312), backward, Batch::accumulateGradients (batch.cpp:62-79).
+ * Outputs (device; any may be NULL): loss [1]; grad [U,d] = d loss / d node_embeddings_;
+ * delta_e, delta_s [U,d] (node_gradients_, node_state_update_); rel_grad, inv_rel_grad [R,d] (overwritten).  */
+mb_status mb_train_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, const float* state, int64_t state_ld,
+                         float lr, int reduction, int precision, float* loss, float* grad, float* delta_e, float* delta_s, float* rel_grad,
+                         float* inv_rel_grad, void* stream);
+
+/* The whole per-batch path on a device-resident table (SynchronousTrainer::train loop body, pipeline/trainer.cpp:106-138
+ * == ComputeWorkerGPU::run, pipeline/pipeline_gpu.cpp:49-91):
+ *   loadGPUParameters (gather emb; the state row is read in place)  dataloader.cpp:529-548
+ *   Model::train_batch                                               model.cpp:290-333
+ *   updateEmbeddings(batch, gpu=true) (scatter-add emb + state)     dataloader.cpp:550-557
+ * `unique_ids` [U] are table rows (global ids for InMemory, buffer-local ids for the partition buffer).
+ * rel_grad / inv_rel_grad [R,d] receive the dense relation gradients (the reference's dense optimizer, nn/optim.cpp,
+ * consumes them; mb_dense_adagrad_step below is that optimizer).  loss [1] device.                       */
+mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, float* state_table, int64_t num_rows, int64_t ld,
+                        const int64_t* unique_ids, float lr, int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad,
+                        void* stream);
+
+/* Same call with HOST index buffers (pinned or pageable) -- what a reference-side caller holding a CPU Batch would pass
+ * (Batch::to, data/batch.cpp:21-60, moves exactly these tensors): copies unique_ids / edges / negatives to the device on
+ * `stream`, runs mb_train_step, copies the loss back into *loss_host and synchronises the stream.          */
+mb_status mb_train_step_host(mb_context* ctx, const mb_batch* host_batch, float* table, float* state_table, int64_t num_rows, int64_t ld,
+                             const int64_t* unique_ids_host, float lr, int reduction, int precision, float* loss_host, float* rel_grad,
+                             float* inv_rel_grad, void* stream);
+
+/* AdagradOptimizer::step on a dense parameter (nn/optim.cpp:114-145): state += g*g ; p -= lr * g / (sqrt(state) + eps) */
+mb_status mb_dense_adagrad_step(float* param, float* state_sum, const float* grad, int64_t n, float lr, float eps, void* stream);
+
+/* Diagnostic entry point for the contraction kernels (tests/, profiling): D[b] (MxN) = A[b] . B[b] over K, fp32 in/out.
+ * a_mn == 0: A is [batches][M][K]; a_mn == 1: A is [batches][K][M].  b_mn likewise with N.  block_n in {128, 256}. */
+mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* B, int b_mn, float* D, int M, int N, int K, int batches,
+                        int precision, int block_n, void* stream);
+
+/* bytes of device workspace a context currently holds (grows on demand, reused across batches) */
+size_t mb_workspace_bytes(const mb_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARIUS_B200_H_ */

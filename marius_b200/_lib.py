@@ -1,0 +1,69 @@
+"""ctypes binding of include/marius_b200.h (libmarius_b200.so).  There is NO fallback: if the CUDA library is
+missing this module raises at import, and every call raises MariusB200Error on a non-zero status."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmarius_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} not found: build it with `python -m marius_b200.build` (the hot path has no CPU/eager fallback)")
+
+lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+
+
+class MariusB200Error(RuntimeError):
+    """Non-zero mb_status.  MB_ERR_INVALID mirrors the reference's std::runtime_error on bad shapes (storage.cpp:607-610,652-655)."""
+
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"marius_b200 status {status}: {msg}")
+        self.status = status
+
+
+class mb_batch(C.Structure):
+    _fields_ = [("decoder", C.c_int), ("U", C.c_int64), ("d", C.c_int64), ("B", C.c_int64), ("R", C.c_int64), ("C", C.c_int), ("N", C.c_int),
+                ("edges", C.c_void_p), ("edge_cols", C.c_int), ("dst_negs", C.c_void_p), ("src_negs", C.c_void_p), ("rel", C.c_void_p),
+                ("inv_rel", C.c_void_p)]
+
+
+_vp, _i64, _i32, _f = C.c_void_p, C.c_int64, C.c_int, C.c_float
+_SIGS = {
+    "mb_create": [_i32, C.POINTER(_vp)],
+    "mb_gather_rows": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
+    "mb_scatter_add_rows": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
+    "mb_scatter_put_rows": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
+    "mb_global_to_local_map": [_vp, _i64, _i64, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _vp],
+    "mb_adagrad_deltas": [_vp, _vp, _i64, _i64, _i64, _f, _vp, _vp, _vp],
+    "mb_adagrad_update_rows": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _f, _vp],
+    "mb_map_tensors": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
+    "mb_decoder_forward": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
+    "mb_train_batch": [_vp, C.POINTER(mb_batch), _vp, _i64, _vp, _i64, _f, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mb_train_step": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
+    "mb_train_step_host": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
+    "mb_dense_adagrad_step": [_vp, _vp, _vp, _i64, _f, _f, _vp],
+    "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
+}
+EXPORTS = list(_SIGS) + ["mb_destroy", "mb_last_error", "mb_version", "mb_launch_count", "mb_build_info", "mb_workspace_bytes"]
+for _name, _args in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = C.c_int
+lib.mb_destroy.argtypes = [_vp]
+lib.mb_destroy.restype = None
+lib.mb_last_error.restype = C.c_char_p
+lib.mb_version.restype = C.c_int
+lib.mb_launch_count.restype = C.c_uint64
+lib.mb_build_info.restype = C.c_char_p
+lib.mb_workspace_bytes.argtypes = [_vp]
+lib.mb_workspace_bytes.restype = C.c_size_t
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise MariusB200Error(status, lib.mb_last_error().decode())
+
+
+def launch_count() -> int:
+    return int(lib.mb_launch_count())

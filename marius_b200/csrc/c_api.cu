@@ -1,0 +1,547 @@
+// c_api.cu -- the extern "C" boundary (include/marius_b200.h) and the per-batch orchestration of the hot path.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+
+namespace mb {
+
+static thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const std::string& msg) { g_error = msg; }
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        cached = prop.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached > 0 ? cached : 148;
+}
+
+// bump allocator over the context's workspace; run once with base == nullptr to size, once to place
+struct Arena {
+    char* base;
+    size_t off = 0;
+    explicit Arena(char* b) : base(b) {}
+    template <typename T>
+    T* take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+}  // namespace mb
+
+struct mb_context {
+    int device = 0;
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    // device staging for mb_train_step_host
+    int64_t* h_uniq = nullptr;
+    int64_t* h_edges = nullptr;
+    int64_t* h_dneg = nullptr;
+    int64_t* h_sneg = nullptr;
+    float* h_loss = nullptr;
+    size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
+};
+
+namespace mb {
+
+static mb_status ensure_ws(mb_context* ctx, size_t bytes, cudaStream_t st) {
+    if (bytes <= ctx->ws_bytes) return MB_OK;
+    MB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (ctx->ws) MB_CUDA_TRY(cudaFree(ctx->ws));
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+    size_t want = bytes + bytes / 8 + (1 << 20);
+    cudaError_t e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) {
+        set_error("workspace allocation of " + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+        return MB_ERR_NOMEM;
+    }
+    ctx->ws_bytes = want;
+    return MB_OK;
+}
+
+static int bits_for(uint64_t max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b) != 0) b++;
+    return b;
+}
+
+// Everything one batch needs, carved out of the workspace.
+struct Plan {
+    // dims
+    int64_t U, d, B, Bc, Bp, R, CN, n_slots;
+    int C, N, sides, cols;
+    bool has_rel, use_tc;
+    // buffers
+    float *emb_u, *A, *pos, *gpos, *row_loss, *NegE, *S, *dA, *gcat, *drel;
+    __nv_bfloat16 *A_hl, *Neg_hl, *G_hl;
+    uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *offsets, *hist;
+    uint32_t *rkeys_a, *rkeys_b, *rvals_a, *rvals_b, *roffsets, *rhist;
+
+    void layout(Arena& ar, bool need_emb_u, bool training, bool own_scores) {
+        emb_u = need_emb_u ? ar.take<float>(U * d) : nullptr;
+        A = ar.take<float>(sides * Bp * d);
+        pos = ar.take<float>(sides * Bp);
+        NegE = use_tc ? nullptr : ar.take<float>(sides * CN * d);
+        S = own_scores ? ar.take<float>(sides * Bp * N) : nullptr;
+        A_hl = use_tc ? ar.take<__nv_bfloat16>(2 * sides * Bp * d) : nullptr;
+        Neg_hl = use_tc ? ar.take<__nv_bfloat16>(2 * sides * CN * d) : nullptr;
+        gpos = row_loss = dA = gcat = drel = nullptr;
+        G_hl = nullptr;
+        keys_a = keys_b = vals_a = vals_b = offsets = hist = nullptr;
+        rkeys_a = rkeys_b = rvals_a = rvals_b = roffsets = rhist = nullptr;
+        if (training) {
+            gpos = ar.take<float>(sides * Bp);
+            row_loss = ar.take<float>(sides * Bp);
+            dA = ar.take<float>(sides * Bp * d);
+            gcat = ar.take<float>(n_slots * d);
+            G_hl = use_tc ? ar.take<__nv_bfloat16>(2 * sides * Bp * N) : nullptr;
+            keys_a = ar.take<uint32_t>(n_slots);
+            keys_b = ar.take<uint32_t>(n_slots);
+            vals_a = ar.take<uint32_t>(n_slots);
+            vals_b = ar.take<uint32_t>(n_slots);
+            offsets = ar.take<uint32_t>(U + 2);
+            hist = reinterpret_cast<uint32_t*>(ar.take<char>(sort_scratch_bytes(n_slots)));
+            if (has_rel) {
+                drel = ar.take<float>(sides * B * d);
+                rkeys_a = ar.take<uint32_t>(B);
+                rkeys_b = ar.take<uint32_t>(B);
+                rvals_a = ar.take<uint32_t>(B);
+                rvals_b = ar.take<uint32_t>(B);
+                roffsets = ar.take<uint32_t>(R + 2);
+                rhist = reinterpret_cast<uint32_t*>(ar.take<char>(sort_scratch_bytes(B)));
+            }
+        }
+    }
+};
+
+static mb_status validate_batch(const mb_batch* b) {
+    MB_REQUIRE(b != nullptr, "batch is null");
+    MB_REQUIRE(b->decoder >= MB_DECODER_DOT && b->decoder <= MB_DECODER_COMPLEX, "unknown decoder kind");
+    MB_REQUIRE(b->U >= 0 && b->d > 0 && b->B >= 0 && b->C > 0 && b->N > 0, "bad batch dimensions");
+    MB_REQUIRE(b->edge_cols == 2 || b->edge_cols == 3, "Edge list must be a 3 or 2 column tensor");  // decoder_methods.cpp:66-72
+    MB_REQUIRE(b->edges != nullptr || b->B == 0, "edges is null");
+    MB_REQUIRE(b->dst_negs != nullptr, "dst_negs is null");
+    if (b->decoder != MB_DECODER_DOT && b->edge_cols == 3) MB_REQUIRE(b->rel != nullptr && b->R > 0, "relations required for DistMult/ComplEx");
+    if (b->decoder == MB_DECODER_COMPLEX) MB_REQUIRE(b->d % 2 == 0, "ComplEx needs an even embedding dimension");
+    MB_REQUIRE(b->U < ((int64_t)1 << 31), "U too large");
+    return MB_OK;
+}
+
+static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
+    p.U = b->U;
+    p.d = b->d;
+    p.B = b->B;
+    p.C = b->C;
+    p.N = b->N;
+    p.R = b->R;
+    p.cols = b->edge_cols;
+    p.Bc = (b->B + b->C - 1) / b->C;  // ceil(B / C)   comparators.cpp:9
+    if (p.Bc == 0) p.Bc = 0;
+    p.Bp = p.Bc * b->C;
+    p.CN = (int64_t)b->C * b->N;
+    p.has_rel = (b->edge_cols == 3) && (b->decoder != MB_DECODER_DOT) && b->rel != nullptr;
+    p.sides = (p.has_rel && b->inv_rel != nullptr && b->src_negs != nullptr) ? 2 : 1;  // use_inverse_relations_ (decoder_methods.cpp:90)
+    p.n_slots = 2 * p.B + 2 * p.CN;
+    p.use_tc = (precision != MB_PREC_FP32) && gemm_tc_supported(p.d, p.N) && p.Bc > 0;
+}
+
+// forward: A, pos, negative rows, scores.  S0/S1 are the score outputs per side ([Bp,N] each).
+static mb_status run_forward(const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, int precision, float* pos0, float* pos1, float* S0,
+                             float* S1, bool uniform_S, cudaStream_t st) {
+    const int d = (int)p.d;
+    float* A0 = p.A;
+    float* A1 = p.sides == 2 ? p.A + p.Bp * d : nullptr;
+    __nv_bfloat16 *A0_hi = nullptr, *A0_lo = nullptr, *A1_hi = nullptr, *A1_lo = nullptr;
+    const int64_t a_half = p.sides * p.Bp * d;  // hi block then lo block, each [sides][Bp][d]
+    if (p.use_tc) {
+        A0_hi = p.A_hl;
+        A0_lo = p.A_hl + a_half;
+        if (p.sides == 2) {
+            A1_hi = A0_hi + p.Bp * d;
+            A1_lo = A0_lo + p.Bp * d;
+        }
+    }
+    MB_TRY(launch_edge_prep(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, A0, A1, pos0,
+                            p.sides == 2 ? pos1 : nullptr, A0_hi, A0_lo, A1_hi, A1_lo, st));
+    const int64_t n_half = p.sides * p.CN * d;
+    for (int s = 0; s < p.sides; s++) {
+        const int64_t* negs = s == 0 ? b->dst_negs : b->src_negs;
+        float* out = p.use_tc ? nullptr : p.NegE + s * p.CN * d;
+        void* hi = p.use_tc ? (void*)(p.Neg_hl + s * p.CN * d) : nullptr;
+        void* lo = p.use_tc ? (void*)(p.Neg_hl + n_half + s * p.CN * d) : nullptr;
+        MB_TRY(launch_gather_split(emb, emb_ld, negs, p.CN, d, out, hi, lo, st));
+    }
+    if (p.Bc == 0) return MB_OK;
+    const int passes = precision == MB_PREC_BF16 ? 1 : 3;
+    // scores[side][chunk] = A[side][chunk] . Neg[side][chunk]^T     (comparators.cpp:69-72)
+    int launches = uniform_S ? 1 : p.sides;
+    for (int l = 0; l < launches; l++) {
+        int batches = uniform_S ? p.sides * p.C : p.C;
+        float* S = l == 0 ? S0 : S1;
+        int64_t aoff = (int64_t)l * p.Bp * d, noff = (int64_t)l * p.CN * d;
+        if (p.use_tc) {
+            MB_TRY(gemm_tc(p.A_hl + aoff, p.A_hl + a_half + aoff, d, p.Bc * d, false, p.Neg_hl + noff, p.Neg_hl + n_half + noff, d, (int64_t)p.N * d,
+                           false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, 256, st));
+        } else {
+            MB_TRY(gemm_simt(p.A + aoff, d, 1, p.Bc * d, p.NegE + noff, 1, d, (int64_t)p.N * d, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, st));
+        }
+    }
+    return MB_OK;
+}
+
+enum class UpdateMode { kBatchLocal, kFusedTable };
+
+static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_in, int64_t emb_ld, const float* state, int64_t state_ld, float* table,
+                           float* state_table, int64_t ld, const int64_t* unique_ids, float lr, int reduction, int precision, float* loss,
+                           float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad, UpdateMode mode, cudaStream_t st) {
+    MB_TRY(validate_batch(b));
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
+    Plan p;
+    fill_plan_dims(p, b, precision);
+    const bool fused = mode == UpdateMode::kFusedTable;
+    {
+        Arena sizing(nullptr);
+        p.layout(sizing, fused, true, true);
+        MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+        Arena place(ctx->ws);
+        p.layout(place, fused, true, true);
+    }
+    const int d = (int)p.d;
+    const float* emb = emb_in;
+    if (fused) {
+        // DataLoader::loadGPUParameters (dataloader.cpp:529-548): gather the unique rows; the state rows are read in place later
+        MB_TRY(gather_rows(table, ld, d, unique_ids, p.U, p.emb_u, d, st));
+        emb = p.emb_u;
+        emb_ld = d;
+    }
+    // duplicate-accumulation plan: sort gradient slots by batch-local node id
+    uint32_t *skeys = nullptr, *svals = nullptr;
+    MB_TRY(launch_slot_keys(b->edges, p.cols, p.B, b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, p.CN, p.keys_a, st));
+    MB_TRY(radix_sort_pairs<uint32_t>(p.keys_a, p.keys_b, p.vals_a, p.vals_b, p.n_slots, p.sides == 2 ? bits_for((uint64_t)std::max<int64_t>(p.U, 1)) : 32,
+                                      p.hist, &skeys, &svals, st));
+    MB_TRY(segment_offsets_u32(skeys, p.n_slots, p.U, p.offsets, st));
+
+    float* pos0 = p.pos;
+    float* pos1 = p.pos + p.Bp;
+    MB_TRY(run_forward(p, b, emb, emb_ld, precision, pos0, pos1, p.S, p.S + p.Bp * p.N, true, st));
+
+    // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
+    const int64_t rows = p.sides * p.Bp;
+    const float w = reduction == MB_REDUCTION_SUM ? 1.0f : (p.Bp > 0 ? 1.0f / (float)p.Bp : 0.f);
+    const int64_t g_half = p.sides * p.Bp * p.N;
+    if (rows > 0) {
+        MB_TRY(launch_loss_grad(p.S, p.pos, p.gpos, p.row_loss, p.use_tc ? (void*)p.G_hl : nullptr, p.use_tc ? (void*)(p.G_hl + g_half) : nullptr, rows,
+                                p.N, w, st));
+    }
+    if (loss) {
+        if (rows > 0)
+            MB_TRY(launch_loss_reduce(p.row_loss, rows, loss, st));
+        else
+            MB_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    }
+    const int passes = precision == MB_PREC_BF16 ? 1 : 3;
+    const int batches = p.sides * p.C;
+    float* gneg = p.gcat + 2 * p.B * d;  // d dst_negs | d src_negs, [sides][C][N][d]
+    if (p.Bc > 0) {
+        const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
+        if (p.use_tc) {
+            // dA = G . Neg   ;   dNeg = G^T . A
+            MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, false, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, true, p.dA, d, p.Bc * d,
+                           (int)p.Bc, d, p.N, batches, passes, 256, st));
+            MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, true, p.A_hl, p.A_hl + a_half, d, p.Bc * d, true, gneg, d, (int64_t)p.N * d, p.N, d,
+                           (int)p.Bc, batches, passes, 256, st));
+        } else {
+            MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
+            MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, st));
+        }
+    } else {
+        MB_CUDA_TRY(cudaMemsetAsync(gneg, 0, sizeof(float) * 2 * p.CN * d, st));
+    }
+    if (p.sides == 1) {
+        // no inverse side: the src_negs slots carry key 0xffffffff and are never reduced
+    }
+    MB_TRY(launch_edge_backward(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, d, b->decoder, p.A,
+                                p.sides == 2 ? p.A + p.Bp * d : nullptr, p.dA, p.sides == 2 ? p.dA + p.Bp * d : nullptr, p.gpos,
+                                p.sides == 2 ? p.gpos + p.Bp : nullptr, p.gcat, p.has_rel ? p.drel : nullptr,
+                                (p.has_rel && p.sides == 2) ? p.drel + p.B * d : nullptr, st));
+    // node gradients: segmented sum over sorted slots (+ Adagrad)
+    if (fused) {
+        MB_TRY(launch_segment_reduce(2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr,
+                                     st));
+    } else if (delta_e != nullptr || delta_s != nullptr) {
+        MB_REQUIRE(state != nullptr && delta_e != nullptr && delta_s != nullptr, "delta_e/delta_s need state and both outputs");
+        MB_TRY(launch_segment_reduce(1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
+    } else if (grad != nullptr) {
+        MB_TRY(launch_segment_reduce(0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
+    }
+    // relation gradients: segmented sum of per-edge gradients by relation id
+    if (p.has_rel && (rel_grad != nullptr || inv_rel_grad != nullptr) && p.R > 0) {
+        uint32_t *rk = nullptr, *rv = nullptr;
+        MB_TRY(launch_rel_keys(b->edges, p.cols, p.B, p.rkeys_a, st));
+        MB_TRY(radix_sort_pairs<uint32_t>(p.rkeys_a, p.rkeys_b, p.rvals_a, p.rvals_b, p.B, bits_for((uint64_t)p.R), p.rhist, &rk, &rv, st));
+        MB_TRY(segment_offsets_u32(rk, p.B, p.R, p.roffsets, st));
+        if (rel_grad)
+            MB_TRY(launch_segment_reduce(0, p.drel, rv, p.roffsets, p.R, d, rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
+        if (inv_rel_grad && p.sides == 2)
+            MB_TRY(launch_segment_reduce(0, p.drel + p.B * d, rv, p.roffsets, p.R, d, inv_rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0,
+                                         nullptr, lr, st));
+    }
+    return MB_OK;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+const char* mb_last_error(void) { return g_error.c_str(); }
+int mb_version(void) { return MB_VERSION; }
+uint64_t mb_launch_count(void) { return g_launches.load(); }
+const char* mb_build_info(void) { return "sm_100a tcgen05+TMA (bf16x3 split GEMM), fp32 SIMT fallback"; }
+
+mb_status mb_create(int device, mb_context** out) {
+    MB_REQUIRE(out != nullptr, "out is null");
+    int count = 0;
+    MB_CUDA_TRY(cudaGetDeviceCount(&count));
+    if (count <= 0) {
+        set_error("no CUDA device: the marius_b200 hot path has no CPU fallback");
+        return MB_ERR_CUDA;
+    }
+    MB_REQUIRE(device >= 0 && device < count, "device out of range");
+    MB_CUDA_TRY(cudaSetDevice(device));
+    mb_context* c = new mb_context();
+    c->device = device;
+    cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
+    if (e != cudaSuccess) {
+        delete c;
+        set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        return MB_ERR_CUDA;
+    }
+    *out = c;
+    return MB_OK;
+}
+
+void mb_destroy(mb_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->h_uniq) cudaFree(ctx->h_uniq);
+    if (ctx->h_edges) cudaFree(ctx->h_edges);
+    if (ctx->h_dneg) cudaFree(ctx->h_dneg);
+    if (ctx->h_sneg) cudaFree(ctx->h_sneg);
+    if (ctx->h_loss) cudaFree(ctx->h_loss);
+    delete ctx;
+}
+
+size_t mb_workspace_bytes(const mb_context* ctx) { return ctx ? ctx->ws_bytes : 0; }
+
+mb_status mb_gather_rows(const float* table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n, float* out, int64_t out_ld,
+                         void* stream) {
+    MB_REQUIRE(n >= 0 && d >= 0 && num_rows >= 0, "negative size");
+    MB_REQUIRE(n == 0 || (table && idx && out), "null pointer");
+    MB_REQUIRE(ld >= d && out_ld >= d, "leading dimension smaller than row length");
+    return gather_rows(table, ld, d, idx, n, out, out_ld, (cudaStream_t)stream);
+}
+
+mb_status mb_scatter_add_rows(float* table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n, const float* vals, int64_t vals_ld,
+                              void* stream) {
+    MB_REQUIRE(n >= 0 && d >= 0 && num_rows >= 0, "negative size");
+    MB_REQUIRE(n == 0 || (table && idx && vals), "null pointer");  // storage.cpp:652-655 (!values.defined())
+    MB_REQUIRE(ld >= d && vals_ld >= d, "leading dimension smaller than row length");
+    return scatter_rows(table, ld, d, idx, n, vals, vals_ld, true, (cudaStream_t)stream);
+}
+
+mb_status mb_scatter_put_rows(float* table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n, const float* vals, int64_t vals_ld,
+                              void* stream) {
+    MB_REQUIRE(n >= 0 && d >= 0 && num_rows >= 0, "negative size");
+    MB_REQUIRE(n == 0 || (table && idx && vals), "null pointer");
+    MB_REQUIRE(ld >= d && vals_ld >= d, "leading dimension smaller than row length");
+    return scatter_rows(table, ld, d, idx, n, vals, vals_ld, false, (cudaStream_t)stream);
+}
+
+mb_status mb_global_to_local_map(int64_t* map, int64_t total_rows, int64_t partition_size, const int32_t* partition_ids, const int32_t* buffer_slots,
+                                 int n_resident, void* stream) {
+    MB_REQUIRE(map != nullptr && total_rows >= 0 && partition_size > 0 && n_resident >= 0, "bad arguments");
+    MB_REQUIRE(n_resident == 0 || (partition_ids && buffer_slots), "null pointer");
+    return global_to_local_map(map, total_rows, partition_size, partition_ids, buffer_slots, n_resident, (cudaStream_t)stream);
+}
+
+mb_status mb_adagrad_deltas(const float* grad, const float* state, int64_t n, int64_t d, int64_t ld, float lr, float* delta_e, float* delta_s,
+                            void* stream) {
+    MB_REQUIRE(n >= 0 && d >= 0 && ld >= d, "bad sizes");
+    MB_REQUIRE(n == 0 || (grad && state && delta_e && delta_s), "null pointer");
+    return adagrad_deltas(grad, state, n, d, ld, lr, delta_e, delta_s, (cudaStream_t)stream);
+}
+
+mb_status mb_adagrad_update_rows(float* table, float* state_table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n,
+                                 const float* grad, int64_t grad_ld, float lr, void* stream) {
+    MB_REQUIRE(n >= 0 && d >= 0 && num_rows >= 0 && ld >= d && grad_ld >= d, "bad sizes");
+    MB_REQUIRE(n == 0 || (table && state_table && idx && grad), "null pointer");
+    return adagrad_update_rows(table, state_table, ld, d, idx, n, grad, grad_ld, lr, (cudaStream_t)stream);
+}
+
+mb_status mb_dense_adagrad_step(float* param, float* state_sum, const float* grad, int64_t n, float lr, float eps, void* stream) {
+    MB_REQUIRE(n >= 0 && (n == 0 || (param && state_sum && grad)), "bad arguments");
+    return dense_adagrad_step(param, state_sum, grad, n, lr, eps, (cudaStream_t)stream);
+}
+
+mb_status mb_map_tensors(mb_context* ctx, const int64_t* all_ids, int64_t n, int64_t max_id, int64_t* unique_out, int64_t* mapped_out,
+                         int64_t* num_unique_dev, void* stream) {
+    MB_REQUIRE(ctx != nullptr && n >= 0 && max_id >= 0, "bad arguments");
+    MB_REQUIRE(n == 0 || (all_ids && unique_out && mapped_out), "null pointer");
+    MB_REQUIRE(num_unique_dev != nullptr, "num_unique_dev is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    Arena sizing(nullptr);
+    auto lay = [&](Arena& ar, uint64_t*& ka, uint64_t*& kb, uint32_t*& va, uint32_t*& vb, uint32_t*& flags, uint32_t*& hist, uint32_t*& total) {
+        ka = ar.take<uint64_t>(n);
+        kb = ar.take<uint64_t>(n);
+        va = ar.take<uint32_t>(n);
+        vb = ar.take<uint32_t>(n);
+        flags = ar.take<uint32_t>(n + 1);
+        hist = reinterpret_cast<uint32_t*>(ar.take<char>(sort_scratch_bytes(n)));
+        total = ar.take<uint32_t>(1);
+    };
+    uint64_t *ka, *kb;
+    uint32_t *va, *vb, *flags, *hist, *total;
+    lay(sizing, ka, kb, va, vb, flags, hist, total);
+    MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+    Arena place(ctx->ws);
+    lay(place, ka, kb, va, vb, flags, hist, total);
+    return map_tensors_device(all_ids, n, bits_for((uint64_t)max_id), ka, kb, va, vb, flags, hist, total, unique_out, mapped_out, num_unique_dev, st);
+}
+
+mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, float* pos, float* neg,
+                             float* inv_pos, float* inv_neg, void* stream) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    MB_TRY(validate_batch(batch));
+    MB_REQUIRE(emb != nullptr && pos != nullptr && neg != nullptr, "UndefinedTensor");  // comparators.cpp:63-65
+    MB_REQUIRE(emb_ld >= batch->d, "emb_ld < d");
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    Plan p;
+    fill_plan_dims(p, batch, precision);
+    if (p.sides == 2) MB_REQUIRE(inv_pos != nullptr && inv_neg != nullptr, "inverse outputs required when inverse relations are used");
+    {
+        Arena sizing(nullptr);
+        p.layout(sizing, false, false, false);
+        MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+        Arena place(ctx->ws);
+        p.layout(place, false, false, false);
+    }
+    return run_forward(p, batch, emb, emb_ld, precision, pos, inv_pos, neg, inv_neg, false, st);
+}
+
+mb_status mb_train_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, const float* state, int64_t state_ld, float lr,
+                         int reduction, int precision, float* loss, float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad,
+                         void* stream) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    MB_REQUIRE(emb != nullptr, "UndefinedTensor: node embeddings");
+    MB_REQUIRE(batch == nullptr || emb_ld >= batch->d, "emb_ld < d");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return run_train(ctx, batch, emb, emb_ld, state, state_ld, nullptr, nullptr, 0, nullptr, lr, reduction, precision, loss, grad, delta_e, delta_s,
+                     rel_grad, inv_rel_grad, UpdateMode::kBatchLocal, (cudaStream_t)stream);
+}
+
+mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, float* state_table, int64_t num_rows, int64_t ld,
+                        const int64_t* unique_ids, float lr, int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad,
+                        void* stream) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    MB_REQUIRE(table != nullptr && state_table != nullptr && unique_ids != nullptr, "null table / ids");
+    MB_REQUIRE(batch == nullptr || ld >= batch->d, "ld < d");
+    MB_REQUIRE(num_rows >= 0, "num_rows < 0");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return run_train(ctx, batch, nullptr, 0, nullptr, 0, table, state_table, ld, unique_ids, lr, reduction, precision, loss, nullptr, nullptr, nullptr,
+                     rel_grad, inv_rel_grad, UpdateMode::kFusedTable, (cudaStream_t)stream);
+}
+
+// Diagnostic: D[b] = A[b] . B[b] over K through the contraction kernels, fp32 in / fp32 out.
+//   a_mn == 0: A is [batches][M][K] (K contiguous)      a_mn == 1: A is [batches][K][M]
+//   b_mn == 0: B is [batches][N][K]                     b_mn == 1: B is [batches][K][N]
+mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* B, int b_mn, float* D, int M, int N, int K, int batches, int precision,
+                        int block_n, void* stream) {
+    MB_REQUIRE(ctx && A && B && D && M > 0 && N > 0 && K > 0 && batches > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const int64_t na = (int64_t)batches * M * K, nb = (int64_t)batches * N * K;
+    if (precision == MB_PREC_FP32) {
+        return gemm_simt(A, a_mn ? 1 : K, a_mn ? M : 1, (int64_t)M * K, B, b_mn ? N : 1, b_mn ? 1 : K, (int64_t)N * K, D, N, (int64_t)M * N, M, N, K,
+                         batches, st);
+    }
+    MB_REQUIRE(gemm_tc_supported(a_mn ? M : K, b_mn ? N : K), "tcgen05 path needs inner extents that are multiples of 8");
+    Arena sizing(nullptr);
+    sizing.take<__nv_bfloat16>(2 * na);
+    sizing.take<__nv_bfloat16>(2 * nb);
+    MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+    Arena place(ctx->ws);
+    __nv_bfloat16* a_hl = place.take<__nv_bfloat16>(2 * na);
+    __nv_bfloat16* b_hl = place.take<__nv_bfloat16>(2 * nb);
+    MB_TRY(launch_split(A, na, a_hl, a_hl + na, st));
+    MB_TRY(launch_split(B, nb, b_hl, b_hl + nb, st));
+    return gemm_tc(a_hl, a_hl + na, a_mn ? M : K, (int64_t)M * K, a_mn != 0, b_hl, b_hl + nb, b_mn ? N : K, (int64_t)N * K, b_mn != 0, D, N,
+                   (int64_t)M * N, M, N, K, batches, precision == MB_PREC_BF16 ? 1 : 3, block_n, st);
+}
+
+static mb_status grow_i64(int64_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return MB_OK;
+    if (*p) MB_CUDA_TRY(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4 + 1024;
+    MB_CUDA_TRY(cudaMalloc(p, want * sizeof(int64_t)));
+    *cap = want;
+    return MB_OK;
+}
+
+mb_status mb_train_step_host(mb_context* ctx, const mb_batch* hb, float* table, float* state_table, int64_t num_rows, int64_t ld,
+                             const int64_t* unique_ids_host, float lr, int reduction, int precision, float* loss_host, float* rel_grad,
+                             float* inv_rel_grad, void* stream) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    MB_TRY(validate_batch(hb));
+    MB_REQUIRE(unique_ids_host != nullptr, "unique ids are null");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t n_e = (size_t)hb->B * hb->edge_cols, n_n = (size_t)hb->C * hb->N;
+    MB_CUDA_TRY(cudaStreamSynchronize(st));  // staging buffers may still be in use by the previous step on this stream
+    MB_TRY(grow_i64(&ctx->h_uniq, &ctx->h_uniq_cap, (size_t)hb->U));
+    MB_TRY(grow_i64(&ctx->h_edges, &ctx->h_edges_cap, n_e));
+    MB_TRY(grow_i64(&ctx->h_dneg, &ctx->h_dneg_cap, n_n));
+    MB_TRY(grow_i64(&ctx->h_sneg, &ctx->h_sneg_cap, n_n));
+    // Batch::to (batch.cpp:21-60): the index tensors of the batch go host -> device on the compute stream
+    MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_uniq, unique_ids_host, sizeof(int64_t) * hb->U, cudaMemcpyHostToDevice, st));
+    MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_edges, hb->edges, sizeof(int64_t) * n_e, cudaMemcpyHostToDevice, st));
+    MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_dneg, hb->dst_negs, sizeof(int64_t) * n_n, cudaMemcpyHostToDevice, st));
+    if (hb->src_negs) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_sneg, hb->src_negs, sizeof(int64_t) * n_n, cudaMemcpyHostToDevice, st));
+    mb_batch db = *hb;
+    db.edges = ctx->h_edges;
+    db.dst_negs = ctx->h_dneg;
+    db.src_negs = hb->src_negs ? ctx->h_sneg : nullptr;
+    MB_TRY(run_train(ctx, &db, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->h_uniq, lr, reduction, precision, ctx->h_loss, nullptr, nullptr,
+                     nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st));
+    if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(loss_host, ctx->h_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    MB_CUDA_TRY(cudaStreamSynchronize(st));
+    (void)num_rows;
+    return MB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,469 @@
+// gemm_tc.cu -- tcgen05 (5th-gen tensor core) batched GEMM for the only dense contraction on the Marius hot path:
+//   scores  S  = A . Neg^T     (DotCompare bmm, comparators.cpp:69-72)          A K-major,  B K-major
+//   dA         = G . Neg       (bmm backward w.r.t. the adjusted positives)     A K-major,  B MN-major
+//   dNeg       = G^T . A       (bmm backward w.r.t. the negative rows)          A MN-major, B MN-major
+// fp32 semantics on a bf16 tensor pipe: every fp32 operand x is pre-split into bf16 hi = rn(x), lo = rn(x - hi) and the
+// kernel accumulates  hi.hi + hi.lo + lo.hi  into one fp32 TMEM accumulator (3 UMMA products per k-step, |rel err| ~ 2^-16;
+// the dropped lo.lo term is ~2^-18).  MB_PREC_BF16 issues only hi.hi.
+//
+// Structure (one CTA per SM, persistent over output tiles, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor (3-D maps: inner, rows, batch) -> SWIZZLE_128B smem tiles, mbarrier tx-count
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BLOCK_N, K=16), tcgen05.commit -> mbarriers
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (each warp owns its TMEM lane quarter) -> registers -> fp32 rows in global
+//   two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+// OOB handling is TMA zero fill: ragged M / N / K tiles need no special cases in the MMA loop (zero rows/columns contribute 0).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                      // bf16 elements = one 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int kTcThreads = 192;
+constexpr long long kWaitTimeoutCycles = 4000000000ll;  // ~2 s: trap instead of hanging the GPU
+
+struct TcParams {
+    float* D;
+    int64_t ldd;      // elements
+    int64_t sDb;      // batch stride (elements)
+    int M, N, K, batches;
+    int passes;       // 1 (hi.hi) or 3 (hi.hi + hi.lo + lo.hi)
+    int m_tiles, n_tiles;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > kWaitTimeoutCycles) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ----------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (InstrDescriptor): c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), a_major [15], b_major [16],
+// N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+    static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
+               const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered fp32 accumulator: 256 or 512 columns (power of two)
+    static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_holder = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int tiles_per_batch = p.m_tiles * p.n_tiles;
+    const int num_tiles = tiles_per_batch * p.batches;
+    const uint32_t stage_tx = (uint32_t)((p.passes == 3 ? 2 : 1) * (A_TILE_BYTES + L::B_TILE_BYTES));
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi);
+        prefetch_tmap(&tmB_hi);
+        if (p.passes == 3) {
+            prefetch_tmap(&tmA_lo);
+            prefetch_tmap(&tmB_lo);
+        }
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<TMEM_COLS>(tmem_holder);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int b = t / tiles_per_batch;
+                const int rem = t - b * tiles_per_batch;
+                const int m0 = (rem / p.n_tiles) * BLOCK_M;
+                const int n0 = (rem % p.n_tiles) * BLOCK_N;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA_hi = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
+                    const uint32_t sB_hi = sA_lo + A_TILE_BYTES;
+                    const uint32_t sB_lo = sB_hi + L::B_TILE_BYTES;
+                    mbar_expect_tx(full_bar(stage), stage_tx);
+                    const int k0 = kb * BLOCK_K;
+                    if (!A_MN) {
+                        tma_load_3d(sA_hi, &tmA_hi, full_bar(stage), k0, m0, b);
+                        if (p.passes == 3) tma_load_3d(sA_lo, &tmA_lo, full_bar(stage), k0, m0, b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 64; j++) {
+                            tma_load_3d(sA_hi + j * (BLOCK_K * 128), &tmA_hi, full_bar(stage), m0 + 64 * j, k0, b);
+                            if (p.passes == 3) tma_load_3d(sA_lo + j * (BLOCK_K * 128), &tmA_lo, full_bar(stage), m0 + 64 * j, k0, b);
+                        }
+                    }
+                    if (!B_MN) {
+                        tma_load_3d(sB_hi, &tmB_hi, full_bar(stage), k0, n0, b);
+                        if (p.passes == 3) tma_load_3d(sB_lo, &tmB_lo, full_bar(stage), k0, n0, b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_N / 64; j++) {
+                            tma_load_3d(sB_hi + j * (BLOCK_K * 128), &tmB_hi, full_bar(stage), n0 + 64 * j, k0, b);
+                            if (p.passes == 3) tma_load_3d(sB_lo + j * (BLOCK_K * 128), &tmB_lo, full_bar(stage), n0 + 64 * j, k0, b);
+                        }
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused (=16 B); k-step = +32 B inside the swizzle span.
+            // MN-major SW128: 64-element MN slabs BLOCK_K*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO); k-step = +2048 B.
+            constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16, A_SBO = 1024, A_KSTEP = A_MN ? 2048 : 32;
+            constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16, B_SBO = 1024, B_KSTEP = B_MN ? 2048 : 32;
+            int stage = 0;
+            uint32_t phase = 0;
+            int local_tile = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, local_tile++) {
+                const int buf = local_tile & 1;
+                const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
+                // ragged last N tile: shrink the instruction's N (multiple of 16) so no tensor cycles are spent on zero columns
+                const int n0 = ((t % tiles_per_batch) % p.n_tiles) * BLOCK_N;
+                const int n_eff = min(BLOCK_N, ((p.N - n0 + 15) / 16) * 16);
+                const uint32_t idesc = make_idesc(BLOCK_M, n_eff, A_MN, B_MN);
+                mbar_wait(tempty_bar(buf), buf_phase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BLOCK_N);
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sA_hi = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
+                    const uint32_t sB_hi = sA_lo + A_TILE_BYTES;
+                    const uint32_t sB_lo = sB_hi + L::B_TILE_BYTES;
+                    const int k_valid = min(BLOCK_K, p.K - kb * BLOCK_K);
+                    const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
+                    for (int prod = 0; prod < p.passes; prod++) {
+                        const uint32_t sa = (prod == 2) ? sA_lo : sA_hi;  // hi.hi, hi.lo, lo.hi
+                        const uint32_t sb = (prod == 1) ? sB_lo : sB_hi;
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            uint64_t adesc = make_smem_desc(sa + ks * A_KSTEP, A_LBO, A_SBO);
+                            uint64_t bdesc = make_smem_desc(sb + ks * B_KSTEP, B_LBO, B_SBO);
+                            umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ================= epilogue warps 2..5 =================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int local_tile = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, local_tile++) {
+            const int buf = local_tile & 1;
+            const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
+            const int b = t / tiles_per_batch;
+            const int rem = t - b * tiles_per_batch;
+            const int m0 = (rem / p.n_tiles) * BLOCK_M;
+            const int n0 = (rem % p.n_tiles) * BLOCK_N;
+            mbar_wait(tfull_bar(buf), buf_phase);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            float* drow = p.D + (int64_t)b * p.sDb + (int64_t)row * p.ldd;
+            const bool row_ok = row < p.M;
+            const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15u) == 0) && ((p.sDb & 3) == 0);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; c++) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), r);
+                tmem_ld_wait();
+                if (row_ok) {
+                    if (vec_ok && col0 + 32 <= p.N) {
+                        float4* dst = reinterpret_cast<float4*>(drow + col0);
+#pragma unroll
+                        for (int v = 0; v < 8; v++)
+                            dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                                 __uint_as_float(r[4 * v + 3]));
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 32; v++)
+                            if (col0 + v < p.N) drow[col0 + v] = __uint_as_float(r[v]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---- host side: tensor maps -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 3-D bf16 map: dims {inner, rows, batches}; box {64, box_rows, 1}; SWIZZLE_128B; zero OOB fill.
+mb_status make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches, uint64_t row_stride_elems,
+                   uint64_t batch_stride_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return MB_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {inner, rows, batches};
+    cuuint64_t strides[2] = {row_stride_elems * 2, batch_stride_elems * 2};
+    if (batches == 1) strides[1] = strides[0] * rows;
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (strides[0] & 15u) || (strides[1] & 15u)) {
+        set_error("gemm_tc: operand not 16-byte aligned / stride not a multiple of 16 bytes");
+        return MB_ERR_INVALID;
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return MB_ERR_CUDA;
+    }
+    return MB_OK;
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+mb_status launch_variant(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p,
+                         cudaStream_t st) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    int tiles = p.m_tiles * p.n_tiles * p.batches;
+    int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, kTcThreads, L::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int64_t a_inner, int64_t b_inner) {
+    // TMA: 16-byte global strides => inner extents (bf16) multiples of 8
+    return (a_inner % 8 == 0) && (b_inner % 8 == 0) && get_encode_fn() != nullptr;
+}
+
+// D[b] (M x N, fp32, ld = ldd) = A[b] . B[b]^T-like contraction over K with bf16 hi/lo operands.
+//   a_mn == false : A stored [batch][M][K] (K contiguous, row stride lda)   a_mn == true : stored [batch][K][M] (M contiguous)
+//   b_mn == false : B stored [batch][N][K]                                  b_mn == true : stored [batch][K][N]
+mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int64_t sBb,
+                  bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, int block_n, cudaStream_t st) {
+    if (M == 0 || N == 0 || batches == 0) return MB_OK;
+    if (K == 0) {
+        set_error("gemm_tc: K == 0");
+        return MB_ERR_INVALID;
+    }
+    if (!A_lo || !B_lo) passes = 1;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    const uint32_t bn = (uint32_t)block_n;
+    if (!a_mn) {
+        MB_TRY(make_map(&ma_hi, A_hi, K, M, batches, lda, sAb, BLOCK_M));
+        if (passes == 3) MB_TRY(make_map(&ma_lo, A_lo, K, M, batches, lda, sAb, BLOCK_M));
+    } else {
+        MB_TRY(make_map(&ma_hi, A_hi, M, K, batches, lda, sAb, BLOCK_K));
+        if (passes == 3) MB_TRY(make_map(&ma_lo, A_lo, M, K, batches, lda, sAb, BLOCK_K));
+    }
+    if (!b_mn) {
+        MB_TRY(make_map(&mb_hi, B_hi, K, N, batches, ldb, sBb, bn));
+        if (passes == 3) MB_TRY(make_map(&mb_lo, B_lo, K, N, batches, ldb, sBb, bn));
+    } else {
+        MB_TRY(make_map(&mb_hi, B_hi, N, K, batches, ldb, sBb, BLOCK_K));
+        if (passes == 3) MB_TRY(make_map(&mb_lo, B_lo, N, K, batches, ldb, sBb, BLOCK_K));
+    }
+    if (passes != 3) {
+        ma_lo = ma_hi;
+        mb_lo = mb_hi;
+    }
+    TcParams p;
+    p.D = D;
+    p.ldd = ldd;
+    p.sDb = sDb;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.batches = batches;
+    p.passes = passes;
+    p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = (N + block_n - 1) / block_n;
+#define MB_TC_DISPATCH(BN, ST)                                                                          \
+    if (!a_mn && !b_mn) return launch_variant<BN, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st); \
+    if (!a_mn && b_mn) return launch_variant<BN, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);   \
+    if (a_mn && b_mn) return launch_variant<BN, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);     \
+    return launch_variant<BN, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
+    if (block_n == 256) {
+        MB_TC_DISPATCH(256, 2)
+    } else if (block_n == 128) {
+        MB_TC_DISPATCH(128, 3)
+    }
+#undef MB_TC_DISPATCH
+    set_error("gemm_tc: unsupported block_n");
+    return MB_ERR_UNSUPPORTED;
+}
+
+}  // namespace mb

@@ -1,0 +1,53 @@
+// kernels.h -- internal launch interfaces between the translation units of libmarius_b200.so
+#pragma once
+#include "common.cuh"
+
+namespace mb {
+
+// storage_kernels.cu
+mb_status gather_rows(const float* table, int64_t ld, int64_t d, const int64_t* idx, int64_t n, float* out, int64_t out_ld, cudaStream_t st);
+mb_status scatter_rows(float* table, int64_t ld, int64_t d, const int64_t* idx, int64_t n, const float* vals, int64_t vals_ld, bool add, cudaStream_t st);
+mb_status adagrad_deltas(const float* grad, const float* state, int64_t n, int64_t d, int64_t ld, float lr, float* de, float* ds, cudaStream_t st);
+mb_status adagrad_update_rows(float* table, float* state_table, int64_t ld, int64_t d, const int64_t* idx, int64_t n, const float* grad, int64_t grad_ld,
+                              float lr, cudaStream_t st);
+mb_status global_to_local_map(int64_t* map, int64_t total_rows, int64_t psize, const int32_t* part_ids, const int32_t* slots, int n_res, cudaStream_t st);
+mb_status dense_adagrad_step(float* p, float* sum, const float* g, int64_t n, float lr, float eps, cudaStream_t st);
+
+// radix_sort.cu
+size_t sort_scratch_bytes(int64_t n);
+template <typename K>
+mb_status radix_sort_pairs(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_t* vals_b, int64_t n, int key_bits, uint32_t* hist_scratch, K** keys_sorted,
+                           uint32_t** vals_sorted, cudaStream_t st);
+mb_status segment_offsets_u32(const uint32_t* sorted_keys, int64_t n, int64_t num_keys, uint32_t* offsets, cudaStream_t st);
+mb_status map_tensors_device(const int64_t* all_ids, int64_t n, int key_bits, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+                             uint32_t* flags, uint32_t* hist_scratch, uint32_t* total_scratch, int64_t* unique_out, int64_t* mapped_out,
+                             int64_t* num_unique_dev, cudaStream_t st);
+
+// decoder_kernels.cu
+mb_status launch_edge_prep(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+                           int d, int decoder, float* A0, float* A1, float* pos0, float* pos1, void* A0_hi, void* A0_lo, void* A1_hi, void* A1_lo,
+                           cudaStream_t st);
+mb_status launch_gather_split(const float* emb, int64_t emb_ld, const int64_t* idx, int64_t n, int d, float* out, void* hi, void* lo, cudaStream_t st);
+mb_status launch_split(const float* x, int64_t n, void* hi, void* lo, cudaStream_t st);
+mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w, cudaStream_t st);
+mb_status launch_loss_reduce(const float* row_loss, int64_t n, float* loss, cudaStream_t st);
+mb_status launch_edge_backward(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int d,
+                               int decoder, const float* A0, const float* A1, const float* dA0, const float* dA1, const float* gpos0,
+                               const float* gpos1, float* gcat, float* drel0, float* drel1, cudaStream_t st);
+mb_status launch_slot_keys(const int64_t* edges, int cols, int64_t B, const int64_t* dst_negs, const int64_t* src_negs, int64_t CN, uint32_t* keys,
+                           cudaStream_t st);
+mb_status launch_rel_keys(const int64_t* edges, int cols, int64_t B, uint32_t* keys, cudaStream_t st);
+mb_status launch_segment_reduce(int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
+                                const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
+                                const int64_t* ids, float lr, cudaStream_t st);
+
+// gemm_simt.cu
+mb_status gemm_simt(const float* A, int64_t sAm, int64_t sAk, int64_t sAb, const float* B, int64_t sBk, int64_t sBn, int64_t sBb, float* C, int64_t ldc,
+                    int64_t sCb, int M, int N, int K, int batches, cudaStream_t st);
+
+// gemm_tc.cu
+bool gemm_tc_supported(int64_t a_inner, int64_t b_inner);
+mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int64_t sBb,
+                  bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, int block_n, cudaStream_t st);
+
+}  // namespace mb

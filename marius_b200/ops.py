@@ -1,0 +1,279 @@
+"""marius_b200.ops -- thin Python entry points over the C ABI (include/marius_b200.h).
+
+torch is used only for device memory and streams (tensors in, tensors out); every function below is one
+C-ABI call into the hand-written sm_100a kernels.  There is no eager / CPU fallback: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import MariusB200Error, check, lib, mb_batch
+
+DOT, DISTMULT, COMPLEX = 0, 1, 2
+REDUCTION_MEAN, REDUCTION_SUM = 0, 1
+PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+
+_INVALID = 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise MariusB200Error(_INVALID, "marius_b200 ops need CUDA tensors (the hot path has no CPU fallback)")
+
+
+def _rowmajor(t: torch.Tensor, name: str) -> int:
+    """leading dimension (elements) of a 2-D tensor whose rows are contiguous"""
+    if t.dim() != 2 or (t.size(1) > 1 and t.stride(1) != 1):
+        raise MariusB200Error(_INVALID, f"{name} must be 2-D with contiguous rows")
+    return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
+
+
+def _check_indices(idx: torch.Tensor):
+    # storage.cpp:607-610 / buffer.cpp:442-445: indices must be 1-D (std::runtime_error otherwise)
+    if idx.dim() != 1 or idx.dtype != torch.int64:
+        raise MariusB200Error(_INVALID, "indices must be a 1-D int64 tensor")
+    if not idx.is_contiguous():
+        raise MariusB200Error(_INVALID, "indices must be contiguous")
+
+
+class Context:
+    """Owns the device workspace of one in-flight batch (mb_context)."""
+
+    def __init__(self, device: int = 0):
+        self.device = int(device)
+        h = C.c_void_p()
+        check(lib.mb_create(self.device, C.byref(h)))
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    def workspace_bytes(self) -> int:
+        return int(lib.mb_workspace_bytes(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.mb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def gather_rows(table: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Storage::indexRead on a device-resident table (storage.cpp:613-614, buffer.cpp:441-455)."""
+    _need_cuda(table, idx)
+    _check_indices(idx)
+    ld = _rowmajor(table, "table")
+    n, d = idx.numel(), table.size(1)
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+    check(lib.mb_gather_rows(_ptr(table), table.size(0), ld, d, _ptr(idx), n, _ptr(out), _rowmajor(out, "out") if n > 0 else d, _stream()))
+    return out
+
+
+def _check_values(table, idx, vals):
+    # storage.cpp:652-655: values defined, idx 1-D, idx.size(0) == values.size(0), values.size(1) == dim1
+    if vals is None or idx.dim() != 1 or vals.dim() != 2 or idx.size(0) != vals.size(0) or table.size(1) != vals.size(1):
+        raise MariusB200Error(_INVALID, "indexAdd: values undefined or shape mismatch")
+
+
+def scatter_add_rows(table: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor) -> None:
+    """Storage::indexAdd on a device-resident table, unique ids (storage.cpp:656-657, buffer.cpp:459-480)."""
+    _need_cuda(table, idx, vals)
+    _check_values(table, idx, vals)
+    _check_indices(idx)
+    check(lib.mb_scatter_add_rows(_ptr(table), table.size(0), _rowmajor(table, "table"), table.size(1), _ptr(idx), idx.numel(), _ptr(vals),
+                                  _rowmajor(vals, "values"), _stream()))
+
+
+def scatter_put_rows(table: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor) -> None:
+    """Storage::indexPut (storage.cpp:675-696)."""
+    _need_cuda(table, idx, vals)
+    _check_values(table, idx, vals)
+    _check_indices(idx)
+    check(lib.mb_scatter_put_rows(_ptr(table), table.size(0), _rowmajor(table, "table"), table.size(1), _ptr(idx), idx.numel(), _ptr(vals),
+                                  _rowmajor(vals, "values"), _stream()))
+
+
+def global_to_local_map(total_rows: int, partition_size: int, partition_ids, buffer_slots, device) -> torch.Tensor:
+    """PartitionBuffer::getGlobalToLocalMap (buffer.cpp:581-633)."""
+    n = len(partition_ids)
+    out = torch.empty(total_rows, dtype=torch.int64, device=device)
+    pa = (C.c_int32 * max(n, 1))(*[int(x) for x in partition_ids])
+    sa = (C.c_int32 * max(n, 1))(*[int(x) for x in buffer_slots])
+    check(lib.mb_global_to_local_map(_ptr(out), total_rows, partition_size, pa, sa, n, _stream()))
+    return out
+
+
+def adagrad_deltas(grad: torch.Tensor, state: torch.Tensor, lr: float):
+    """Batch::accumulateGradients (batch.cpp:62-79): returns (node_gradients_ = delta_e, node_state_update_ = delta_s)."""
+    _need_cuda(grad, state)
+    g2 = grad.reshape(-1, grad.size(-1)) if grad.dim() > 1 else grad.reshape(1, -1)
+    s2 = state.reshape(g2.shape)
+    g2, s2 = g2.contiguous(), s2.contiguous()
+    de, ds = torch.empty_like(g2), torch.empty_like(g2)
+    check(lib.mb_adagrad_deltas(_ptr(g2), _ptr(s2), g2.size(0), g2.size(1), g2.size(1), float(lr), _ptr(de), _ptr(ds), _stream()))
+    return de.reshape(grad.shape), ds.reshape(grad.shape)
+
+
+def adagrad_update_rows(table: torch.Tensor, state_table: torch.Tensor, idx: torch.Tensor, grad: torch.Tensor, lr: float) -> None:
+    """accumulateGradients + indexAdd(embeddings) + indexAdd(state), fused (dataloader.cpp:550-557)."""
+    _need_cuda(table, state_table, idx, grad)
+    _check_values(table, idx, grad)
+    _check_indices(idx)
+    ld = _rowmajor(table, "table")
+    if _rowmajor(state_table, "state_table") != ld or state_table.shape != table.shape:
+        raise MariusB200Error(_INVALID, "state table must have the table's shape and stride")
+    check(lib.mb_adagrad_update_rows(_ptr(table), _ptr(state_table), table.size(0), ld, table.size(1), _ptr(idx), idx.numel(), _ptr(grad),
+                                     _rowmajor(grad, "grad"), float(lr), _stream()))
+
+
+def dense_adagrad_step(param: torch.Tensor, state_sum: torch.Tensor, grad: torch.Tensor, lr: float, eps: float = 1e-10) -> None:
+    """AdagradOptimizer::step (optim.cpp:114-145) on one dense parameter."""
+    _need_cuda(param, state_sum, grad)
+    if not (param.is_contiguous() and state_sum.is_contiguous() and grad.is_contiguous()):
+        raise MariusB200Error(_INVALID, "dense parameters must be contiguous")
+    check(lib.mb_dense_adagrad_step(_ptr(param), _ptr(state_sum), _ptr(grad), param.numel(), float(lr), float(eps), _stream()))
+
+
+def map_tensors(ctx: Context, all_ids: torch.Tensor, max_id: Optional[int] = None):
+    """map_tensors (util.cpp:180-205): (sorted unique ids, position of every input id)."""
+    _need_cuda(all_ids)
+    if all_ids.dim() != 1:
+        raise MariusB200Error(_INVALID, "Input tensors must be 1D")  # util.cpp:182-185
+    all_ids = all_ids.contiguous()
+    n = all_ids.numel()
+    if max_id is None:
+        max_id = int(all_ids.max().item()) if n else 0
+    uniq = torch.empty(n, dtype=torch.int64, device=all_ids.device)
+    mapped = torch.empty(n, dtype=torch.int64, device=all_ids.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=all_ids.device)
+    check(lib.mb_map_tensors(ctx.handle, _ptr(all_ids), n, int(max_id), _ptr(uniq), _ptr(mapped), _ptr(cnt), _stream()))
+    return uniq[: int(cnt.item())], mapped
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _make_batch(kind, U, d, edges, rel, inv_rel, dst_negs, src_negs, host=False):
+    if edges.dim() != 2 or edges.size(1) not in (2, 3):
+        raise MariusB200Error(_INVALID, "Edge list must be a 3 or 2 column tensor")  # decoder_methods.cpp:66-72
+    if dst_negs is None or dst_negs.dim() != 2:
+        raise MariusB200Error(_INVALID, "negative index mapping must be [num_chunks, num_negatives]")
+    keep = [edges.contiguous(), dst_negs.contiguous(), None if src_negs is None else src_negs.contiguous(),
+            None if rel is None else rel.contiguous(), None if inv_rel is None else inv_rel.contiguous()]
+    b = mb_batch()
+    b.decoder = int(kind)
+    b.U, b.d, b.B = int(U), int(d), int(edges.size(0))
+    b.R = int(rel.size(0)) if rel is not None else 0
+    b.C, b.N = int(dst_negs.size(0)), int(dst_negs.size(1))
+    b.edges = keep[0].data_ptr()
+    b.edge_cols = int(edges.size(1))
+    b.dst_negs = keep[1].data_ptr()
+    b.src_negs = keep[2].data_ptr() if keep[2] is not None else None
+    b.rel = keep[3].data_ptr() if keep[3] is not None else None
+    b.inv_rel = keep[4].data_ptr() if keep[4] is not None else None
+    return b, keep
+
+
+def padded_rows(B: int, C_: int) -> int:
+    return C_ * ((B + C_ - 1) // C_)
+
+
+def decoder_forward(ctx: Context, kind: int, emb: torch.Tensor, edges, rel, inv_rel, dst_negs, src_negs, precision: int = PREC_BF16X3):
+    """Model::forward_lp / node_corrupt_forward (decoder_methods.cpp:57-114): (pos, neg, inv_pos, inv_neg)."""
+    _need_cuda(emb, edges, rel, inv_rel, dst_negs, src_negs)
+    if emb is None:
+        raise MariusB200Error(_INVALID, "UndefinedTensor")
+    b, keep = _make_batch(kind, emb.size(0), emb.size(1), edges, rel, inv_rel, dst_negs, src_negs)
+    Bp = padded_rows(b.B, b.C)
+    inverse = b.inv_rel is not None and b.src_negs is not None and kind != DOT and b.edge_cols == 3
+    dev = emb.device
+    pos = torch.empty(Bp, dtype=torch.float32, device=dev)
+    neg = torch.empty((Bp, b.N), dtype=torch.float32, device=dev)
+    inv_pos = torch.empty(Bp, dtype=torch.float32, device=dev) if inverse else None
+    inv_neg = torch.empty((Bp, b.N), dtype=torch.float32, device=dev) if inverse else None
+    check(lib.mb_decoder_forward(ctx.handle, C.byref(b), _ptr(emb), _rowmajor(emb, "node_embeddings"), int(precision), _ptr(pos), _ptr(neg),
+                                 _ptr(inv_pos), _ptr(inv_neg), _stream()))
+    return pos, neg, inv_pos, inv_neg
+
+
+def train_batch(ctx: Context, kind: int, emb, state, edges, rel, inv_rel, dst_negs, src_negs, lr: float, reduction: int = REDUCTION_SUM,
+                precision: int = PREC_BF16X3, want_grad: bool = True):
+    """Model::train_batch (model.cpp:290-333) on batch-local tensors.  Returns a dict: loss, grad, delta_e, delta_s, rel_grad, inv_rel_grad."""
+    _need_cuda(emb, state, edges, rel, inv_rel, dst_negs, src_negs)
+    b, keep = _make_batch(kind, emb.size(0), emb.size(1), edges, rel, inv_rel, dst_negs, src_negs)
+    dev = emb.device
+    U, d = emb.shape
+    out = dict(loss=torch.empty(1, dtype=torch.float32, device=dev))
+    out["grad"] = torch.empty((U, d), dtype=torch.float32, device=dev) if want_grad else None
+    if state is not None:
+        out["delta_e"] = torch.empty((U, d), dtype=torch.float32, device=dev)
+        out["delta_s"] = torch.empty((U, d), dtype=torch.float32, device=dev)
+    has_rel = rel is not None and kind != DOT and b.edge_cols == 3
+    inverse = has_rel and inv_rel is not None and src_negs is not None
+    out["rel_grad"] = torch.empty_like(rel) if has_rel else None
+    out["inv_rel_grad"] = torch.empty_like(inv_rel) if inverse else None
+    check(lib.mb_train_batch(ctx.handle, C.byref(b), _ptr(emb), _rowmajor(emb, "node_embeddings"), _ptr(state),
+                             _rowmajor(state, "state") if state is not None else 0, float(lr), int(reduction), int(precision), _ptr(out["loss"]),
+                             _ptr(out["grad"]), _ptr(out.get("delta_e")), _ptr(out.get("delta_s")), _ptr(out["rel_grad"]),
+                             _ptr(out["inv_rel_grad"]), _stream()))
+    return out
+
+
+def train_step(ctx: Context, kind: int, table, state_table, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr: float,
+               reduction: int = REDUCTION_SUM, precision: int = PREC_BF16X3, loss=None, rel_grad=None, inv_rel_grad=None):
+    """gather -> train_batch -> fused Adagrad scatter on a device-resident table (trainer.cpp:106-138 with DEVICE_MEMORY embeddings)."""
+    _need_cuda(table, state_table, unique_ids, edges, rel, inv_rel, dst_negs, src_negs)
+    _check_indices(unique_ids)
+    b, keep = _make_batch(kind, unique_ids.numel(), table.size(1), edges, rel, inv_rel, dst_negs, src_negs)
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=table.device)
+    check(lib.mb_train_step(ctx.handle, C.byref(b), _ptr(table), _ptr(state_table), table.size(0), _rowmajor(table, "table"), _ptr(unique_ids),
+                            float(lr), int(reduction), int(precision), _ptr(loss), _ptr(rel_grad), _ptr(inv_rel_grad), _stream()))
+    return loss
+
+
+def train_step_host(ctx: Context, kind: int, table, state_table, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, lr: float,
+                    reduction: int = REDUCTION_SUM, precision: int = PREC_BF16X3, rel_grad=None, inv_rel_grad=None) -> float:
+    """Same step with HOST (ideally pinned) index tensors: H2D of the batch indices and D2H of the loss are inside the call."""
+    _need_cuda(table, state_table, rel, inv_rel)
+    for t in (unique_ids_h, edges_h, dst_negs_h, src_negs_h):
+        if t is not None and t.is_cuda:
+            raise MariusB200Error(_INVALID, "train_step_host takes host index tensors")
+    b, keep = _make_batch(kind, unique_ids_h.numel(), table.size(1), edges_h, rel, inv_rel, dst_negs_h, src_negs_h, host=True)
+    loss = C.c_float(0.0)
+    uid = unique_ids_h.contiguous()
+    check(lib.mb_train_step_host(ctx.handle, C.byref(b), _ptr(table), _ptr(state_table), table.size(0), _rowmajor(table, "table"),
+                                 C.c_void_p(uid.data_ptr()), float(lr), int(reduction), int(precision), C.cast(C.pointer(loss), C.c_void_p), _ptr(rel_grad),
+                                 _ptr(inv_rel_grad), _stream()))
+    return float(loss.value)
+
+
+def debug_gemm(ctx: Context, A: torch.Tensor, a_mn: bool, B: torch.Tensor, b_mn: bool, precision: int = PREC_BF16X3, block_n: int = 256):
+    """Diagnostic: batched D = A . B over K through the contraction kernels (see mb_debug_gemm)."""
+    _need_cuda(A, B)
+    A, B = A.contiguous(), B.contiguous()
+    batches = A.size(0)
+    M, K = (A.size(2), A.size(1)) if a_mn else (A.size(1), A.size(2))
+    N = B.size(2) if b_mn else B.size(1)
+    D = torch.empty((batches, M, N), dtype=torch.float32, device=A.device)
+    check(lib.mb_debug_gemm(ctx.handle, _ptr(A), int(a_mn), _ptr(B), int(b_mn), _ptr(D), M, N, K, batches, int(precision), int(block_n), _stream()))
+    return D

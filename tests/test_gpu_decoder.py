@@ -1,0 +1,220 @@
+"""GPU parity of the decoder / training step through the C ABI against the oracle and the reference-generated golden fixtures.
+Tolerance: 1e-4 relative (north_star) with rel(a,b) = max|a-b| / max(max|b|, tau), tau = 1e-6; indices / gathers bit-exact."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import marius_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from marius_b200 import ops as o
+
+    return o
+
+
+@pytest.fixture(scope="module")
+def ctx(ops):
+    return ops.Context(0)
+
+
+def dev(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_err(a, b, tau=1e-6):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(np.abs(b).max(), tau))
+
+
+def test_distmult_known_answer(ops, ctx):
+    # test/python/bindings/integration/test_nn.py:15-25,148-160 : exact [12.5, -3.75, -0.25]
+    emb = torch.tensor([[1.5, 2.5], [2.5, 3.5], [4.25, 1.0], [-1.0, 0.5]], device="cuda")
+    edges = torch.tensor([[0, 0, 1], [2, 0, 3], [3, 1, 0]], device="cuda")
+    rel = torch.ones(2, 2, device="cuda")
+    negs = torch.tensor([[2, 0], [0, 1], [1, 0]], device="cuda")
+    pos, neg, inv_pos, inv_neg = ops.decoder_forward(ctx, ops.DISTMULT, emb, edges, rel, None, negs, None)
+    assert torch.equal(pos, torch.tensor([12.5, -3.75, -0.25], device="cuda"))
+    assert inv_pos is None and inv_neg is None
+    ref = O.node_corrupt_forward(O.DISTMULT, emb.cpu().numpy(), edges.cpu().numpy(), rel.cpu().numpy(), None, negs.cpu().numpy(), None)
+    assert np.array_equal(neg.cpu().numpy(), ref.neg)
+
+
+TRAIN_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "train_*.npz")))
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_golden_train_batch(ops, ctx, golden_dir, name, prec):
+    """Against outputs of the unmodified reference C++ (Model::forward_lp + Model::train_batch)."""
+    g = np.load(os.path.join(golden_dir, name))
+    p = ops.PREC_FP32 if prec == "fp32" else ops.PREC_BF16X3
+    kind = int(g["kind"])
+    emb, state, edges, rel, inv_rel, dn, sn = (dev(g[k]) for k in ("emb", "state", "edges", "rel", "inv_rel", "dst_negs", "src_negs"))
+    pos, neg, ipos, ineg = ops.decoder_forward(ctx, kind, emb, edges, rel, inv_rel, dn, sn, p)
+    assert rel_err(pos, g["ref_pos"]) < TOL and rel_err(neg, g["ref_neg"]) < TOL
+    assert rel_err(ipos, g["ref_inv_pos"]) < TOL and rel_err(ineg, g["ref_inv_neg"]) < TOL
+    out = ops.train_batch(ctx, kind, emb, state, edges, rel, inv_rel, dn, sn, float(g["lr"]), int(g["reduction"]), p)
+    assert abs(float(out["loss"].item()) - float(g["ref_loss"][0])) <= TOL * abs(float(g["ref_loss"][0]))
+    assert rel_err(out["grad"], g["ref_grad"]) < TOL
+    assert rel_err(out["delta_e"], g["ref_delta_e"]) < TOL
+    assert rel_err(out["delta_s"], g["ref_delta_s"]) < TOL
+    assert rel_err(out["rel_grad"], g["ref_rel_grad"]) < TOL
+    assert rel_err(out["inv_rel_grad"], g["ref_inv_rel_grad"]) < TOL
+
+
+def _random_problem(seed, kind, B, C, N, d, num_nodes, R, scale=0.3, with_rel=True):
+    rng = np.random.default_rng(seed)
+    uniq, edges, dn, sn = O.make_batch(rng, num_nodes, R, B, C, N, with_rel=with_rel)
+    U = len(uniq)
+    emb = rng.uniform(-scale, scale, (U, d)).astype(np.float32)
+    state = rng.uniform(0, 0.05, (U, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    return uniq, edges, dn, sn, emb, state, rel, inv_rel
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("kind,B,C,N,d", [(1, 100, 1, 64, 32), (2, 333, 4, 200, 64), (2, 1000, 1, 1000, 400), (1, 2000, 2, 1000, 400),
+                                          (1, 17, 5, 24, 16), (2, 130, 3, 136, 72)])
+def test_train_batch_vs_oracle(ops, ctx, prec, kind, B, C, N, d):
+    p = ops.PREC_FP32 if prec == "fp32" else ops.PREC_BF16X3
+    uniq, edges, dn, sn, emb, state, rel, inv_rel = _random_problem(B + d, kind, B, C, N, d, 50000, 11)
+    ref = O.train_batch(kind, emb, state, edges, rel, inv_rel, dn, sn, 0.1, O.REDUCTION_SUM, acc=np.float64)
+    out = ops.train_batch(ctx, kind, dev(emb), dev(state), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, ops.REDUCTION_SUM, p)
+    pos, neg, ipos, ineg = ops.decoder_forward(ctx, kind, dev(emb), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), p)
+    assert rel_err(pos, ref.scores.pos) < TOL and rel_err(neg, ref.scores.neg) < TOL
+    assert rel_err(ipos, ref.scores.inv_pos) < TOL and rel_err(ineg, ref.scores.inv_neg) < TOL
+    assert abs(float(out["loss"].item()) - float(ref.loss)) <= TOL * abs(float(ref.loss))
+    assert rel_err(out["grad"], ref.grad) < TOL
+    assert rel_err(out["delta_e"], ref.delta_e) < TOL and rel_err(out["delta_s"], ref.delta_s) < TOL
+    assert rel_err(out["rel_grad"], ref.rel_grad) < TOL and rel_err(out["inv_rel_grad"], ref.inv_rel_grad) < TOL
+
+
+def test_no_inverse_and_dot_decoder(ops, ctx):
+    uniq, edges, dn, sn, emb, state, rel, inv_rel = _random_problem(7, 1, 200, 2, 64, 32, 3000, 5)
+    # use_inverse_relations = false (decoder_methods.cpp:90)
+    ref = O.train_batch(O.DISTMULT, emb, state, edges, rel, None, dn, None, 0.1, O.REDUCTION_SUM, acc=np.float64)
+    for p in (ops.PREC_FP32, ops.PREC_BF16X3):
+        out = ops.train_batch(ctx, ops.DISTMULT, dev(emb), dev(state), dev(edges), dev(rel), None, dev(dn), None, 0.1, ops.REDUCTION_SUM, p)
+        assert out["inv_rel_grad"] is None
+        assert rel_err(out["grad"], ref.grad) < TOL and rel_err(out["rel_grad"], ref.rel_grad) < TOL
+        assert abs(float(out["loss"].item()) - float(ref.loss)) <= TOL * abs(float(ref.loss))
+    # 2-column edges: no relations at all (decoder_methods.cpp:99-101)
+    e2 = np.ascontiguousarray(edges[:, [0, 2]])
+    ref = O.train_batch(O.DOT, emb, state, e2, None, None, dn, None, 0.1, O.REDUCTION_SUM, acc=np.float64)
+    out = ops.train_batch(ctx, ops.DOT, dev(emb), dev(state), dev(e2), None, None, dev(dn), None, 0.1, ops.REDUCTION_SUM, ops.PREC_BF16X3)
+    assert out["rel_grad"] is None
+    assert rel_err(out["grad"], ref.grad) < TOL and rel_err(out["delta_e"], ref.delta_e) < TOL
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("kind", [1, 2])
+def test_fused_train_step_on_table(ops, ctx, prec, kind):
+    """gather -> train_batch -> Adagrad scatter on a device-resident table == the reference's per-batch sequence (trainer.cpp:106-138)."""
+    p = ops.PREC_FP32 if prec == "fp32" else ops.PREC_BF16X3
+    rng = np.random.default_rng(99)
+    num_nodes, R, B, C, N, d = 20000, 9, 512, 2, 256, 128
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    state = rng.uniform(0, 0.01, (num_nodes, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    t, st = dev(table), dev(state)
+    rg, irg = torch.empty(R, d, device="cuda"), torch.empty(R, d, device="cuda")
+    for step in range(3):
+        uniq, edges, dn, sn = O.make_batch(rng, num_nodes, R, B, C, N)
+        loss = ops.train_step(ctx, kind, t, st, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, ops.REDUCTION_SUM, p,
+                              rel_grad=rg, inv_rel_grad=irg)
+        res = O.train_step_on_table(kind, table, state, uniq, edges, rel, inv_rel, dn, sn, 0.1, O.REDUCTION_SUM, acc=np.float64)
+        assert abs(float(loss.item()) - float(res.loss)) <= TOL * abs(float(res.loss))
+        assert rel_err(rg, res.rel_grad) < TOL and rel_err(irg, res.inv_rel_grad) < TOL
+        # untouched rows are bit-identical, touched rows within tolerance
+        got_t, got_s = t.cpu().numpy(), st.cpu().numpy()
+        mask = np.ones(num_nodes, bool)
+        mask[uniq] = False
+        assert np.array_equal(got_t[mask], table[mask]) and np.array_equal(got_s[mask], state[mask])
+        assert rel_err(got_t[uniq] - table[uniq] + res.delta_e, res.delta_e) < 2 * TOL  # the applied update
+        assert rel_err(got_s, state) < TOL
+        # continue from the device result so errors do not compound in the comparison
+        table, state = got_t.copy(), got_s.copy()
+
+
+def test_host_buffer_step_matches_device_step(ops, ctx):
+    rng = np.random.default_rng(5)
+    num_nodes, R, B, C, N, d = 5000, 4, 256, 1, 128, 64
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    uniq, edges, dn, sn = O.make_batch(rng, num_nodes, R, B, C, N)
+    t1, s1 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    t2, s2 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    l1 = ops.train_step(ctx, ops.COMPLEX, t1, s1, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    l2 = ops.train_step_host(ctx, ops.COMPLEX, t2, s2, pin(uniq), pin(edges), dev(rel), dev(inv_rel), pin(dn), pin(sn), 0.1)
+    assert float(l1.item()) == l2
+    assert torch.equal(t1, t2) and torch.equal(s1, s2)  # deterministic: same kernels, same order
+
+
+def test_determinism_with_heavy_duplicates(ops, ctx):
+    """60 nodes, 128 edges x 4 chunks x 64 negatives: every node id collides many times; two runs are bit-identical."""
+    uniq, edges, dn, sn, emb, state, rel, inv_rel = _random_problem(5, 1, 128, 4, 64, 32, 60, 4)
+    args = (dev(emb), dev(state), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1)
+    a = ops.train_batch(ctx, ops.DISTMULT, *args)
+    b = ops.train_batch(ctx, ops.DISTMULT, *args)
+    for k in ("grad", "delta_e", "delta_s", "rel_grad", "inv_rel_grad", "loss"):
+        assert torch.equal(a[k], b[k])
+
+
+def test_mean_reduction_and_padding(ops, ctx):
+    # B % C != 0: padded rows add log(1+N) each to the loss and divide the MEAN by C*ceil(B/C) (hard part 2)
+    uniq, edges, dn, sn, emb, state, rel, inv_rel = _random_problem(21, 2, 50, 4, 40, 24, 500, 3)
+    for red in (O.REDUCTION_MEAN, O.REDUCTION_SUM):
+        ref = O.train_batch(O.COMPLEX, emb, state, edges, rel, inv_rel, dn, sn, 0.1, red, acc=np.float64)
+        out = ops.train_batch(ctx, ops.COMPLEX, dev(emb), dev(state), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, red, ops.PREC_BF16X3)
+        assert abs(float(out["loss"].item()) - float(ref.loss)) <= TOL * abs(float(ref.loss))
+        assert rel_err(out["grad"], ref.grad) < TOL
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("block_n", [256, 128])
+def test_contraction_kernel_layouts(ops, ctx, a_mn, b_mn, block_n):
+    """tcgen05 GEMM, every operand-major combination the path uses, ragged M/N/K, vs fp64 matmul."""
+    torch.manual_seed(1)
+    for (bt, M, N, K) in [(1, 128, 256, 64), (3, 1000, 1000, 400), (2, 1000, 400, 1000), (2, 200, 72, 136), (1, 8, 16, 8)]:
+        A = torch.randn(bt, M, K, device="cuda")
+        Bm = torch.randn(bt, N, K, device="cuda")
+        ref = torch.matmul(A.double(), Bm.double().transpose(1, 2))
+        Ain = A.transpose(1, 2).contiguous() if a_mn else A
+        Bin = Bm.transpose(1, 2).contiguous() if b_mn else Bm
+        D = ops.debug_gemm(ctx, Ain, a_mn, Bin, b_mn, ops.PREC_BF16X3, block_n)
+        err = float((D.double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-5, (a_mn, b_mn, block_n, bt, M, N, K, err)
+        D1 = ops.debug_gemm(ctx, Ain, a_mn, Bin, b_mn, ops.PREC_BF16, block_n)
+        err1 = float((D1.double() - ref).abs().max() / ref.abs().max())
+        assert err1 < 2e-2
+        D0 = ops.debug_gemm(ctx, Ain, a_mn, Bin, b_mn, ops.PREC_FP32, block_n)
+        assert float((D0.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_full_shape_property_checks(ops, ctx):
+    """BASELINE configs[1] shape (ComplEx d=400, 1000 negatives, B=10000 / 10 chunks): tensor-core path vs the fp32 SIMT path
+    of the same library, plus size-independent properties: the loss gradient rows sum to 0 over (pos, negs) and
+    zero relation => zero scores."""
+    uniq, edges, dn, sn, emb, state, rel, inv_rel = _random_problem(1234, 2, 10000, 10, 1000, 400, 10**8, 1000, scale=0.1)
+    a = ops.train_batch(ctx, ops.COMPLEX, dev(emb), dev(state), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, ops.REDUCTION_SUM,
+                        ops.PREC_BF16X3)
+    b = ops.train_batch(ctx, ops.COMPLEX, dev(emb), dev(state), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, ops.REDUCTION_SUM,
+                        ops.PREC_FP32)
+    for k in ("grad", "delta_e", "delta_s", "rel_grad", "inv_rel_grad"):
+        assert rel_err(a[k], b[k].cpu().numpy()) < TOL, k
+    assert abs(float(a["loss"].item()) - float(b["loss"].item())) <= TOL * abs(float(b["loss"].item()))
+    zero = torch.zeros_like(dev(rel))
+    pos, neg, ipos, ineg = ops.decoder_forward(ctx, ops.COMPLEX, dev(emb), dev(edges), zero, zero, dev(dn), dev(sn))
+    assert float(pos.abs().max()) == 0.0 and float(neg.abs().max()) == 0.0 and float(ineg.abs().max()) == 0.0
