@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- edges/sec through the Marius per-batch embedding hot path (gather + score fwd/bwd + Adagrad update).
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref) on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic edges: ComplEx, d=400, 1000 negatives per chunk of
+1000 positives, both-side corruption, SoftmaxCE-SUM, sparse Adagrad lr 0.1 (BASELINE.json configs[1] shape; the
+table is sized to fit one B200 WITH its Adagrad state).  Negative sampling and unique-id mapping are
+inputs: batches are pre-built and excluded from every timed region, for both arms.
+
+One JSON line on stdout (rank 0).  `value` = edges/s with the batch indices already resident in HBM; `e2e` = the same
+step through the host-buffer C-ABI call (pinned host index tensors in, loss out, every step); `roofline` = the dominant
+kernel of the step timed live with CUDA events on the launching stream; `cpu_baseline` = the reference CPU path on a
+bounded sample on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "edges/sec (gather+score+update) at d=400, 1000 negs"
+UNIT = "edges/s"
+D, NEG, CHUNK = 400, 1000, 1000  # embedding dim, negatives per chunk, positives per chunk
+NUM_REL = 1000
+LR = 0.1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return dict(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j["bf16_tflops"]),
+                        bf16_tflops_sustained=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), source="measured")
+        except Exception:
+            pass
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def make_batches(rng, num_nodes, n_batches, B):
+    from oracle import marius_oracle as O
+
+    C = max(B // CHUNK, 1)
+    out = []
+    for _ in range(n_batches):
+        out.append(O.make_batch(rng, num_nodes, NUM_REL, B, C, NEG))
+    return out, C
+
+
+# ------------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_run(steps, warmup, B, num_nodes, seed=0):
+    """Times the reference's CPU hot loop (InMemory::indexRead x2 -> Model::train_batch -> indexAdd x2) on the host cores.
+    Uses oracle/_ref (the unmodified reference C++) when it was built, else the numpy oracle port."""
+    from oracle import marius_oracle as O
+    from oracle import ref_lib as R
+
+    rng = np.random.default_rng(seed)
+    table = rng.uniform(-0.1, 0.1, (num_nodes, D)).astype(np.float32)
+    state = np.zeros((num_nodes, D), np.float32)
+    batches, C = make_batches(rng, num_nodes, max(steps, 1), B)
+    if R.available():
+        uniq = np.concatenate([b[0] for b in batches])
+        off = np.zeros(len(batches) + 1, np.int64)
+        off[1:] = np.cumsum([len(b[0]) for b in batches])
+        edges = np.ascontiguousarray(np.stack([b[1] for b in batches]))
+        dn = np.ascontiguousarray(np.stack([b[2] for b in batches]))
+        sn = np.ascontiguousarray(np.stack([b[3] for b in batches]))
+        cores = R.num_threads()
+        secs = R.train_loop(O.COMPLEX, D, NUM_REL, table, state, uniq, off, edges, dn, sn, LR, O.REDUCTION_SUM, warmup_batches=min(warmup, len(batches)))
+        kind = "reference"
+    else:
+        rel = np.zeros((NUM_REL, D), np.float32)
+        rel[:, : D // 2] = 1
+        inv = rel.copy()
+        t0 = time.perf_counter()
+        for (u, e, dnn, snn) in batches:
+            O.train_step_on_table(O.COMPLEX, table, state, u, e, rel, inv, dnn, snn, LR, O.REDUCTION_SUM)
+        secs = time.perf_counter() - t0
+        cores = os.cpu_count() or 1
+        kind = "port"
+    n = len(batches)
+    return dict(value=n * B / secs, ms_per_step=secs / n * 1e3, cores=cores, kind=kind,
+                sample=f"{n} batches x {B} edges (C={C}, N={NEG}, d={D}, ComplEx), host table {num_nodes} rows", C=C)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    B = args.ref_batch
+    res = cpu_reference_run(args.steps, args.warmup, B, args.ref_nodes)
+    line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=res["ms_per_step"],
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=f"ComplEx d={D}, {NEG} negatives, batch {B} ({res['C']} chunks), both-side corruption, SoftmaxCE-SUM, Adagrad; "
+                                     f"reference CPU path (InMemory host table {args.ref_nodes} rows)", timing="wall clock, host only"),
+                cpu_baseline=dict(value=res["value"], unit=UNIT, cores=res["cores"], kind=res["kind"], sample=res["sample"]),
+                e2e=dict(value=res["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from marius_b200 import _lib, ops
+    from oracle import marius_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the marius_b200 hot path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, K, W = args.batch, args.steps, args.warmup
+    C = max(B // CHUNK, 1)
+    prec = {"bf16x3": ops.PREC_BF16X3, "fp32": ops.PREC_FP32, "bf16": ops.PREC_BF16}[args.precision]
+    # per-GPU shard of the node-partitioned table (weak scaling: rows per GPU fixed; ids below are shard-local rows)
+    free, total = torch.cuda.mem_get_info()
+    rows = args.nodes
+    need = 2 * rows * D * 4 + (6 << 30)
+    if need > free:
+        rows = int((free - (6 << 30)) // (2 * D * 4))
+    table = torch.empty((rows, D), dtype=torch.float32, device=dev).uniform_(-0.1, 0.1)
+    state = torch.zeros((rows, D), dtype=torch.float32, device=dev)
+    rel = torch.zeros((NUM_REL, D), device=dev)
+    rel[:, : D // 2] = 1.0  # ComplEx::reset (complex.cpp:21-30)
+    inv_rel = rel.clone()
+    rel_state, inv_state = torch.zeros_like(rel), torch.zeros_like(rel)
+    rg, irg = torch.empty_like(rel), torch.empty_like(rel)
+    ctx = ops.Context(local)
+
+    rng = np.random.default_rng(1000 + rank)
+    n_b = K + W
+    host_batches, _ = make_batches(rng, rows, n_b, B)
+    pinned = [tuple(torch.from_numpy(x).pin_memory() for x in b) for b in host_batches]
+    resident = [tuple(t.to(dev) for t in b) for b in pinned]
+    U_mean = float(np.mean([len(b[0]) for b in host_batches]))
+    loss = torch.zeros(1, device=dev)
+
+    def dense_step():
+        # Model::step(): the reference's dense Adagrad on the relation tables (optim.cpp:114-145), all-reduced across ranks
+        if world > 1:
+            dist.all_reduce(rg)
+            dist.all_reduce(irg)
+        ops.dense_adagrad_step(rel, rel_state, rg, LR)
+        ops.dense_adagrad_step(inv_rel, inv_state, irg, LR)
+
+    def step_resident(i):
+        u, e, dn, sn = resident[i]
+        ops.train_step(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, loss=loss, rel_grad=rg, inv_rel_grad=irg)
+        dense_step()
+
+    def step_host(i):
+        u, e, dn, sn = pinned[i]
+        l = ops.train_step_host(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
+        dense_step()
+        return l
+
+    # ---- value: indices resident in HBM, device-timed, max over ranks
+    for i in range(W):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        step_resident(i)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = world * K * B / (total_ms / 1e3)
+
+    # ---- e2e: host (pinned) index buffers in, loss out, every step; wall clock bracketed by barriers
+    for i in range(min(W, 2)):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    last_loss = 0.0
+    for i in range(W, W + K):
+        last_loss = step_host(i)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = world * K * B / float(e2e_s.item())
+    h2d = int(np.mean([sum(t.numel() * 8 for t in b) for b in pinned]))
+
+    # ---- roofline: per-stage CUDA-event timing of the same steps (separate pass: events add launch gaps)
+    ctx.profile(True)
+    for i in range(W, W + K):
+        step_resident(i)
+    stages = ctx.profile_read()
+    ctx.profile(False)
+    pk = peaks()
+    per_stage = {k: v[0] / max(v[1], 1) for k, v in stages.items() if v[1] > 0}
+    step_stage_ms = sum(v[0] for v in stages.values()) / K
+    dom = max(per_stage, key=per_stage.get) if per_stage else None
+    Bc = B // C
+    flops = {"gemm_scores": 2 * 2 * C * Bc * NEG * D, "gemm_dA": 2 * 2 * C * Bc * D * NEG, "gemm_dNeg": 2 * 2 * C * NEG * D * Bc}
+    byts = {"gather_rows": 8 * U_mean * D, "segment_reduce+adagrad_update": 20 * U_mean * D}
+    roof = None
+    if dom in flops:
+        ach = flops[dom] / (per_stage[dom] * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = dict(bound="tensor", kernel=dom, achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+                    note=f"algorithmic fp32 flops 2MNK per launch; the kernel issues 3 bf16 products per fp32 product (bf16x3), peak = "
+                         f"{pk['source']} sustained cuBLAS bf16")
+    elif dom in byts:
+        ach = byts[dom] / (per_stage[dom] * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel=dom, achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"], traffic=None,
+                    note=f"peak = {pk['source']} copy bandwidth")
+    elif dom is not None:
+        roof = dict(bound="hbm", kernel=dom, achieved=None, peak=pk["hbm_gbs"], unit="GB/s", frac=None, traffic=None, note="non-roofline stage dominant")
+    step_ms = total_ms / K
+    step_hbm = 16 * U_mean * D / (step_ms * 1e-3) / 1e9
+
+    # ---- CPU baseline (rank 0, N = 1): the reference path on a bounded sample on this box's host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference_run(args.cpu_steps, 1, B, args.ref_nodes, seed=7)
+            cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
+        except Exception as ex:  # the baseline is reported, never required
+            cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="unavailable", sample=str(ex)[:200])
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=step_ms, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=f"BASELINE configs[1] shape: ComplEx d={D}, {NEG} negatives/chunk, batch {B} = {C} chunks x {CHUNK}, both-side "
+                                         f"corruption, SoftmaxCE-SUM, sparse Adagrad lr {LR}; table {rows} rows x {D} fp32 + Adagrad state resident per GPU "
+                                         f"({2 * rows * D * 4 / 1e9:.0f} GB; 1e8 rows + state = 320 GB does not fit 180 GB)",
+                                precision=args.precision, parallelism=f"node-partition shard per GPU x{world}, relation grads all-reduced",
+                                l2="inputs larger than L2: every step gathers/updates a fresh uniform-random row set of a table >> 126 MB",
+                                unique_rows_per_step=U_mean, step_hbm_gbs_algorithmic=step_hbm, step_hbm_frac=step_hbm / pk["hbm_gbs"],
+                                stage_ms={k: round(v, 4) for k, v in per_stage.items()}, stage_sum_ms=step_stage_ms, last_loss=last_loss),
+                    clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4), gpu_launches=int(launches),
+                    roofline=roof, cpu_baseline=cpu, impl="marius_b200")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=10000, help="positives per step (chunks of 1000)")
+    ap.add_argument("--nodes", type=int, default=40_000_000, help="table rows per GPU (with Adagrad state: 2 x rows x 1600 B)")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32", "bf16"])
+    ap.add_argument("--ref-nodes", type=int, default=2_000_000, help="host table rows for the CPU reference arm")
+    ap.add_argument("--ref-batch", type=int, default=10000)
+    ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

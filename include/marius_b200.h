@@ -130,6 +130,13 @@ typedef struct mb_batch {
 mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, float* pos, float* neg,
                              float* inv_pos, float* inv_neg, void* stream);
 
+/* Backward of node_corrupt_forward for ARBITRARY upstream gradients (what libtorch autograd computes under loss.backward(),
+ * model.cpp:324, for any of the reference's loss functions, nn/loss.cpp:50-175): gpos [Bp], gneg [Bp,N] (+ inverse side) ->
+ * grad [U,d] = d/d node_embeddings_, rel_grad / inv_rel_grad [R,d].  Used by the autograd::Function of the C++ adapter. */
+mb_status mb_decoder_backward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, const float* gpos,
+                              const float* gneg, const float* ginv_pos, const float* ginv_neg, float* grad, float* rel_grad, float* inv_rel_grad,
+                              void* stream);
+
 /* Model::train_batch for link prediction (nn/model.cpp:290-333) on batch-local tensors: forward_lp, SoftmaxCrossEntropy on
  * both sides (nn/loss.cpp:50-67, model.cpp:309-312), backward, Batch::accumulateGradients (batch.cpp:62-79).
  * Outputs (device; any may be NULL): loss [1]; grad [U,d] = d loss / d node_embeddings_;
@@ -164,6 +171,14 @@ mb_status mb_dense_adagrad_step(float* param, float* state_sum, const float* gra
  * a_mn == 0: A is [batches][M][K]; a_mn == 1: A is [batches][K][M].  b_mn likewise with N.  block_n in {128, 256}. */
 mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* B, int b_mn, float* D, int M, int N, int K, int batches,
                         int precision, int block_n, void* stream);
+
+/* Per-stage device timing of the step (bench.py's roofline): when enabled, every stage of mb_train_step / mb_train_batch is
+ * bracketed by CUDA events recorded on the caller's stream.  mb_profile_read synchronises the device, fills total_ms[stage] and
+ * counts[stage] (arrays of mb_profile_num_stages() entries) with the time accumulated since the last read, and resets them. */
+mb_status mb_profile_enable(mb_context* ctx, int on);
+int mb_profile_num_stages(void);
+const char* mb_profile_stage_name(int stage);
+mb_status mb_profile_read(mb_context* ctx, float* total_ms, int* counts);
 
 /* bytes of device workspace a context currently holds (grows on demand, reused across batches) */
 size_t mb_workspace_bytes(const mb_context* ctx);

@@ -39,13 +39,16 @@ _SIGS = {
     "mb_adagrad_update_rows": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _f, _vp],
     "mb_map_tensors": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "mb_decoder_forward": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
+    "mb_decoder_backward": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mb_train_batch": [_vp, C.POINTER(mb_batch), _vp, _i64, _vp, _i64, _f, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mb_train_step": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
     "mb_train_step_host": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
     "mb_dense_adagrad_step": [_vp, _vp, _vp, _i64, _f, _f, _vp],
+    "mb_profile_enable": [_vp, _i32],
+    "mb_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }
-EXPORTS = list(_SIGS) + ["mb_destroy", "mb_last_error", "mb_version", "mb_launch_count", "mb_build_info", "mb_workspace_bytes"]
+EXPORTS = list(_SIGS) + ["mb_profile_num_stages", "mb_profile_stage_name", "mb_destroy", "mb_last_error", "mb_version", "mb_launch_count", "mb_build_info", "mb_workspace_bytes"]
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
@@ -56,6 +59,9 @@ lib.mb_last_error.restype = C.c_char_p
 lib.mb_version.restype = C.c_int
 lib.mb_launch_count.restype = C.c_uint64
 lib.mb_build_info.restype = C.c_char_p
+lib.mb_profile_num_stages.restype = C.c_int
+lib.mb_profile_stage_name.argtypes = [C.c_int]
+lib.mb_profile_stage_name.restype = C.c_char_p
 lib.mb_workspace_bytes.argtypes = [_vp]
 lib.mb_workspace_bytes.restype = C.c_size_t
 

@@ -77,7 +77,7 @@ def build_host(force: bool = False, verbose: bool = True):
             if p.wait() != 0:
                 raise RuntimeError("host compile failed")
         link = ["g++", "-shared", "-fopenmp", "-o", out] + objs + ["-L" + os.path.join(tdir, "lib"), "-Wl,-rpath," + os.path.join(tdir, "lib"),
-                                                                  "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_python", "-L" + LIBDIR,
+                                                                  "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda", "-ltorch_python", "-L" + LIBDIR,
                                                                   "-Wl,-rpath,$ORIGIN", "-lmarius_b200"]
         if verbose:
             print("[marius_b200.build] LD", os.path.basename(out), flush=True)

@@ -56,6 +56,14 @@ struct mb_context {
     int64_t* h_sneg = nullptr;
     float* h_loss = nullptr;
     size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
+    // optional per-stage CUDA-event timing (mb_profile_*): events are recorded on the caller's stream
+    bool profiling = false;
+    struct Span {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
 };
 
 namespace mb {
@@ -75,6 +83,40 @@ static mb_status ensure_ws(mb_context* ctx, size_t bytes, cudaStream_t st) {
     ctx->ws_bytes = want;
     return MB_OK;
 }
+
+enum Stage { ST_GATHER = 0, ST_SORT, ST_PREP, ST_GEMM_FWD, ST_LOSS, ST_GEMM_DA, ST_GEMM_DNEG, ST_EDGE_BWD, ST_UPDATE, ST_REL_GRAD, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"gather_rows", "slot_sort", "edge_prep+neg_gather", "gemm_scores", "loss_grad", "gemm_dA",
+                                            "gemm_dNeg", "edge_backward", "segment_reduce+adagrad_update", "rel_grad"};
+
+struct StageTimer {
+    mb_context* ctx;
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int stage;
+    static cudaEvent_t get_event(mb_context* c) {
+        if (!c->event_pool.empty()) {
+            cudaEvent_t e = c->event_pool.back();
+            c->event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    StageTimer(mb_context* c, int stage_, cudaStream_t s) : ctx(c), st(s), stage(stage_) {
+        if (ctx && ctx->profiling) {
+            a = get_event(ctx);
+            b = get_event(ctx);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~StageTimer() {
+        if (a) {
+            cudaEventRecord(b, st);
+            ctx->spans.push_back({stage, a, b});
+        }
+    }
+};
 
 static int bits_for(uint64_t max_value) {
     int b = 1;
@@ -163,8 +205,8 @@ static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
 }
 
 // forward: A, pos, negative rows, scores.  S0/S1 are the score outputs per side ([Bp,N] each).
-static mb_status run_forward(const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, int precision, float* pos0, float* pos1, float* S0,
-                             float* S1, bool uniform_S, cudaStream_t st) {
+static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, int precision, float* pos0, float* pos1, float* S0,
+                             float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false) {
     const int d = (int)p.d;
     float* A0 = p.A;
     float* A1 = p.sides == 2 ? p.A + p.Bp * d : nullptr;
@@ -178,9 +220,11 @@ static mb_status run_forward(const Plan& p, const mb_batch* b, const float* emb,
             A1_lo = A0_lo + p.Bp * d;
         }
     }
+    const int64_t n_half = p.sides * p.CN * d;
+    {
+    StageTimer tm(ctx, ST_PREP, st);
     MB_TRY(launch_edge_prep(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, A0, A1, pos0,
                             p.sides == 2 ? pos1 : nullptr, A0_hi, A0_lo, A1_hi, A1_lo, st));
-    const int64_t n_half = p.sides * p.CN * d;
     for (int s = 0; s < p.sides; s++) {
         const int64_t* negs = s == 0 ? b->dst_negs : b->src_negs;
         float* out = p.use_tc ? nullptr : p.NegE + s * p.CN * d;
@@ -188,8 +232,10 @@ static mb_status run_forward(const Plan& p, const mb_batch* b, const float* emb,
         void* lo = p.use_tc ? (void*)(p.Neg_hl + n_half + s * p.CN * d) : nullptr;
         MB_TRY(launch_gather_split(emb, emb_ld, negs, p.CN, d, out, hi, lo, st));
     }
-    if (p.Bc == 0) return MB_OK;
+    }
+    if (p.Bc == 0 || skip_scores) return MB_OK;
     const int passes = precision == MB_PREC_BF16 ? 1 : 3;
+    StageTimer tm_fwd(ctx, ST_GEMM_FWD, st);
     // scores[side][chunk] = A[side][chunk] . Neg[side][chunk]^T     (comparators.cpp:69-72)
     int launches = uniform_S ? 1 : p.sides;
     for (int l = 0; l < launches; l++) {
@@ -210,7 +256,8 @@ enum class UpdateMode { kBatchLocal, kFusedTable };
 
 static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_in, int64_t emb_ld, const float* state, int64_t state_ld, float* table,
                            float* state_table, int64_t ld, const int64_t* unique_ids, float lr, int reduction, int precision, float* loss,
-                           float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad, UpdateMode mode, cudaStream_t st) {
+                           float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad, UpdateMode mode, cudaStream_t st,
+                           const float* const* ext = nullptr /* {gpos, gneg, ginv_pos, ginv_neg}: upstream gradients instead of the fused loss */) {
     MB_TRY(validate_batch(b));
     MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
     MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
@@ -227,6 +274,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     const int d = (int)p.d;
     const float* emb = emb_in;
     if (fused) {
+        StageTimer tm(ctx, ST_GATHER, st);
         // DataLoader::loadGPUParameters (dataloader.cpp:529-548): gather the unique rows; the state rows are read in place later
         MB_TRY(gather_rows(table, ld, d, unique_ids, p.U, p.emb_u, d, st));
         emb = p.emb_u;
@@ -234,24 +282,36 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     }
     // duplicate-accumulation plan: sort gradient slots by batch-local node id
     uint32_t *skeys = nullptr, *svals = nullptr;
+    {
+    StageTimer tm(ctx, ST_SORT, st);
     MB_TRY(launch_slot_keys(b->edges, p.cols, p.B, b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, p.CN, p.keys_a, st));
     MB_TRY(radix_sort_pairs<uint32_t>(p.keys_a, p.keys_b, p.vals_a, p.vals_b, p.n_slots, p.sides == 2 ? bits_for((uint64_t)std::max<int64_t>(p.U, 1)) : 32,
                                       p.hist, &skeys, &svals, st));
     MB_TRY(segment_offsets_u32(skeys, p.n_slots, p.U, p.offsets, st));
+    }
 
     float* pos0 = p.pos;
     float* pos1 = p.pos + p.Bp;
-    MB_TRY(run_forward(p, b, emb, emb_ld, precision, pos0, pos1, p.S, p.S + p.Bp * p.N, true, st));
+    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, precision, pos0, pos1, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr));
 
     // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
     const int64_t rows = p.sides * p.Bp;
     const float w = reduction == MB_REDUCTION_SUM ? 1.0f : (p.Bp > 0 ? 1.0f / (float)p.Bp : 0.f);
     const int64_t g_half = p.sides * p.Bp * p.N;
-    if (rows > 0) {
+    if (rows > 0 && ext != nullptr) {
+        // generic autograd path: the caller's loss produced d loss / d (pos, neg, inv_pos, inv_neg)
+        for (int sd = 0; sd < p.sides; sd++) {
+            MB_REQUIRE(ext[2 * sd] != nullptr && ext[2 * sd + 1] != nullptr, "upstream gradients missing");
+            MB_CUDA_TRY(cudaMemcpyAsync(p.gpos + sd * p.Bp, ext[2 * sd], sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
+            MB_CUDA_TRY(cudaMemcpyAsync(p.S + sd * p.Bp * p.N, ext[2 * sd + 1], sizeof(float) * p.Bp * p.N, cudaMemcpyDeviceToDevice, st));
+        }
+        if (p.use_tc) MB_TRY(launch_split(p.S, rows * p.N, p.G_hl, p.G_hl + g_half, st));
+    } else if (rows > 0) {
+        StageTimer tm(ctx, ST_LOSS, st);
         MB_TRY(launch_loss_grad(p.S, p.pos, p.gpos, p.row_loss, p.use_tc ? (void*)p.G_hl : nullptr, p.use_tc ? (void*)(p.G_hl + g_half) : nullptr, rows,
                                 p.N, w, st));
     }
-    if (loss) {
+    if (loss && ext == nullptr) {
         if (rows > 0)
             MB_TRY(launch_loss_reduce(p.row_loss, rows, loss, st));
         else
@@ -264,13 +324,25 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
         if (p.use_tc) {
             // dA = G . Neg   ;   dNeg = G^T . A
-            MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, false, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, true, p.dA, d, p.Bc * d,
-                           (int)p.Bc, d, p.N, batches, passes, 256, st));
-            MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, true, p.A_hl, p.A_hl + a_half, d, p.Bc * d, true, gneg, d, (int64_t)p.N * d, p.N, d,
-                           (int)p.Bc, batches, passes, 256, st));
+            {
+                StageTimer tm(ctx, ST_GEMM_DA, st);
+                MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, false, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, true, p.dA, d,
+                               p.Bc * d, (int)p.Bc, d, p.N, batches, passes, 256, st));
+            }
+            {
+                StageTimer tm(ctx, ST_GEMM_DNEG, st);
+                MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, true, p.A_hl, p.A_hl + a_half, d, p.Bc * d, true, gneg, d, (int64_t)p.N * d,
+                               p.N, d, (int)p.Bc, batches, passes, 256, st));
+            }
         } else {
-            MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
-            MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, st));
+            {
+                StageTimer tm(ctx, ST_GEMM_DA, st);
+                MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
+            }
+            {
+                StageTimer tm(ctx, ST_GEMM_DNEG, st);
+                MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, st));
+            }
         }
     } else {
         MB_CUDA_TRY(cudaMemsetAsync(gneg, 0, sizeof(float) * 2 * p.CN * d, st));
@@ -278,11 +350,15 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     if (p.sides == 1) {
         // no inverse side: the src_negs slots carry key 0xffffffff and are never reduced
     }
+    {
+    StageTimer tm(ctx, ST_EDGE_BWD, st);
     MB_TRY(launch_edge_backward(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, d, b->decoder, p.A,
                                 p.sides == 2 ? p.A + p.Bp * d : nullptr, p.dA, p.sides == 2 ? p.dA + p.Bp * d : nullptr, p.gpos,
                                 p.sides == 2 ? p.gpos + p.Bp : nullptr, p.gcat, p.has_rel ? p.drel : nullptr,
                                 (p.has_rel && p.sides == 2) ? p.drel + p.B * d : nullptr, st));
+    }
     // node gradients: segmented sum over sorted slots (+ Adagrad)
+    StageTimer tm_upd(ctx, ST_UPDATE, st);
     if (fused) {
         MB_TRY(launch_segment_reduce(2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr,
                                      st));
@@ -292,8 +368,11 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     } else if (grad != nullptr) {
         MB_TRY(launch_segment_reduce(0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
     }
+    tm_upd.~StageTimer();
+    tm_upd.a = nullptr;
     // relation gradients: segmented sum of per-edge gradients by relation id
     if (p.has_rel && (rel_grad != nullptr || inv_rel_grad != nullptr) && p.R > 0) {
+        StageTimer tm(ctx, ST_REL_GRAD, st);
         uint32_t *rk = nullptr, *rv = nullptr;
         MB_TRY(launch_rel_keys(b->edges, p.cols, p.B, p.rkeys_a, st));
         MB_TRY(radix_sort_pairs<uint32_t>(p.rkeys_a, p.rkeys_b, p.rvals_a, p.rvals_b, p.B, bits_for((uint64_t)p.R), p.rhist, &rk, &rv, st));
@@ -349,10 +428,45 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->h_dneg) cudaFree(ctx->h_dneg);
     if (ctx->h_sneg) cudaFree(ctx->h_sneg);
     if (ctx->h_loss) cudaFree(ctx->h_loss);
+    for (auto& sp : ctx->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     delete ctx;
 }
 
 size_t mb_workspace_bytes(const mb_context* ctx) { return ctx ? ctx->ws_bytes : 0; }
+
+mb_status mb_profile_enable(mb_context* ctx, int on) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    ctx->profiling = on != 0;
+    return MB_OK;
+}
+
+int mb_profile_num_stages(void) { return ST_COUNT; }
+const char* mb_profile_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : ""; }
+
+mb_status mb_profile_read(mb_context* ctx, float* total_ms, int* counts) {
+    MB_REQUIRE(ctx != nullptr && total_ms != nullptr && counts != nullptr, "bad arguments");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    MB_CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < ST_COUNT; i++) {
+        total_ms[i] = 0.f;
+        counts[i] = 0;
+    }
+    for (auto& sp : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            total_ms[sp.stage] += ms;
+            counts[sp.stage] += 1;
+        }
+        ctx->event_pool.push_back(sp.a);
+        ctx->event_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+    return MB_OK;
+}
 
 mb_status mb_gather_rows(const float* table, int64_t num_rows, int64_t ld, int64_t d, const int64_t* idx, int64_t n, float* out, int64_t out_ld,
                          void* stream) {
@@ -449,7 +563,7 @@ mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float
         Arena place(ctx->ws);
         p.layout(place, false, false, false);
     }
-    return run_forward(p, batch, emb, emb_ld, precision, pos, inv_pos, neg, inv_neg, false, st);
+    return run_forward(ctx, p, batch, emb, emb_ld, precision, pos, inv_pos, neg, inv_neg, false, st);
 }
 
 mb_status mb_train_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, const float* state, int64_t state_ld, float lr,
@@ -461,6 +575,18 @@ mb_status mb_train_batch(mb_context* ctx, const mb_batch* batch, const float* em
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
     return run_train(ctx, batch, emb, emb_ld, state, state_ld, nullptr, nullptr, 0, nullptr, lr, reduction, precision, loss, grad, delta_e, delta_s,
                      rel_grad, inv_rel_grad, UpdateMode::kBatchLocal, (cudaStream_t)stream);
+}
+
+mb_status mb_decoder_backward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, const float* gpos,
+                              const float* gneg, const float* ginv_pos, const float* ginv_neg, float* grad, float* rel_grad, float* inv_rel_grad,
+                              void* stream) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    MB_REQUIRE(emb != nullptr && gpos != nullptr && gneg != nullptr && grad != nullptr, "UndefinedTensor");
+    MB_REQUIRE(batch == nullptr || emb_ld >= batch->d, "emb_ld < d");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    const float* ext[4] = {gpos, gneg, ginv_pos, ginv_neg};
+    return run_train(ctx, batch, emb, emb_ld, nullptr, 0, nullptr, nullptr, 0, nullptr, 0.f, MB_REDUCTION_SUM, precision, nullptr, grad, nullptr, nullptr,
+                     rel_grad, inv_rel_grad, UpdateMode::kBatchLocal, (cudaStream_t)stream, ext);
 }
 
 mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, float* state_table, int64_t num_rows, int64_t ld,

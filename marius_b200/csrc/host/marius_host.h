@@ -1,0 +1,277 @@
+// marius_host.h -- C++/libtorch adapters that keep Marius's operator surface for the embedding hot path
+//  on top of the C ABI (include/marius_b200.h).  libtorch is plumbing here (tensor handles, autograd
+// bookkeeping, streams); every row of data is moved / computed by the sm_100a kernels behind mb_*.
+//
+//   reference type (src/cpp/include/...)            this file
+//   storage/storage.h   Storage, InMemory            Storage, InMemory  (device-resident table)
+//   storage/buffer.h    Partition, PartitionedFile,  Partition, PartitionedFile, PartitionBuffer (HBM slab, host file backing),
+//                       PartitionBuffer              PartitionBufferStorage
+//   nn/decoders/edge/*  EdgeDecoder, DistMult,       EdgeDecoder, DistMult, ComplEx, DotDecoder + only_pos_forward /
+//                       ComplEx, decoder methods     node_corrupt_forward (fused autograd::Function)
+//   nn/loss.h           LossFunction, SoftmaxCE      LossFunction, SoftmaxCrossEntropy (+ generic libtorch losses via autograd)
+//   data/batch.h        Batch                        Batch
+//   nn/model.h          Model                        Model (forward_lp / train_batch / evaluate-side scores)
+// Error conventions follow common/exception.h:12-42 (all derive std::runtime_error).
+#pragma once
+
+#include <torch/extension.h>
+
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "marius_b200.h"
+
+using std::shared_ptr;
+using std::string;
+using std::vector;
+typedef torch::Tensor Indices;  // common/datatypes.h
+
+// ---- exceptions (common/exception.h:12-42) -------------------------------------------------------------------
+struct MariusRuntimeException : public std::runtime_error {
+    explicit MariusRuntimeException(const string& msg) : std::runtime_error(msg) {}
+};
+struct UndefinedTensorException : public MariusRuntimeException {
+    UndefinedTensorException() : MariusRuntimeException("Tensor undefined") {}
+};
+struct TensorSizeMismatchException : public MariusRuntimeException {
+    TensorSizeMismatchException(const torch::Tensor& t, const string& msg) : MariusRuntimeException(msg) { (void)t; }
+};
+struct UnexpectedNullPtrException : public MariusRuntimeException {
+    explicit UnexpectedNullPtrException(const string& msg = "") : MariusRuntimeException(msg) {}
+};
+
+// ---- options (configuration/options.h) ------------------------------------------------------------------------
+enum class LossReduction { MEAN, SUM };                                          // options.h:24
+enum class EdgeDecoderMethod { ONLY_POS, POS_AND_NEG, CORRUPT_NODE, CORRUPT_REL };  // options.h:64
+enum class LearningTask { NODE_CLASSIFICATION, LINK_PREDICTION, ENCODE };         // options.h:12
+
+// ---- glue ------------------------------------------------------------------------------------------------------
+void mb_throw_on_error(int status);          // MB_ERR_INVALID -> std::runtime_error (storage.cpp:607-610); others -> MariusRuntimeException
+void* mb_current_stream(const torch::Device& device);
+mb_context* mb_context_for(const torch::Device& device);  // one context per (thread, device): re-entrant like the reference's workers
+void mb_set_default_precision(int precision);             // MB_PREC_BF16X3 by default
+int mb_default_precision();
+
+// ---- storage ---------------------------------------------------------------------------------------------------
+/** Abstract storage class (storage/storage.h:35-86) */
+class Storage {
+   public:
+    int64_t dim0_size_ = 0;
+    int64_t dim1_size_ = 0;
+    torch::Dtype dtype_ = torch::kFloat32;
+    bool initialized_ = false;
+    vector<int64_t> edge_bucket_sizes_;
+    torch::Tensor data_;
+    torch::Device device_ = torch::kCPU;
+    string filename_;
+
+    virtual ~Storage() {}
+    virtual torch::Tensor indexRead(Indices indices) = 0;
+    virtual void indexAdd(Indices indices, torch::Tensor values) = 0;
+    virtual torch::Tensor range(int64_t offset, int64_t n) = 0;
+    virtual void indexPut(Indices indices, torch::Tensor values) = 0;
+    virtual void rangePut(int64_t offset, int64_t n, torch::Tensor values) = 0;
+    virtual void load() = 0;
+    virtual void write() = 0;
+    virtual void unload(bool write = false) = 0;
+    virtual void shuffle() = 0;
+    virtual void sort(bool src) = 0;
+    int64_t getDim0() { return dim0_size_; }
+    bool isInitialized() { return initialized_; }
+    void setInitialized(bool init) { initialized_ = init; }
+};
+
+/** Device-resident table: the DEVICE_MEMORY backend of the reference (InMemory with device_ == cuda, storage.cpp:488-775) */
+class InMemory : public Storage {
+    bool loaded_ = false;
+
+   public:
+    InMemory(string filename, int64_t dim0_size, int64_t dim1_size, torch::Dtype dtype, torch::Device device);
+    InMemory(string filename, torch::Tensor data, torch::Device device);
+    explicit InMemory(torch::Tensor data);
+    void load() override;
+    void write() override;
+    void unload(bool perform_write) override;
+    torch::Tensor indexRead(Indices indices) override;
+    void indexAdd(Indices indices, torch::Tensor values) override;
+    torch::Tensor range(int64_t offset, int64_t n) override;
+    void indexPut(Indices indices, torch::Tensor values) override;
+    void rangePut(int64_t offset, int64_t n, torch::Tensor values) override;
+    void shuffle() override;
+    void sort(bool src) override;
+    /** fused accumulateGradients + indexAdd(embeddings) + indexAdd(state) on two device tables (dataloader.cpp:550-557) */
+    static void adagradUpdate(InMemory& embeddings, InMemory& state, Indices indices, torch::Tensor gradients, float learning_rate);
+};
+
+/** storage/buffer.h:16-41 */
+class Partition {
+   public:
+    int partition_id_;
+    bool present_ = false;
+    int64_t partition_size_;
+    int embedding_size_;
+    int64_t total_size_;
+    int64_t idx_offset_;
+    int64_t file_offset_;
+    int buffer_idx_ = -1;
+    Partition(int partition_id, int64_t partition_size, int embedding_size, int64_t idx_offset, int64_t file_offset)
+        : partition_id_(partition_id), partition_size_(partition_size), embedding_size_(embedding_size),
+          total_size_(partition_size * embedding_size * 4), idx_offset_(idx_offset), file_offset_(file_offset) {}
+};
+
+/** Flat fp32 row-major file of all partitions back to back (storage/buffer.cpp:65-116; the embeddings.bin format, constants.h:39-42) */
+class PartitionedFile {
+   public:
+    string filename_;
+    int fd_ = -1;
+    explicit PartitionedFile(string filename);
+    ~PartitionedFile();
+    void readPartition(void* host_addr, Partition* partition);
+    void writePartition(const void* host_addr, Partition* partition);
+};
+
+/** PartitionBuffer (storage/buffer.h:116-190) with the slab in HBM: `capacity` partitions resident on the GPU, the rest in the
+ *  backing file; swaps follow the caller-supplied buffer-state sequence (BETA/COMET orderings are reused unchanged). */
+class PartitionBuffer {
+    int capacity_, num_partitions_, fine_to_coarse_ratio_, embedding_size_;
+    int64_t partition_size_, total_embeddings_;
+    bool loaded_ = false, prefetching_;
+    torch::Device device_;
+    torch::Tensor buffer_tensor_view_;  // [capacity * partition_size, embedding_size] fp32 in HBM
+    torch::Tensor staging_;             // pinned host bounce buffer, one partition
+    vector<Partition*> partition_table_;
+    string filename_;
+    PartitionedFile* partitioned_file_;
+    torch::Tensor buffer_state_;
+    vector<torch::Tensor> buffer_states_;
+    size_t state_pos_ = 0;  // index of the NEXT state in buffer_states_
+    void admit(vector<Partition*> admit_partitions, vector<int64_t> buffer_idxs);
+    void evict(vector<Partition*> evict_partitions);
+
+   public:
+    PartitionBuffer(int capacity, int num_partitions, int fine_to_coarse_ratio, int64_t partition_size, int embedding_size, int64_t total_embeddings,
+                    torch::Dtype dtype, string filename, bool prefetching, torch::Device device = torch::Device(torch::kCUDA, 0));
+    ~PartitionBuffer();
+    void load();
+    void write();
+    void unload(bool write);
+    vector<int> getNextAdmit();
+    vector<int> getNextEvict();
+    Indices getRandomIds(int64_t size);
+    torch::Tensor indexRead(torch::Tensor indices);
+    torch::Tensor getGlobalToLocalMap(bool get_current);
+    void indexAdd(torch::Tensor indices, torch::Tensor values);
+    void adagradUpdate(PartitionBuffer& state, torch::Tensor indices, torch::Tensor gradients, float learning_rate);
+    void setBufferOrdering(vector<torch::Tensor> buffer_states);
+    bool hasSwap();
+    void performNextSwap();
+    void sync();
+    int64_t getNumInMemory() { return buffer_tensor_view_.defined() ? buffer_tensor_view_.size(0) : 0; }
+    torch::Tensor bufferTensor() { return buffer_tensor_view_; }
+};
+
+// ---- decoders --------------------------------------------------------------------------------------------------
+/** nn/decoders/edge/edge_decoder.h:13-31 restricted to the DotCompare family the kernels implement */
+class EdgeDecoder : public torch::nn::Module {
+   public:
+    int decoder_kind_;  // mb_decoder
+    torch::Tensor relations_;
+    torch::Tensor inverse_relations_;
+    int num_relations_;
+    int embedding_size_;
+    torch::TensorOptions tensor_options_;
+    EdgeDecoderMethod decoder_method_;
+    bool use_inverse_relations_;
+    LearningTask learning_task_ = LearningTask::LINK_PREDICTION;
+
+    torch::Tensor apply_relation(torch::Tensor nodes, torch::Tensor relations);
+    torch::Tensor compute_scores(torch::Tensor src, torch::Tensor dst);
+    torch::Tensor select_relations(torch::Tensor indices, bool inverse = false);
+};
+
+class DistMult : public EdgeDecoder {
+   public:
+    DistMult(int num_relations, int embedding_dim, torch::TensorOptions tensor_options = torch::TensorOptions(), bool use_inverse_relations = true,
+             EdgeDecoderMethod decoder_method = EdgeDecoderMethod::CORRUPT_NODE);
+    void reset();
+};
+
+class ComplEx : public EdgeDecoder {
+   public:
+    ComplEx(int num_relations, int embedding_dim, torch::TensorOptions tensor_options = torch::TensorOptions(), bool use_inverse_relations = true,
+            EdgeDecoderMethod decoder_method = EdgeDecoderMethod::CORRUPT_NODE);
+    void reset();
+};
+
+/** decoder_methods.h:11-21 */
+std::tuple<torch::Tensor, torch::Tensor> only_pos_forward(shared_ptr<EdgeDecoder> decoder, torch::Tensor edges, torch::Tensor node_embeddings);
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> node_corrupt_forward(shared_ptr<EdgeDecoder> decoder, torch::Tensor positive_edges,
+                                                                                            torch::Tensor node_embeddings, torch::Tensor dst_negs,
+                                                                                            torch::Tensor src_negs);
+
+// ---- loss ------------------------------------------------------------------------------------------------------
+class LossFunction {
+   public:
+    virtual ~LossFunction() {}
+    virtual torch::Tensor operator()(torch::Tensor y_pred, torch::Tensor targets, bool scores) = 0;
+};
+
+/** nn/loss.cpp:50-67 (libtorch ops: the generic autograd path; Model::train_batch uses the fused kernels instead) */
+class SoftmaxCrossEntropy : public LossFunction {
+   public:
+    LossReduction reduction_type_;
+    explicit SoftmaxCrossEntropy(LossReduction reduction) : reduction_type_(reduction) {}
+    torch::Tensor operator()(torch::Tensor y_pred, torch::Tensor targets, bool scores) override;
+};
+
+// ---- batch -----------------------------------------------------------------------------------------------------
+/** data/batch.h:32-89 (link-prediction fields) */
+class Batch {
+   public:
+    int batch_id_ = 0;
+    int64_t start_idx_ = 0;
+    int batch_size_ = 0;
+    bool train_;
+    int device_id_ = -1;
+    Indices unique_node_indices_;
+    torch::Tensor node_embeddings_;
+    torch::Tensor node_gradients_;
+    torch::Tensor node_embeddings_state_;
+    torch::Tensor node_state_update_;
+    Indices src_neg_indices_mapping_;
+    Indices dst_neg_indices_mapping_;
+    torch::Tensor edges_;
+    Indices src_neg_indices_;
+    Indices dst_neg_indices_;
+    torch::Tensor src_neg_filter_;
+    torch::Tensor dst_neg_filter_;
+
+    explicit Batch(bool train);
+    void to(torch::Device device);
+    void accumulateGradients(float learning_rate);
+    void embeddingsToHost();
+    void clear();
+};
+
+// ---- model -----------------------------------------------------------------------------------------------------
+/** nn/model.h:16-63, link-prediction path with a pure-embedding encoder (EmbeddingLayer::forward is a view, embedding.cpp:17) */
+class Model : public torch::nn::Module {
+   public:
+    shared_ptr<EdgeDecoder> decoder_;
+    shared_ptr<LossFunction> loss_function_;
+    torch::Device device_;
+    LearningTask learning_task_ = LearningTask::LINK_PREDICTION;
+    float sparse_lr_ = 0.1f;
+    float dense_lr_ = 0.1f;                       // learning rate of the dense (relation) Adagrad optimizer
+    std::vector<torch::Tensor> dense_state_;      // Adagrad "sum" per named parameter (optim.cpp:100-112)
+
+    Model(shared_ptr<EdgeDecoder> decoder, shared_ptr<LossFunction> loss, torch::Device device);
+    std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> forward_lp(shared_ptr<Batch> batch, bool train);
+    void train_batch(shared_ptr<Batch> batch, bool call_step = true);
+    /** train_batch + DataLoader::updateEmbeddings(batch, gpu=true) fused on device-resident tables (pipeline_gpu.cpp:49-91) */
+    float train_batch_fused(shared_ptr<Batch> batch, InMemory& embeddings, InMemory& state, bool call_step = true);
+    void clear_grad();
+    void step();
+};

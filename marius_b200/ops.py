@@ -65,6 +65,17 @@ class Context:
     def workspace_bytes(self) -> int:
         return int(lib.mb_workspace_bytes(self._h))
 
+    def profile(self, on: bool) -> None:
+        check(lib.mb_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self) -> dict:
+        """{stage name: (total ms, launches)} accumulated since the last read (synchronises the device)."""
+        n = lib.mb_profile_num_stages()
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        check(lib.mb_profile_read(self._h, ms, cnt))
+        return {lib.mb_profile_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     def close(self):
         if getattr(self, "_h", None):
             lib.mb_destroy(self._h)

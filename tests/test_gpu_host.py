@@ -1,0 +1,264 @@
+"""The C++/libtorch adapters, exercised the way the reference's own tests exercise the originals:
+test/python/bindings/integration/test_nn.py (forward_lp / train_batch), test_data.py (Batch.accumulateGradients),
+test/cpp/unit/test_buffer.cpp + test_storage.cpp (PartitionBuffer / InMemory indexRead / indexAdd / swap order / maps)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import marius_oracle as O
+
+pytestmark = pytest.mark.gpu
+CUDA = torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def host():
+    from marius_b200 import host as h
+
+    return h
+
+
+# ---- test_nn.py ------------------------------------------------------------------------------------------------
+node_embeddings = torch.tensor([[1.5, 2.5], [2.5, 3.5], [4.25, 1.0], [-1.0, 0.5]])
+batch_edges = torch.tensor([[0, 0, 1], [2, 0, 3], [3, 1, 0]])
+
+
+def get_test_model_lp(host, mode="infer", inverse=False):
+    decoder = host.nn.decoders.edge.DistMult(num_relations=2, embedding_dim=2, use_inverse_relations=inverse, device=CUDA, mode=mode)
+    loss = host.nn.SoftmaxCrossEntropy(reduction="sum")
+    return host.nn.Model(decoder, loss, CUDA)
+
+
+def test_forward_lp(host):
+    # test_nn.py:148-160
+    model = get_test_model_lp(host)
+    batch = host.data.Batch(False)
+    batch.node_embeddings = node_embeddings.to(CUDA)
+    batch.edges = batch_edges.to(CUDA)
+    scores, _, _, _ = model.forward_lp(batch=batch, train=False)
+    assert torch.all(torch.eq(scores.cpu(), torch.tensor([12.5, -3.75, -0.25]))).item() is True
+
+
+def test_train_batch(host):
+    # test_nn.py:162-172, with the result checked against the oracle
+    model = get_test_model_lp(host, mode="train")
+    batch = host.data.Batch(True)
+    batch.node_embeddings = node_embeddings.to(CUDA)
+    batch.node_embeddings_state = torch.zeros_like(node_embeddings).to(CUDA)
+    batch.edges = batch_edges.to(CUDA)
+    negs = torch.tensor([[2, 0], [0, 1], [1, 0]])
+    batch.dst_neg_indices_mapping = negs.to(CUDA)
+    model.train_batch(batch, True)
+    ref = O.train_batch(O.DISTMULT, node_embeddings.numpy(), np.zeros((4, 2), np.float32), batch_edges.numpy(), np.ones((2, 2), np.float32), None,
+                        negs.numpy(), None, 0.1, O.REDUCTION_SUM)
+    assert batch.node_embeddings_state is None
+    assert np.allclose(batch.node_gradients.cpu().numpy(), ref.delta_e, rtol=1e-5, atol=1e-7)
+    assert np.allclose(batch.node_state_update.cpu().numpy(), ref.delta_s, rtol=1e-5, atol=1e-9)
+    # dense relation step happened (Adagrad on ones): relations moved where the gradient is non-zero
+    assert not torch.equal(model.decoder.relations.detach().cpu(), torch.ones(2, 2))
+
+
+@pytest.mark.parametrize("decoder_name,kind", [("DistMult", 1), ("ComplEx", 2)])
+def test_generic_autograd_path_matches_fused(host, decoder_name, kind):
+    """loss.backward() through the fused decoder autograd::Function (any libtorch loss) == the fully fused SoftmaxCE path == oracle."""
+    rng = np.random.default_rng(3)
+    uniq, edges, dn, sn = O.make_batch(rng, 2000, 5, 96, 2, 64)
+    U, d = len(uniq), 32
+    emb = rng.uniform(-0.4, 0.4, (U, d)).astype(np.float32)
+    state = rng.uniform(0, 0.05, (U, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (5, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (5, d)).astype(np.float32)
+    ref = O.train_batch(kind, emb, state, edges, rel, inv_rel, dn, sn, 0.1, O.REDUCTION_SUM, acc=np.float64)
+
+    def make():
+        dec = getattr(host.nn.decoders.edge, decoder_name)(num_relations=5, embedding_dim=d, use_inverse_relations=True, device=CUDA, mode="train")
+        with torch.no_grad():
+            dec.relations.copy_(torch.from_numpy(rel))
+            dec.inverse_relations.copy_(torch.from_numpy(inv_rel))
+        m = host.nn.Model(dec, host.nn.SoftmaxCrossEntropy(reduction="sum"), CUDA)
+        b = host.data.Batch(True)
+        b.node_embeddings = torch.from_numpy(emb).to(CUDA)
+        b.node_embeddings_state = torch.from_numpy(state).to(CUDA)
+        b.edges = torch.from_numpy(edges).to(CUDA)
+        b.dst_neg_indices_mapping = torch.from_numpy(dn).to(CUDA)
+        b.src_neg_indices_mapping = torch.from_numpy(sn).to(CUDA)
+        return m, b
+
+    # (1) fused path
+    m, b = make()
+    m.train_batch(b, False)
+    rel_err = lambda a, r: float(np.abs(a.cpu().numpy() - r).max() / max(np.abs(r).max(), 1e-6))
+    assert rel_err(b.node_gradients, ref.delta_e) < 1e-4 and rel_err(b.node_state_update, ref.delta_s) < 1e-4
+    assert rel_err(m.decoder.relations.grad, ref.rel_grad) < 1e-4 and rel_err(m.decoder.inverse_relations.grad, ref.inv_rel_grad) < 1e-4
+    # (2) generic autograd path: scores -> libtorch loss -> backward through mb_decoder_backward
+    m2, b2 = make()
+    b2.node_embeddings.requires_grad_()
+    pos, neg, ipos, ineg = m2.forward_lp(b2, True)
+    assert rel_err(neg.detach(), ref.scores.neg) < 1e-4 and rel_err(ineg.detach(), ref.scores.inv_neg) < 1e-4
+    loss = m2.loss_function(ipos, ineg, True) + m2.loss_function(pos, neg, True)
+    assert abs(float(loss.item()) - float(ref.loss)) < 1e-4 * abs(float(ref.loss))
+    loss.backward()
+    assert rel_err(b2.node_embeddings.grad, ref.grad) < 1e-4
+    assert rel_err(m2.decoder.relations.grad, ref.rel_grad) < 1e-4
+    b2.accumulateGradients(0.1)
+    assert rel_err(b2.node_gradients, ref.delta_e) < 1e-4
+
+
+# ---- test_data.py ----------------------------------------------------------------------------------------------
+def test_batch_construction_and_accumulate_gradients(host):
+    b1 = host.data.Batch(train=False)
+    assert b1.node_embeddings is None and b1.train is False and b1.device_id == -1
+    # test_data.py:34-47
+    b = host.data.Batch(train=True)
+    b.node_embeddings = torch.tensor([2.0, 4.0], device=CUDA)
+    b.node_embeddings.grad = torch.tensor([0.5, -1.0], device=CUDA)
+    b.node_embeddings_state = torch.tensor([0.0, 0.0], device=CUDA)
+    b.accumulateGradients(learning_rate=1.0)
+    assert b.node_embeddings_state is None
+    assert torch.all(torch.eq(b.node_state_update, b.node_embeddings.grad.pow(2))).item() is True
+    expected = -1.0 * (b.node_embeddings.grad / (b.node_state_update.sqrt().add_(1e-10)))
+    assert torch.all(torch.eq(b.node_gradients, expected)).item() is True
+    b.clear()
+    assert b.node_embeddings is None and b.node_gradients is None
+
+
+# ---- test_storage.cpp / test_buffer.cpp ------------------------------------------------------------------------
+def test_inmemory_index_read_add_put(host, tmp_path):
+    # test_storage.cpp:260-316
+    rand = torch.randn(200, 24)
+    fn = str(tmp_path / "emb.bin")
+    st = host.storage.InMemory(fn, rand, CUDA)
+    st.load()
+    idx = torch.randint(200, (50,))
+    assert torch.equal(st.indexRead(idx).cpu(), rand.index_select(0, idx))
+    with pytest.raises(RuntimeError):
+        st.indexRead(torch.randint(100, (10, 10)))
+    uidx = torch.randperm(200)[:60]
+    vals = torch.randn(60, 24)
+    st.indexAdd(uidx, vals)
+    exp = rand.clone().index_add_(0, uidx, vals)
+    assert torch.equal(st.indexRead(uidx).cpu(), exp.index_select(0, uidx))
+    with pytest.raises(RuntimeError):
+        st.indexAdd(uidx, torch.randn(61, 24))
+    with pytest.raises(RuntimeError):
+        st.indexAdd(uidx, torch.randn(60, 25))
+    st.indexPut(uidx, vals)
+    assert torch.equal(st.indexRead(uidx).cpu(), vals)
+    assert torch.equal(st.range(10, 5).cpu(), st.indexRead(torch.arange(10, 15)).cpu())
+    # flat fp32 row-major file format on unload(write=true) (constants.h:39-42)
+    st.unload(True)
+    disk = torch.from_numpy(np.fromfile(fn, dtype=np.float32).reshape(200, 24))
+    exp[uidx] = vals
+    assert torch.equal(disk, exp)
+
+
+class TestPartitionBuffer:
+    # test_buffer.cpp:20-75 fixture: 45 rows, 5 partitions of 10 (last 5), capacity 2, ordering of TestPartitionBufferOrdering
+    total, nparts, psize, d, cap = 45, 5, 10, 16, 2
+    states = [[0, 1], [0, 2], [0, 3], [0, 4], [1, 4], [1, 3], [1, 2], [3, 2], [4, 2], [4, 3]]
+
+    def make(self, host, tmp_path):
+        rand = torch.randn(self.total, self.d)
+        fn = str(tmp_path / "pb.bin")
+        rand.numpy().tofile(fn)
+        pb = host.storage.PartitionBuffer(self.cap, self.nparts, 1, self.psize, self.d, self.total, fn, False, CUDA)
+        pb.setBufferOrdering([torch.tensor(s) for s in self.states])
+        pb.load()
+        return pb, rand, fn
+
+    def test_ordering(self, host, tmp_path):
+        # test_buffer.cpp:241-259
+        pb, _, _ = self.make(host, tmp_path)
+        admits, evicts = [], []
+        while pb.hasSwap():
+            admits.append(pb.getNextAdmit()[0])
+            evicts.append(pb.getNextEvict()[0])
+            pb.performNextSwap()
+        assert admits == [2, 3, 4, 1, 3, 2, 3, 4, 3] and evicts == [1, 2, 3, 0, 4, 3, 1, 3, 2]
+        assert pb.hasSwap() is False
+
+    def test_index_read_add(self, host, tmp_path, golden_dir):
+        # test_buffer.cpp:275-297
+        pb, rand, _ = self.make(host, tmp_path)
+        idx = pb.getRandomIds(20)
+        assert torch.equal(rand.index_select(0, idx), pb.indexRead(idx).cpu())
+        with pytest.raises(RuntimeError):
+            pb.indexRead(torch.randint(1000, (10, 10)))
+        uidx = torch.unique(pb.getRandomIds(1000))
+        vals = torch.randint(1000, (uidx.size(0), self.d)).float()
+        upd = rand.clone().index_add_(0, uidx, vals).index_select(0, uidx)
+        pb.indexAdd(uidx, vals)
+        assert torch.equal(upd, pb.indexRead(uidx).cpu())
+        with pytest.raises(RuntimeError):
+            pb.indexAdd(uidx, torch.zeros(uidx.size(0) + 1, self.d))
+        with pytest.raises(RuntimeError):
+            pb.indexAdd(uidx, torch.zeros(uidx.size(0), self.d + 1))
+        with pytest.raises(RuntimeError):
+            pb.indexAdd(torch.randint(1000, (10, 10)), vals)
+
+    def test_global_map_and_sync(self, host, tmp_path):
+        # test_buffer.cpp:299-318
+        pb, rand, fn = self.make(host, tmp_path)
+        exp = -torch.ones(self.total, dtype=torch.int64)
+        exp[:20] = torch.arange(20)
+        assert torch.equal(exp, pb.getGlobalToLocalMap(True).cpu())
+        exp[10:20] = -1
+        exp[20:30] = torch.arange(10, 20)
+        assert torch.equal(exp, pb.getGlobalToLocalMap(False).cpu())
+        # updates survive eviction: add to partition 1 rows, swap it out, read the file
+        ids = torch.arange(10, 20)
+        vals = torch.ones(10, self.d)
+        pb.indexAdd(ids, vals)
+        pb.performNextSwap()  # evicts partition 1
+        disk = torch.from_numpy(np.fromfile(fn, dtype=np.float32).reshape(self.total, self.d))
+        assert torch.equal(disk[10:20], rand[10:20] + 1)
+        # partition 2 now lives in slot 1: buffer-local row 10 is global row 20
+        assert torch.equal(pb.indexRead(torch.tensor([10])).cpu(), rand[20:21])
+        pb.unload(True)
+        disk = torch.from_numpy(np.fromfile(fn, dtype=np.float32).reshape(self.total, self.d))
+        assert torch.equal(disk[20:30], rand[20:30]) and torch.equal(disk[:10], rand[:10])
+
+    def test_against_reference_golden(self, host, tmp_path, golden_dir):
+        g = np.load(os.path.join(golden_dir, "partition_buffer.npz"))
+        fn = str(tmp_path / "pbg.bin")
+        g["table"].tofile(fn)
+        pb = host.storage.PartitionBuffer(int(g["cap"]), int(g["nparts"]), 1, int(g["psize"]), int(g["d"]), int(g["total"]), fn, False, CUDA)
+        pb.setBufferOrdering([torch.from_numpy(s) for s in g["states"]])
+        pb.load()
+        idx = torch.from_numpy(g["idx"])
+        assert np.array_equal(pb.indexRead(idx).cpu().numpy(), g["read"])
+        assert np.array_equal(pb.getGlobalToLocalMap(True).cpu().numpy(), g["map_current"])
+        assert np.array_equal(pb.getGlobalToLocalMap(False).cpu().numpy(), g["map_next"])
+        pb.indexAdd(idx, torch.from_numpy(g["vals"]))
+        assert np.array_equal(pb.indexRead(idx).cpu().numpy(), g["read_after_add"])
+        while pb.hasSwap():
+            pb.performNextSwap()
+        pb.unload(True)
+        assert np.array_equal(np.fromfile(fn, dtype=np.float32).reshape(g["table"].shape), g["file_after"])
+
+
+def test_train_batch_fused_on_device_tables(host):
+    rng = np.random.default_rng(11)
+    num_nodes, R, B, C, N, d = 3000, 4, 200, 2, 100, 48
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    state = np.zeros((num_nodes, d), np.float32)
+    emb_st = host.storage.InMemory(torch.from_numpy(table).to(CUDA))
+    state_st = host.storage.InMemory(torch.from_numpy(state).to(CUDA))
+    dec = host.nn.decoders.edge.ComplEx(num_relations=R, embedding_dim=d, use_inverse_relations=True, device=CUDA, mode="train")
+    model = host.nn.Model(dec, host.nn.SoftmaxCrossEntropy(reduction="sum"), CUDA)
+    rel = dec.relations.detach().cpu().numpy().copy()
+    inv = dec.inverse_relations.detach().cpu().numpy().copy()
+    uniq, edges, dn, sn = O.make_batch(rng, num_nodes, R, B, C, N)
+    b = host.data.Batch(True)
+    b.unique_node_indices = torch.from_numpy(uniq)
+    b.edges = torch.from_numpy(edges)
+    b.dst_neg_indices_mapping = torch.from_numpy(dn)
+    b.src_neg_indices_mapping = torch.from_numpy(sn)
+    loss = model.train_batch_fused(b, emb_st, state_st, False)
+    res = O.train_step_on_table(O.COMPLEX, table, state, uniq, edges, rel, inv, dn, sn, 0.1, O.REDUCTION_SUM, acc=np.float64)
+    assert abs(loss - float(res.loss)) < 1e-4 * abs(float(res.loss))
+    got = emb_st.data.cpu().numpy()
+    assert np.abs(got - table).max() / np.abs(table).max() < 1e-4
+    assert np.abs(state_st.data.cpu().numpy() - state).max() / max(np.abs(state).max(), 1e-6) < 1e-4
