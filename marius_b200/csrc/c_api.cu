@@ -56,6 +56,8 @@ struct mb_context {
     int64_t* h_sneg = nullptr;
     float* h_loss = nullptr;
     size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
+    cudaStream_t side = nullptr;          // index plans (slot / relation sorts) overlap the forward pass here
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // optional per-stage CUDA-event timing (mb_profile_*): events are recorded on the caller's stream
     bool profiling = false;
     struct Span {
@@ -84,9 +86,9 @@ static mb_status ensure_ws(mb_context* ctx, size_t bytes, cudaStream_t st) {
     return MB_OK;
 }
 
-enum Stage { ST_GATHER = 0, ST_SORT, ST_PREP, ST_GEMM_FWD, ST_LOSS, ST_GEMM_DA, ST_GEMM_DNEG, ST_EDGE_BWD, ST_UPDATE, ST_REL_GRAD, ST_COUNT };
-static const char* kStageNames[ST_COUNT] = {"gather_rows", "slot_sort", "edge_prep+neg_gather", "gemm_scores", "loss_grad", "gemm_dA",
-                                            "gemm_dNeg", "edge_backward", "segment_reduce+adagrad_update", "rel_grad"};
+enum Stage { ST_GATHER = 0, ST_SORT, ST_REL_SORT, ST_PREP, ST_GEMM_FWD, ST_LOSS, ST_GEMM_DA, ST_GEMM_DNEG, ST_EDGE_BWD, ST_UPDATE, ST_REL_GRAD, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"gather_rows", "slot_sort", "rel_sort", "edge_prep+neg_gather", "gemm_scores", "loss_grad", "gemm_dA",
+                                            "gemm_dNeg", "edge_backward", "segment_reduce+adagrad_update", "rel_grad_reduce"};
 
 struct StageTimer {
     mb_context* ctx;
@@ -204,34 +206,20 @@ static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
     p.use_tc = (precision != MB_PREC_FP32) && gemm_tc_supported(p.d, p.N) && p.Bc > 0;
 }
 
-// forward: A, pos, negative rows, scores.  S0/S1 are the score outputs per side ([Bp,N] each).
-static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, int precision, float* pos0, float* pos1, float* S0,
+// forward: adjusted rows A, positive scores, negative rows, score GEMM.  S0/S1 are the score outputs per side ([Bp,N] each).
+static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, int precision, float* pos, float* S0,
                              float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false) {
     const int d = (int)p.d;
-    float* A0 = p.A;
-    float* A1 = p.sides == 2 ? p.A + p.Bp * d : nullptr;
-    __nv_bfloat16 *A0_hi = nullptr, *A0_lo = nullptr, *A1_hi = nullptr, *A1_lo = nullptr;
     const int64_t a_half = p.sides * p.Bp * d;  // hi block then lo block, each [sides][Bp][d]
-    if (p.use_tc) {
-        A0_hi = p.A_hl;
-        A0_lo = p.A_hl + a_half;
-        if (p.sides == 2) {
-            A1_hi = A0_hi + p.Bp * d;
-            A1_lo = A0_lo + p.Bp * d;
-        }
-    }
     const int64_t n_half = p.sides * p.CN * d;
     {
-    StageTimer tm(ctx, ST_PREP, st);
-    MB_TRY(launch_edge_prep(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, A0, A1, pos0,
-                            p.sides == 2 ? pos1 : nullptr, A0_hi, A0_lo, A1_hi, A1_lo, st));
-    for (int s = 0; s < p.sides; s++) {
-        const int64_t* negs = s == 0 ? b->dst_negs : b->src_negs;
-        float* out = p.use_tc ? nullptr : p.NegE + s * p.CN * d;
-        void* hi = p.use_tc ? (void*)(p.Neg_hl + s * p.CN * d) : nullptr;
-        void* lo = p.use_tc ? (void*)(p.Neg_hl + n_half + s * p.CN * d) : nullptr;
-        MB_TRY(launch_gather_split(emb, emb_ld, negs, p.CN, d, out, hi, lo, st));
-    }
+        StageTimer tm(ctx, ST_PREP, st);
+        // the fp32 adjusted rows are only read by the SIMT GEMM and by the scalar (general-d) backward kernel
+        const bool need_A = !p.use_tc || !decoder_vec_ok(emb, emb_ld, d, p.has_rel, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.sides);
+        MB_TRY(launch_prep(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, p.CN, d, b->decoder, p.sides,
+                           b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, need_A ? p.A : nullptr, pos, p.use_tc ? (void*)p.A_hl : nullptr,
+                           p.use_tc ? (void*)(p.A_hl + a_half) : nullptr, p.NegE, p.use_tc ? (void*)p.Neg_hl : nullptr,
+                           p.use_tc ? (void*)(p.Neg_hl + n_half) : nullptr, st));
     }
     if (p.Bc == 0 || skip_scores) return MB_OK;
     const int passes = precision == MB_PREC_BF16 ? 1 : 3;
@@ -254,6 +242,27 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
 
 enum class UpdateMode { kBatchLocal, kFusedTable };
 
+// The duplicate-accumulation plans (slot list sorted by node id, edges sorted by relation id) only depend on the batch's
+// index tensors, so they run on the context's side stream concurrently with gather / prep / the score GEMM.
+static mb_status run_index_plans(mb_context* ctx, const Plan& p, const mb_batch* b, bool need_rel, uint32_t** svals, uint32_t** rvals, cudaStream_t st) {
+    uint32_t* skeys = nullptr;
+    {
+        StageTimer tm(ctx, ST_SORT, st);
+        MB_TRY(launch_slot_keys(b->edges, p.cols, p.B, b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, p.CN, p.keys_a, st));
+        MB_TRY(radix_sort_pairs<uint32_t>(p.keys_a, p.keys_b, p.vals_a, p.vals_b, p.n_slots,
+                                          p.sides == 2 ? bits_for((uint64_t)std::max<int64_t>(p.U, 1)) : 32, p.hist, &skeys, svals, st));
+        MB_TRY(segment_offsets_u32(skeys, p.n_slots, p.U, p.offsets, st));
+    }
+    if (need_rel) {
+        StageTimer tm(ctx, ST_REL_SORT, st);
+        uint32_t* rk = nullptr;
+        MB_TRY(launch_rel_keys(b->edges, p.cols, p.B, p.rkeys_a, st));
+        MB_TRY(radix_sort_pairs<uint32_t>(p.rkeys_a, p.rkeys_b, p.rvals_a, p.rvals_b, p.B, bits_for((uint64_t)p.R), p.rhist, &rk, rvals, st));
+        MB_TRY(segment_offsets_u32(rk, p.B, p.R, p.roffsets, st));
+    }
+    return MB_OK;
+}
+
 static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_in, int64_t emb_ld, const float* state, int64_t state_ld, float* table,
                            float* state_table, int64_t ld, const int64_t* unique_ids, float lr, int reduction, int precision, float* loss,
                            float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad, UpdateMode mode, cudaStream_t st,
@@ -272,6 +281,20 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         p.layout(place, fused, true, true);
     }
     const int d = (int)p.d;
+    const bool need_rel = p.has_rel && (rel_grad != nullptr || inv_rel_grad != nullptr) && p.R > 0;
+
+    // ---- fork: index plans on the side stream (inline when profiling so that stage times stay meaningful)
+    uint32_t *svals = nullptr, *rvals = nullptr;
+    const bool overlap = !ctx->profiling && ctx->side != nullptr;
+    if (overlap) {
+        MB_CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+        MB_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        MB_TRY(run_index_plans(ctx, p, b, need_rel, &svals, &rvals, ctx->side));
+        MB_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+    } else {
+        MB_TRY(run_index_plans(ctx, p, b, need_rel, &svals, &rvals, st));
+    }
+
     const float* emb = emb_in;
     if (fused) {
         StageTimer tm(ctx, ST_GATHER, st);
@@ -280,24 +303,15 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         emb = p.emb_u;
         emb_ld = d;
     }
-    // duplicate-accumulation plan: sort gradient slots by batch-local node id
-    uint32_t *skeys = nullptr, *svals = nullptr;
-    {
-    StageTimer tm(ctx, ST_SORT, st);
-    MB_TRY(launch_slot_keys(b->edges, p.cols, p.B, b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, p.CN, p.keys_a, st));
-    MB_TRY(radix_sort_pairs<uint32_t>(p.keys_a, p.keys_b, p.vals_a, p.vals_b, p.n_slots, p.sides == 2 ? bits_for((uint64_t)std::max<int64_t>(p.U, 1)) : 32,
-                                      p.hist, &skeys, &svals, st));
-    MB_TRY(segment_offsets_u32(skeys, p.n_slots, p.U, p.offsets, st));
-    }
 
-    float* pos0 = p.pos;
-    float* pos1 = p.pos + p.Bp;
-    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, precision, pos0, pos1, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr));
+    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr));
 
     // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
     const int64_t rows = p.sides * p.Bp;
     const float w = reduction == MB_REDUCTION_SUM ? 1.0f : (p.Bp > 0 ? 1.0f / (float)p.Bp : 0.f);
     const int64_t g_half = p.sides * p.Bp * p.N;
+    void* G_hi = p.use_tc ? (void*)p.G_hl : nullptr;
+    void* G_lo = p.use_tc ? (void*)(p.G_hl + g_half) : nullptr;
     if (rows > 0 && ext != nullptr) {
         // generic autograd path: the caller's loss produced d loss / d (pos, neg, inv_pos, inv_neg)
         for (int sd = 0; sd < p.sides; sd++) {
@@ -305,11 +319,11 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
             MB_CUDA_TRY(cudaMemcpyAsync(p.gpos + sd * p.Bp, ext[2 * sd], sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
             MB_CUDA_TRY(cudaMemcpyAsync(p.S + sd * p.Bp * p.N, ext[2 * sd + 1], sizeof(float) * p.Bp * p.N, cudaMemcpyDeviceToDevice, st));
         }
-        if (p.use_tc) MB_TRY(launch_split(p.S, rows * p.N, p.G_hl, p.G_hl + g_half, st));
+        if (p.use_tc) MB_TRY(launch_split(p.S, rows * p.N, G_hi, G_lo, st));
     } else if (rows > 0) {
         StageTimer tm(ctx, ST_LOSS, st);
-        MB_TRY(launch_loss_grad(p.S, p.pos, p.gpos, p.row_loss, p.use_tc ? (void*)p.G_hl : nullptr, p.use_tc ? (void*)(p.G_hl + g_half) : nullptr, rows,
-                                p.N, w, st));
+        // the tensor-core path consumes only the bf16 hi/lo gradient; the fp32 copy is written for the SIMT path only
+        MB_TRY(launch_loss(p.S, p.use_tc ? nullptr : p.S, p.pos, p.gpos, p.row_loss, G_hi, G_lo, rows, p.N, w, st));
     }
     if (loss && ext == nullptr) {
         if (rows > 0)
@@ -322,66 +336,52 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     float* gneg = p.gcat + 2 * p.B * d;  // d dst_negs | d src_negs, [sides][C][N][d]
     if (p.Bc > 0) {
         const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
-        if (p.use_tc) {
-            // dA = G . Neg   ;   dNeg = G^T . A
-            {
-                StageTimer tm(ctx, ST_GEMM_DA, st);
+        {
+            StageTimer tm(ctx, ST_GEMM_DA, st);  // dA = G . Neg
+            if (p.use_tc)
                 MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, false, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, true, p.dA, d,
                                p.Bc * d, (int)p.Bc, d, p.N, batches, passes, 256, st));
-            }
-            {
-                StageTimer tm(ctx, ST_GEMM_DNEG, st);
+            else
+                MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
+        }
+        {
+            StageTimer tm(ctx, ST_GEMM_DNEG, st);  // dNeg = G^T . A
+            if (p.use_tc)
                 MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, true, p.A_hl, p.A_hl + a_half, d, p.Bc * d, true, gneg, d, (int64_t)p.N * d,
                                p.N, d, (int)p.Bc, batches, passes, 256, st));
-            }
-        } else {
-            {
-                StageTimer tm(ctx, ST_GEMM_DA, st);
-                MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
-            }
-            {
-                StageTimer tm(ctx, ST_GEMM_DNEG, st);
+            else
                 MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, st));
-            }
         }
     } else {
         MB_CUDA_TRY(cudaMemsetAsync(gneg, 0, sizeof(float) * 2 * p.CN * d, st));
     }
-    if (p.sides == 1) {
-        // no inverse side: the src_negs slots carry key 0xffffffff and are never reduced
-    }
     {
-    StageTimer tm(ctx, ST_EDGE_BWD, st);
-    MB_TRY(launch_edge_backward(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, d, b->decoder, p.A,
-                                p.sides == 2 ? p.A + p.Bp * d : nullptr, p.dA, p.sides == 2 ? p.dA + p.Bp * d : nullptr, p.gpos,
-                                p.sides == 2 ? p.gpos + p.Bp : nullptr, p.gcat, p.has_rel ? p.drel : nullptr,
-                                (p.has_rel && p.sides == 2) ? p.drel + p.B * d : nullptr, st));
+        StageTimer tm(ctx, ST_EDGE_BWD, st);
+        MB_TRY(launch_edge_bwd(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, p.sides, p.A, p.dA,
+                               p.gpos, p.gcat, p.has_rel ? p.drel : nullptr, st));
     }
-    // node gradients: segmented sum over sorted slots (+ Adagrad)
-    StageTimer tm_upd(ctx, ST_UPDATE, st);
-    if (fused) {
-        MB_TRY(launch_segment_reduce(2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr,
-                                     st));
-    } else if (delta_e != nullptr || delta_s != nullptr) {
-        MB_REQUIRE(state != nullptr && delta_e != nullptr && delta_s != nullptr, "delta_e/delta_s need state and both outputs");
-        MB_TRY(launch_segment_reduce(1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
-    } else if (grad != nullptr) {
-        MB_TRY(launch_segment_reduce(0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
+    // ---- join: the slot / relation plans are needed from here on
+    if (overlap) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    {
+        // node gradients: segmented sum over sorted slots (+ Adagrad)
+        StageTimer tm(ctx, ST_UPDATE, st);
+        if (fused) {
+            MB_TRY(launch_seg_reduce(2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st));
+        } else if (delta_e != nullptr || delta_s != nullptr) {
+            MB_REQUIRE(state != nullptr && delta_e != nullptr && delta_s != nullptr, "delta_e/delta_s need state and both outputs");
+            MB_TRY(launch_seg_reduce(1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
+        } else if (grad != nullptr) {
+            MB_TRY(launch_seg_reduce(0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
+        }
     }
-    tm_upd.~StageTimer();
-    tm_upd.a = nullptr;
-    // relation gradients: segmented sum of per-edge gradients by relation id
-    if (p.has_rel && (rel_grad != nullptr || inv_rel_grad != nullptr) && p.R > 0) {
+    if (need_rel) {
+        // relation gradients: segmented sum of per-edge gradients by relation id
         StageTimer tm(ctx, ST_REL_GRAD, st);
-        uint32_t *rk = nullptr, *rv = nullptr;
-        MB_TRY(launch_rel_keys(b->edges, p.cols, p.B, p.rkeys_a, st));
-        MB_TRY(radix_sort_pairs<uint32_t>(p.rkeys_a, p.rkeys_b, p.rvals_a, p.rvals_b, p.B, bits_for((uint64_t)p.R), p.rhist, &rk, &rv, st));
-        MB_TRY(segment_offsets_u32(rk, p.B, p.R, p.roffsets, st));
         if (rel_grad)
-            MB_TRY(launch_segment_reduce(0, p.drel, rv, p.roffsets, p.R, d, rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
+            MB_TRY(launch_seg_reduce(0, p.drel, rvals, p.roffsets, p.R, d, rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
         if (inv_rel_grad && p.sides == 2)
-            MB_TRY(launch_segment_reduce(0, p.drel + p.B * d, rv, p.roffsets, p.R, d, inv_rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0,
-                                         nullptr, lr, st));
+            MB_TRY(launch_seg_reduce(0, p.drel + p.B * d, rvals, p.roffsets, p.R, d, inv_rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0,
+                                     nullptr, lr, st));
     }
     return MB_OK;
 }
@@ -410,9 +410,12 @@ mb_status mb_create(int device, mb_context** out) {
     mb_context* c = new mb_context();
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete c;
-        set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+        set_error(std::string("context creation failed: ") + cudaGetErrorString(e));
         return MB_ERR_CUDA;
     }
     *out = c;
@@ -428,6 +431,9 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->h_dneg) cudaFree(ctx->h_dneg);
     if (ctx->h_sneg) cudaFree(ctx->h_sneg);
     if (ctx->h_loss) cudaFree(ctx->h_loss);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto& sp : ctx->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -563,7 +569,11 @@ mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float
         Arena place(ctx->ws);
         p.layout(place, false, false, false);
     }
-    return run_forward(ctx, p, batch, emb, emb_ld, precision, pos, inv_pos, neg, inv_neg, false, st);
+    // pos / inv_pos are separate user buffers: stage them in the workspace layout [sides][Bp] and copy out
+    MB_TRY(run_forward(ctx, p, batch, emb, emb_ld, precision, p.pos, neg, inv_neg, false, st));
+    MB_CUDA_TRY(cudaMemcpyAsync(pos, p.pos, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
+    if (p.sides == 2) MB_CUDA_TRY(cudaMemcpyAsync(inv_pos, p.pos + p.Bp, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
+    return MB_OK;
 }
 
 mb_status mb_train_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, const float* state, int64_t state_ld, float lr,

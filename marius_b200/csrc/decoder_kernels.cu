@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "decoder_vec.cuh"
 
 namespace mb {
 
@@ -484,6 +485,159 @@ mb_status launch_segment_reduce(int mode, const float* rows, const uint32_t* slo
         segment_reduce_kernel<1><<<grid, kThreads, 0, st>>>(a);
     else
         segment_reduce_kernel<2><<<grid, kThreads, 0, st>>>(a);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+// ---- unified launchers: 128-bit vector kernels when the shapes allow, scalar kernels otherwise ------------------------------
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool decoder_vec_ok(const float* emb, int64_t emb_ld, int d, bool has_rel, const float* rel, const float* inv_rel, int sides) {
+    return (d % 8 == 0) && (emb_ld % 4 == 0) && al16(emb) && (!has_rel || (al16(rel) && (sides == 1 || al16(inv_rel))));
+}
+
+mb_status launch_prep(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+                      int64_t CN, int d, int decoder, int sides, const int64_t* dst_negs, const int64_t* src_negs, float* A /*[sides][Bp][d] or null*/,
+                      float* pos /*[sides][Bp]*/, void* A_hi, void* A_lo /*[sides][Bp][d] or null*/, float* Neg /*[sides][CN][d] or null*/,
+                      void* Neg_hi, void* Neg_lo, cudaStream_t st) {
+    const bool has_rel = (cols == 3) && (decoder != MB_DECODER_DOT) && rel != nullptr;
+    const int dec = has_rel ? decoder : MB_DECODER_DOT;
+    const bool vec_ok = decoder_vec_ok(emb, emb_ld, d, has_rel, rel, inv_rel, sides);
+    if (vec_ok) {
+        vec::PrepArgs a;
+        a.emb = emb;
+        a.emb_ld = emb_ld;
+        a.edges = edges;
+        a.cols = cols;
+        a.rel = rel;
+        a.inv_rel = inv_rel;
+        a.B = B;
+        a.Bp = Bp;
+        a.CN = CN;
+        a.d = d;
+        a.decoder = dec;
+        a.sides = sides;
+        a.negs[0] = dst_negs;
+        a.negs[1] = src_negs;
+        for (int s = 0; s < 2; s++) {
+            const bool on = s < sides;
+            a.A[s] = (on && A) ? A + s * Bp * d : nullptr;
+            a.pos[s] = on ? pos + s * Bp : nullptr;
+            a.A_hi[s] = (on && A_hi) ? (__nv_bfloat16*)A_hi + s * Bp * d : nullptr;
+            a.A_lo[s] = (on && A_lo) ? (__nv_bfloat16*)A_lo + s * Bp * d : nullptr;
+            a.Neg[s] = (on && Neg) ? Neg + s * CN * d : nullptr;
+            a.Neg_hi[s] = (on && Neg_hi) ? (__nv_bfloat16*)Neg_hi + s * CN * d : nullptr;
+            a.Neg_lo[s] = (on && Neg_lo) ? (__nv_bfloat16*)Neg_lo + s * CN * d : nullptr;
+        }
+        int grid = warp_grid(Bp + sides * CN);
+        if (dec == MB_DECODER_COMPLEX)
+            vec::prep_kernel<MB_DECODER_COMPLEX><<<grid, vec::kThreads, 0, st>>>(a);
+        else if (dec == MB_DECODER_DISTMULT)
+            vec::prep_kernel<MB_DECODER_DISTMULT><<<grid, vec::kThreads, 0, st>>>(a);
+        else
+            vec::prep_kernel<MB_DECODER_DOT><<<grid, vec::kThreads, 0, st>>>(a);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
+    // scalar fallback needs the fp32 adjusted rows
+    MB_TRY(launch_edge_prep(emb, emb_ld, edges, cols, rel, sides == 2 ? inv_rel : nullptr, B, Bp, d, decoder, A, sides == 2 ? A + Bp * d : nullptr, pos,
+                            sides == 2 ? pos + Bp : nullptr, A_hi, A_lo, (A_hi && sides == 2) ? (void*)((__nv_bfloat16*)A_hi + Bp * d) : nullptr,
+                            (A_lo && sides == 2) ? (void*)((__nv_bfloat16*)A_lo + Bp * d) : nullptr, st));
+    for (int s = 0; s < sides; s++) {
+        MB_TRY(launch_gather_split(emb, emb_ld, s == 0 ? dst_negs : src_negs, CN, d, Neg ? Neg + s * CN * d : nullptr,
+                                   Neg_hi ? (void*)((__nv_bfloat16*)Neg_hi + s * CN * d) : nullptr,
+                                   Neg_lo ? (void*)((__nv_bfloat16*)Neg_lo + s * CN * d) : nullptr, st));
+    }
+    return MB_OK;
+}
+
+// S -> G (fp32, may be in place or null) and/or bf16 hi/lo
+mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w,
+                      cudaStream_t st) {
+    if (rows == 0) return MB_OK;
+    if ((N % 4 == 0) && N <= 1024 && al16(S) && (!G || al16(G))) {
+        vec::LossVArgs a{S, G, pos, gpos, row_loss, (__nv_bfloat16*)G_hi, (__nv_bfloat16*)G_lo, rows, N, w};
+        int grid = warp_grid(rows);
+        if (N <= 256)
+            vec::loss_kernel<2><<<grid, vec::kThreads, 0, st>>>(a);
+        else
+            vec::loss_kernel<8><<<grid, vec::kThreads, 0, st>>>(a);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
+    // scalar kernel works in place on an fp32 buffer
+    if (G == nullptr) {
+        set_error("launch_loss: scalar fallback needs an fp32 gradient buffer");
+        return MB_ERR_INVALID;
+    }
+    if (G != S) MB_CUDA_TRY(cudaMemcpyAsync(G, S, sizeof(float) * rows * N, cudaMemcpyDeviceToDevice, st));
+    return launch_loss_grad(G, pos, gpos, row_loss, G_hi, G_lo, rows, N, w, st);
+}
+
+mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+                          int d, int decoder, int sides, const float* A /*[sides][Bp][d], scalar path only*/, const float* dA, const float* gpos,
+                          float* gcat, float* drel /*[sides][B][d] or null*/, cudaStream_t st) {
+    if (B == 0) return MB_OK;
+    const bool has_rel = (cols == 3) && (decoder != MB_DECODER_DOT) && rel != nullptr;
+    const int dec = has_rel ? decoder : MB_DECODER_DOT;
+    const bool vec_ok = decoder_vec_ok(emb, emb_ld, d, has_rel, rel, inv_rel, sides);
+    if (vec_ok) {
+        vec::EdgeBwdVArgs a;
+        a.emb = emb;
+        a.emb_ld = emb_ld;
+        a.edges = edges;
+        a.cols = cols;
+        a.rel = rel;
+        a.inv_rel = inv_rel;
+        a.B = B;
+        a.Bp = Bp;
+        a.d = d;
+        a.sides = sides;
+        for (int s = 0; s < 2; s++) {
+            const bool on = s < sides;
+            a.dA[s] = on ? dA + s * Bp * d : nullptr;
+            a.gpos[s] = on ? gpos + s * Bp : nullptr;
+            a.drel[s] = (on && drel && has_rel) ? drel + s * B * d : nullptr;
+        }
+        a.gcat = gcat;
+        int grid = warp_grid(B);
+        if (dec == MB_DECODER_COMPLEX)
+            vec::edge_backward_kernel<MB_DECODER_COMPLEX><<<grid, vec::kThreads, 0, st>>>(a);
+        else if (dec == MB_DECODER_DISTMULT)
+            vec::edge_backward_kernel<MB_DECODER_DISTMULT><<<grid, vec::kThreads, 0, st>>>(a);
+        else
+            vec::edge_backward_kernel<MB_DECODER_DOT><<<grid, vec::kThreads, 0, st>>>(a);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
+    return launch_edge_backward(emb, emb_ld, edges, cols, rel, sides == 2 ? inv_rel : nullptr, B, d, decoder, A, sides == 2 ? A + Bp * d : nullptr, dA,
+                                sides == 2 ? dA + Bp * d : nullptr, gpos, sides == 2 ? gpos + Bp : nullptr, gcat, (drel && has_rel) ? drel : nullptr,
+                                (drel && has_rel && sides == 2) ? drel + B * d : nullptr, st);
+}
+
+mb_status launch_seg_reduce(int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
+                            const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
+                            const int64_t* ids, float lr, cudaStream_t st) {
+    if (n_seg == 0) return MB_OK;
+    const bool vec_ok = (d % 4 == 0) && d <= 512 && al16(rows) && (!out || (al16(out) && out_ld % 4 == 0)) && (!state || (al16(state) && state_ld % 4 == 0)) &&
+                        (!delta_e || (al16(delta_e) && al16(delta_s))) && (!table || (al16(table) && al16(state_table) && ld % 4 == 0));
+    if (!vec_ok)
+        return launch_segment_reduce(mode, rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, lr, st);
+    vec::SegVArgs a{rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, -lr};
+    int grid = warp_grid(n_seg);
+#define MB_SEG(MODE)                                                                      \
+    if (d <= 128)                                                                         \
+        vec::segment_reduce_kernel<MODE, 1><<<grid, vec::kThreads, 0, st>>>(a);           \
+    else                                                                                  \
+        vec::segment_reduce_kernel<MODE, 4><<<grid, vec::kThreads, 0, st>>>(a);
+    if (mode == 0) {
+        MB_SEG(0)
+    } else if (mode == 1) {
+        MB_SEG(1)
+    } else {
+        MB_SEG(2)
+    }
+#undef MB_SEG
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

@@ -37,6 +37,10 @@ struct FusedNodeCorrupt : public torch::autograd::Function<FusedNodeCorrupt> {
     static torch::autograd::variable_list forward(torch::autograd::AutogradContext* ctx, torch::Tensor node_embeddings, torch::Tensor relations,
                                                   torch::Tensor inverse_relations, torch::Tensor edges, torch::Tensor dst_negs, torch::Tensor src_negs,
                                                   int64_t decoder_kind, bool use_inverse, int64_t precision) {
+        auto undef = [](const torch::Tensor& t) { return (t.defined() && t.numel() > 0) ? t : torch::Tensor(); };
+        relations = undef(relations);
+        inverse_relations = undef(inverse_relations);
+        src_negs = undef(src_negs);
         auto dec = std::make_shared<EdgeDecoder>();
         dec->decoder_kind_ = (int)decoder_kind;
         dec->relations_ = relations;
@@ -56,7 +60,8 @@ struct FusedNodeCorrupt : public torch::autograd::Function<FusedNodeCorrupt> {
         mb_throw_on_error(mb_decoder_forward(mb_context_for(emb.device()), &b, emb.data_ptr<float>(), emb.stride(0), (int)precision, pos.data_ptr<float>(),
                                              neg.data_ptr<float>(), inverse ? inv_pos.data_ptr<float>() : nullptr,
                                              inverse ? inv_neg.data_ptr<float>() : nullptr, mb_current_stream(emb.device())));
-        ctx->save_for_backward({emb, relations, inverse_relations, edges, dst_negs, src_negs});
+        auto ph = [&](const torch::Tensor& t, torch::Dtype dt) { return t.defined() ? t : torch::empty({0}, emb.options().dtype(dt)); };
+        ctx->save_for_backward({emb, ph(relations, torch::kFloat32), ph(inverse_relations, torch::kFloat32), edges, dst_negs, ph(src_negs, torch::kInt64)});
         ctx->saved_data["kind"] = decoder_kind;
         ctx->saved_data["inverse"] = use_inverse;
         ctx->saved_data["precision"] = precision;
@@ -69,7 +74,9 @@ struct FusedNodeCorrupt : public torch::autograd::Function<FusedNodeCorrupt> {
 
     static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx, torch::autograd::variable_list grads) {
         auto saved = ctx->get_saved_variables();
-        auto emb = saved[0], relations = saved[1], inverse_relations = saved[2], edges = saved[3], dst_negs = saved[4], src_negs = saved[5];
+        auto undef = [](const torch::Tensor& t) { return (t.defined() && t.numel() > 0) ? t : torch::Tensor(); };
+        auto emb = saved[0], relations = undef(saved[1]), inverse_relations = undef(saved[2]), edges = saved[3], dst_negs = saved[4],
+             src_negs = undef(saved[5]);
         auto dec = std::make_shared<EdgeDecoder>();
         dec->decoder_kind_ = (int)ctx->saved_data["kind"].toInt();
         dec->relations_ = relations;
@@ -92,6 +99,7 @@ struct FusedNodeCorrupt : public torch::autograd::Function<FusedNodeCorrupt> {
         torch::Tensor grad_rel, grad_inv;
         if (b.rel) grad_rel = torch::empty_like(relations);
         if (inverse) grad_inv = torch::empty_like(inverse_relations);
+        else if (inverse_relations.defined()) grad_inv = torch::zeros_like(inverse_relations);
         mb_throw_on_error(mb_decoder_backward(mb_context_for(emb.device()), &b, emb.data_ptr<float>(), emb.stride(0), (int)ctx->saved_data["precision"].toInt(),
                                               gpos.data_ptr<float>(), gneg.data_ptr<float>(), inverse ? gipos.data_ptr<float>() : nullptr,
                                               inverse ? gineg.data_ptr<float>() : nullptr, grad_emb.data_ptr<float>(),
@@ -132,8 +140,10 @@ torch::Tensor EdgeDecoder::compute_scores(torch::Tensor src, torch::Tensor dst) 
     auto emb = torch::cat({src, negs_flat}, 0);
     auto edges = torch::stack({torch::arange(U0, src.options().dtype(torch::kInt64)), torch::arange(U0, src.options().dtype(torch::kInt64))}, 1);
     auto neg_ids = (torch::arange(negs_flat.size(0), src.options().dtype(torch::kInt64)) + U0).reshape({dst.size(0), dst.size(1)});
-    auto out = FusedNodeCorrupt::apply(emb, torch::Tensor(), torch::Tensor(), edges.contiguous(), neg_ids.contiguous(), torch::Tensor(),
-                                       (int64_t)MB_DECODER_DOT, false, (int64_t)mb_default_precision());
+    auto none_f = torch::empty({0}, src.options());
+    auto none_i = torch::empty({0}, src.options().dtype(torch::kInt64));
+    auto out = FusedNodeCorrupt::apply(emb, none_f, none_f, edges.contiguous(), neg_ids.contiguous(), none_i, (int64_t)MB_DECODER_DOT, false,
+                                       (int64_t)mb_default_precision());
     return out[1];
 }
 
@@ -181,10 +191,12 @@ std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> node_corr
     auto dn = dst_negs.to(torch::kInt64).contiguous();
     auto sn = src_negs.defined() ? src_negs.to(torch::kInt64).contiguous() : torch::Tensor();
     bool has_rel = edges.size(1) == 3;
-    auto out = FusedNodeCorrupt::apply(node_embeddings, has_rel ? decoder->relations_ : torch::Tensor(),
-                                       (has_rel && decoder->use_inverse_relations_) ? decoder->inverse_relations_ : torch::Tensor(), edges, dn, sn,
-                                       (int64_t)(has_rel ? decoder->decoder_kind_ : MB_DECODER_DOT), decoder->use_inverse_relations_,
-                                       (int64_t)mb_default_precision());
+    auto none_f = torch::empty({0}, node_embeddings.options());
+    auto none_i = torch::empty({0}, dn.options());
+    auto out = FusedNodeCorrupt::apply(node_embeddings, has_rel ? decoder->relations_ : none_f,
+                                       (has_rel && decoder->use_inverse_relations_) ? decoder->inverse_relations_ : none_f, edges, dn,
+                                       sn.defined() ? sn : none_i, (int64_t)(has_rel ? decoder->decoder_kind_ : MB_DECODER_DOT),
+                                       decoder->use_inverse_relations_, (int64_t)mb_default_precision());
     torch::Tensor inv_pos = out[2].numel() > 0 || (has_rel && decoder->use_inverse_relations_ && sn.defined()) ? out[2] : torch::Tensor();
     torch::Tensor inv_neg = out[3].numel() > 0 || (has_rel && decoder->use_inverse_relations_ && sn.defined()) ? out[3] : torch::Tensor();
     return std::forward_as_tuple(out[0], out[1], inv_pos, inv_neg);

@@ -36,7 +36,11 @@ def _need_cuda(*ts):
 
 def _rowmajor(t: torch.Tensor, name: str) -> int:
     """leading dimension (elements) of a 2-D tensor whose rows are contiguous"""
-    if t.dim() != 2 or (t.size(1) > 1 and t.stride(1) != 1):
+    if t.dim() != 2:
+        raise MariusB200Error(_INVALID, f"{name} must be 2-D with contiguous rows")
+    if t.numel() == 0:
+        return max(t.size(1), 1)
+    if t.size(1) > 1 and t.stride(1) != 1:
         raise MariusB200Error(_INVALID, f"{name} must be 2-D with contiguous rows")
     return t.stride(0) if t.size(0) > 1 else max(t.size(1), t.stride(0))
 
