@@ -57,7 +57,8 @@ struct mb_context {
     float* h_loss = nullptr;
     size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
     cudaStream_t side = nullptr;          // index plans (slot / relation sorts) overlap the forward pass here
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side2 = nullptr;         // the dNeg contraction runs here, concurrently with dA + edge_backward
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     // optional per-stage CUDA-event timing (mb_profile_*): events are recorded on the caller's stream
     bool profiling = false;
     struct Span {
@@ -119,6 +120,17 @@ struct StageTimer {
         }
     }
 };
+
+// tcgen05 tile configuration (gemm_tc.cu): 256 = BLOCK_N 256 / BLOCK_K 32 / 4 stages (default), 2560 = 256 / 64 / 2, 128 = 128 / 64 / 3.
+// MB_TC_CFG overrides it for A/B measurements.
+static int tc_tile_config() {
+    static int cfg = [] {
+        const char* e = getenv("MB_TC_CFG");
+        int v = e ? atoi(e) : 256;
+        return (v == 256 || v == 2560 || v == 128) ? v : 256;
+    }();
+    return cfg;
+}
 
 static int bits_for(uint64_t max_value) {
     int b = 1;
@@ -207,8 +219,8 @@ static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
 }
 
 // forward: adjusted rows A, positive scores, negative rows, score GEMM.  S0/S1 are the score outputs per side ([Bp,N] each).
-static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, int precision, float* pos, float* S0,
-                             float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false) {
+static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, const int64_t* row_map, int precision,
+                             float* pos, float* S0, float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false) {
     const int d = (int)p.d;
     const int64_t a_half = p.sides * p.Bp * d;  // hi block then lo block, each [sides][Bp][d]
     const int64_t n_half = p.sides * p.CN * d;
@@ -216,7 +228,7 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
         StageTimer tm(ctx, ST_PREP, st);
         // the fp32 adjusted rows are only read by the SIMT GEMM and by the scalar (general-d) backward kernel
         const bool need_A = !p.use_tc || !decoder_vec_ok(emb, emb_ld, d, p.has_rel, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.sides);
-        MB_TRY(launch_prep(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, p.CN, d, b->decoder, p.sides,
+        MB_TRY(launch_prep(emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, p.CN, d, b->decoder, p.sides,
                            b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, need_A ? p.A : nullptr, pos, p.use_tc ? (void*)p.A_hl : nullptr,
                            p.use_tc ? (void*)(p.A_hl + a_half) : nullptr, p.NegE, p.use_tc ? (void*)p.Neg_hl : nullptr,
                            p.use_tc ? (void*)(p.Neg_hl + n_half) : nullptr, st));
@@ -232,7 +244,7 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
         int64_t aoff = (int64_t)l * p.Bp * d, noff = (int64_t)l * p.CN * d;
         if (p.use_tc) {
             MB_TRY(gemm_tc(p.A_hl + aoff, p.A_hl + a_half + aoff, d, p.Bc * d, false, p.Neg_hl + noff, p.Neg_hl + n_half + noff, d, (int64_t)p.N * d,
-                           false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, 256, st));
+                           false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, tc_tile_config(), st));
         } else {
             MB_TRY(gemm_simt(p.A + aoff, d, 1, p.Bc * d, p.NegE + noff, 1, d, (int64_t)p.N * d, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, st));
         }
@@ -296,15 +308,24 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     }
 
     const float* emb = emb_in;
+    const int64_t* row_map = nullptr;
     if (fused) {
-        StageTimer tm(ctx, ST_GATHER, st);
-        // DataLoader::loadGPUParameters (dataloader.cpp:529-548): gather the unique rows; the state rows are read in place later
-        MB_TRY(gather_rows(table, ld, d, unique_ids, p.U, p.emb_u, d, st));
-        emb = p.emb_u;
-        emb_ld = d;
+        // DataLoader::loadGPUParameters (dataloader.cpp:529-548).  With the vector kernels the gather is fused away: prep / backward read
+        // table[unique_ids[local id]] directly (the table is not modified until the update at the end of the step, so this is the same
+        // snapshot the reference's gathered copy holds); the state rows are read in place by the update kernel.
+        if (decoder_vec_ok(table, ld, d, p.has_rel, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.sides)) {
+            emb = table;
+            emb_ld = ld;
+            row_map = unique_ids;
+        } else {
+            StageTimer tm(ctx, ST_GATHER, st);
+            MB_TRY(gather_rows(table, ld, d, unique_ids, p.U, p.emb_u, d, st));
+            emb = p.emb_u;
+            emb_ld = d;
+        }
     }
 
-    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr));
+    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, row_map, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr));
 
     // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
     const int64_t rows = p.sides * p.Bp;
@@ -333,35 +354,47 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     }
     const int passes = precision == MB_PREC_BF16 ? 1 : 3;
     const int batches = p.sides * p.C;
+    const int tc_cfg = tc_tile_config();
+    bool dneg_forked = false;
     float* gneg = p.gcat + 2 * p.B * d;  // d dst_negs | d src_negs, [sides][C][N][d]
     if (p.Bc > 0) {
         const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
         {
+            // dNeg = G^T . A : independent of dA / edge_backward, so it runs on the second side stream; the tail wave of one persistent
+            // GEMM then overlaps the head of the other (each has only ~2.2 waves of tiles at B = 10k)
+            cudaStream_t s2 = overlap ? ctx->side2 : st;
+            if (overlap) {
+                MB_CUDA_TRY(cudaEventRecord(ctx->ev_fork2, st));
+                MB_CUDA_TRY(cudaStreamWaitEvent(s2, ctx->ev_fork2, 0));
+                dneg_forked = true;
+            }
+            StageTimer tm(ctx, ST_GEMM_DNEG, s2);
+            if (p.use_tc)
+                MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, true, p.A_hl, p.A_hl + a_half, d, p.Bc * d, true, gneg, d, (int64_t)p.N * d,
+                               p.N, d, (int)p.Bc, batches, passes, tc_cfg, s2));
+            else
+                MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, s2));
+            if (overlap) MB_CUDA_TRY(cudaEventRecord(ctx->ev_join2, s2));
+        }
+        {
             StageTimer tm(ctx, ST_GEMM_DA, st);  // dA = G . Neg
             if (p.use_tc)
                 MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, false, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, true, p.dA, d,
-                               p.Bc * d, (int)p.Bc, d, p.N, batches, passes, 256, st));
+                               p.Bc * d, (int)p.Bc, d, p.N, batches, passes, tc_cfg, st));
             else
                 MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
-        }
-        {
-            StageTimer tm(ctx, ST_GEMM_DNEG, st);  // dNeg = G^T . A
-            if (p.use_tc)
-                MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, true, p.A_hl, p.A_hl + a_half, d, p.Bc * d, true, gneg, d, (int64_t)p.N * d,
-                               p.N, d, (int)p.Bc, batches, passes, 256, st));
-            else
-                MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, st));
         }
     } else {
         MB_CUDA_TRY(cudaMemsetAsync(gneg, 0, sizeof(float) * 2 * p.CN * d, st));
     }
     {
         StageTimer tm(ctx, ST_EDGE_BWD, st);
-        MB_TRY(launch_edge_bwd(emb, emb_ld, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, p.sides, p.A, p.dA,
+        MB_TRY(launch_edge_bwd(emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, p.sides, p.A, p.dA,
                                p.gpos, p.gcat, p.has_rel ? p.drel : nullptr, st));
     }
-    // ---- join: the slot / relation plans are needed from here on
+    // ---- join: the slot / relation plans and the negative-row gradients are needed from here on
     if (overlap) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (dneg_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     {
         // node gradients: segmented sum over sorted slots (+ Adagrad)
         StageTimer tm(ctx, ST_UPDATE, st);
@@ -377,11 +410,8 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     if (need_rel) {
         // relation gradients: segmented sum of per-edge gradients by relation id
         StageTimer tm(ctx, ST_REL_GRAD, st);
-        if (rel_grad)
-            MB_TRY(launch_seg_reduce(0, p.drel, rvals, p.roffsets, p.R, d, rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
-        if (inv_rel_grad && p.sides == 2)
-            MB_TRY(launch_seg_reduce(0, p.drel + p.B * d, rvals, p.roffsets, p.R, d, inv_rel_grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0,
-                                     nullptr, lr, st));
+        MB_TRY(launch_rel_reduce(p.drel, p.sides == 2 ? p.drel + p.B * d : nullptr, rel_grad, p.sides == 2 ? inv_rel_grad : nullptr, rvals, p.roffsets, p.R,
+                                 d, st));
     }
     return MB_OK;
 }
@@ -411,6 +441,9 @@ mb_status mb_create(int device, mb_context** out) {
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -432,6 +465,9 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->h_sneg) cudaFree(ctx->h_sneg);
     if (ctx->h_loss) cudaFree(ctx->h_loss);
     if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto& sp : ctx->spans) {
@@ -570,7 +606,7 @@ mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float
         p.layout(place, false, false, false);
     }
     // pos / inv_pos are separate user buffers: stage them in the workspace layout [sides][Bp] and copy out
-    MB_TRY(run_forward(ctx, p, batch, emb, emb_ld, precision, p.pos, neg, inv_neg, false, st));
+    MB_TRY(run_forward(ctx, p, batch, emb, emb_ld, nullptr, precision, p.pos, neg, inv_neg, false, st));
     MB_CUDA_TRY(cudaMemcpyAsync(pos, p.pos, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
     if (p.sides == 2) MB_CUDA_TRY(cudaMemcpyAsync(inv_pos, p.pos + p.Bp, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
     return MB_OK;

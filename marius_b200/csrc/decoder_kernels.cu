@@ -496,7 +496,7 @@ bool decoder_vec_ok(const float* emb, int64_t emb_ld, int d, bool has_rel, const
     return (d % 8 == 0) && (emb_ld % 4 == 0) && al16(emb) && (!has_rel || (al16(rel) && (sides == 1 || al16(inv_rel))));
 }
 
-mb_status launch_prep(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+mb_status launch_prep(const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                       int64_t CN, int d, int decoder, int sides, const int64_t* dst_negs, const int64_t* src_negs, float* A /*[sides][Bp][d] or null*/,
                       float* pos /*[sides][Bp]*/, void* A_hi, void* A_lo /*[sides][Bp][d] or null*/, float* Neg /*[sides][CN][d] or null*/,
                       void* Neg_hi, void* Neg_lo, cudaStream_t st) {
@@ -507,6 +507,7 @@ mb_status launch_prep(const float* emb, int64_t emb_ld, const int64_t* edges, in
         vec::PrepArgs a;
         a.emb = emb;
         a.emb_ld = emb_ld;
+        a.row_map = row_map;
         a.edges = edges;
         a.cols = cols;
         a.rel = rel;
@@ -539,7 +540,11 @@ mb_status launch_prep(const float* emb, int64_t emb_ld, const int64_t* edges, in
         MB_LAUNCH_CHECK();
         return MB_OK;
     }
-    // scalar fallback needs the fp32 adjusted rows
+    // scalar fallback needs the fp32 adjusted rows and a batch-local embedding matrix
+    if (row_map != nullptr) {
+        set_error("launch_prep: row_map requires the vector path");
+        return MB_ERR_INVALID;
+    }
     MB_TRY(launch_edge_prep(emb, emb_ld, edges, cols, rel, sides == 2 ? inv_rel : nullptr, B, Bp, d, decoder, A, sides == 2 ? A + Bp * d : nullptr, pos,
                             sides == 2 ? pos + Bp : nullptr, A_hi, A_lo, (A_hi && sides == 2) ? (void*)((__nv_bfloat16*)A_hi + Bp * d) : nullptr,
                             (A_lo && sides == 2) ? (void*)((__nv_bfloat16*)A_lo + Bp * d) : nullptr, st));
@@ -574,7 +579,7 @@ mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, f
     return launch_loss_grad(G, pos, gpos, row_loss, G_hi, G_lo, rows, N, w, st);
 }
 
-mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                           int d, int decoder, int sides, const float* A /*[sides][Bp][d], scalar path only*/, const float* dA, const float* gpos,
                           float* gcat, float* drel /*[sides][B][d] or null*/, cudaStream_t st) {
     if (B == 0) return MB_OK;
@@ -585,6 +590,7 @@ mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* edges
         vec::EdgeBwdVArgs a;
         a.emb = emb;
         a.emb_ld = emb_ld;
+        a.row_map = row_map;
         a.edges = edges;
         a.cols = cols;
         a.rel = rel;
@@ -609,6 +615,10 @@ mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* edges
             vec::edge_backward_kernel<MB_DECODER_DOT><<<grid, vec::kThreads, 0, st>>>(a);
         MB_LAUNCH_CHECK();
         return MB_OK;
+    }
+    if (row_map != nullptr) {
+        set_error("launch_edge_bwd: row_map requires the vector path");
+        return MB_ERR_INVALID;
     }
     return launch_edge_backward(emb, emb_ld, edges, cols, rel, sides == 2 ? inv_rel : nullptr, B, d, decoder, A, sides == 2 ? A + Bp * d : nullptr, dA,
                                 sides == 2 ? dA + Bp * d : nullptr, gpos, sides == 2 ? gpos + Bp : nullptr, gcat, (drel && has_rel) ? drel : nullptr,
@@ -638,6 +648,44 @@ mb_status launch_seg_reduce(int mode, const float* rows, const uint32_t* slots, 
         MB_SEG(2)
     }
 #undef MB_SEG
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+// relation gradients: rel_grad[r] = sum of the per-edge gradients of relation r (both relation tables in one launch)
+mb_status launch_rel_reduce(const float* drel0, const float* drel1, float* out0, float* out1, const uint32_t* slots, const uint32_t* offsets, int64_t R,
+                            int d, cudaStream_t st) {
+    if (R == 0) return MB_OK;
+    const int n_out = (out0 ? 1 : 0) + (out1 ? 1 : 0);
+    if (n_out == 0) return MB_OK;
+    const bool vec_ok = (d % 4 == 0) && al16(drel0) && (!drel1 || al16(drel1)) && (!out0 || al16(out0)) && (!out1 || al16(out1));
+    if (!vec_ok) {
+        if (out0) MB_TRY(launch_segment_reduce(0, drel0, slots, offsets, R, d, out0, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0.f, st));
+        if (out1) MB_TRY(launch_segment_reduce(0, drel1, slots, offsets, R, d, out1, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0.f, st));
+        return MB_OK;
+    }
+    vec::SegColArgs a;
+    int k = 0;
+    if (out0) {
+        a.rows[k] = drel0;
+        a.out[k++] = out0;
+    }
+    if (out1) {
+        a.rows[k] = drel1;
+        a.out[k++] = out1;
+    }
+    if (k == 1) {
+        a.rows[1] = a.rows[0];
+        a.out[1] = a.out[0];
+    }
+    a.slots = slots;
+    a.offsets = offsets;
+    a.n_seg = R;
+    a.d = d;
+    a.out_ld = d;
+    const int ncb = ((d >> 2) + 31) >> 5;
+    dim3 grid((unsigned)warp_grid(R * ncb), (unsigned)k);
+    vec::segment_colsplit_kernel<<<grid, vec::kThreads, 0, st>>>(a);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

@@ -55,6 +55,7 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* l
 struct PrepArgs {
     const float* emb;
     int64_t emb_ld;
+    const int64_t* row_map;  // null: emb is the batch-local matrix; else emb is the table and row_map = unique ids (gather fused away)
     const int64_t* edges;
     int cols;
     const float* rel;      // null: no relation operator
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(kThreads) prep_kernel(PrepArgs a) {
             const int64_t q = t - a.Bp;
             const int side = q >= a.CN ? 1 : 0;
             const int64_t j = q - (int64_t)side * a.CN;
-            const float* src = a.emb + a.negs[side][j] * a.emb_ld;
+            const int64_t nid = a.negs[side][j];
+            const float* src = a.emb + (a.row_map ? a.row_map[nid] : nid) * a.emb_ld;
             for (int v = lane; v < dv; v += 32) {
                 float4 x = ld4(src, v);
                 if (a.Neg[side]) st4(a.Neg[side] + j * d, v, x);
@@ -102,7 +104,11 @@ __global__ void __launch_bounds__(kThreads) prep_kernel(PrepArgs a) {
             }
             continue;
         }
-        const int64_t si = a.edges[p * a.cols], ti = a.edges[p * a.cols + a.cols - 1];
+        int64_t si = a.edges[p * a.cols], ti = a.edges[p * a.cols + a.cols - 1];
+        if (a.row_map) {
+            si = a.row_map[si];
+            ti = a.row_map[ti];
+        }
         const float* src = a.emb + si * a.emb_ld;
         const float* dst = a.emb + ti * a.emb_ld;
         const int64_t rid = (DEC != MB_DECODER_DOT) ? a.edges[p * a.cols + 1] : 0;
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(kThreads) loss_kernel(LossVArgs a) {
 struct EdgeBwdVArgs {
     const float* emb;
     int64_t emb_ld;
+    const int64_t* row_map;
     const int64_t* edges;
     int cols;
     const float* rel;
@@ -247,7 +254,11 @@ __global__ void __launch_bounds__(kThreads) edge_backward_kernel(EdgeBwdVArgs a)
     const int d = a.d, dv = d >> 2, hv = d >> 3;
     const bool inverse = a.sides == 2;
     for (int64_t i = warp0; i < a.B; i += nwarps) {
-        const int64_t si = a.edges[i * a.cols], ti = a.edges[i * a.cols + a.cols - 1];
+        int64_t si = a.edges[i * a.cols], ti = a.edges[i * a.cols + a.cols - 1];
+        if (a.row_map) {
+            si = a.row_map[si];
+            ti = a.row_map[ti];
+        }
         const float* src = a.emb + si * a.emb_ld;
         const float* dst = a.emb + ti * a.emb_ld;
         const int64_t rid = (DEC != MB_DECODER_DOT) ? a.edges[i * a.cols + 1] : 0;
@@ -398,6 +409,44 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
                 st_stream(reinterpret_cast<float4*>(erow) + v, addrn4(e[c], de));
                 st_stream(reinterpret_cast<float4*>(srow) + v, sn);
             }
+        }
+    }
+}
+
+// Plain segmented row sum with the columns split over warps: warp = (segment, 32-float4 column block); blockIdx.y selects one of
+// up to two (rows, out) pairs (the two relation tables).  Used where segments are few and long (relation gradients).
+struct SegColArgs {
+    const float* rows[2];
+    float* out[2];
+    const uint32_t* slots;
+    const uint32_t* offsets;
+    int64_t n_seg;
+    int d;
+    int64_t out_ld;
+};
+
+__global__ void __launch_bounds__(kThreads) segment_colsplit_kernel(SegColArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int dv = a.d >> 2;
+    const int ncb = (dv + 31) >> 5;
+    const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const float* rows = a.rows[blockIdx.y];
+    float* out = a.out[blockIdx.y];
+    for (int64_t w = warp0; w < a.n_seg * ncb; w += nwarps) {
+        const int64_t u = w / ncb;
+        const int v = (int)(w - u * ncb) * 32 + lane;
+        const uint32_t beg = a.offsets[u], end = a.offsets[u + 1];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < dv) {
+            uint32_t q = beg;
+            for (; q + 1 < end; q += 2) {  // two rows in flight
+                float4 x0 = ld_f4(reinterpret_cast<const float4*>(rows + (int64_t)a.slots[q] * a.d) + v);
+                float4 x1 = ld_f4(reinterpret_cast<const float4*>(rows + (int64_t)a.slots[q + 1] * a.d) + v);
+                acc = addrn4(addrn4(acc, x0), x1);
+            }
+            if (q < end) acc = addrn4(acc, ld_f4(reinterpret_cast<const float4*>(rows + (int64_t)a.slots[q] * a.d) + v));
+            st4(out + u * a.out_ld, v, acc);
         }
     }
 }

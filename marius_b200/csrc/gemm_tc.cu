@@ -27,9 +27,10 @@ namespace mb {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                      // bf16 elements = one 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+// BLOCK_K (template parameter, bf16 elements per k-block): 64 -> K-major tiles are SWIZZLE_128B rows, 32 -> SWIZZLE_64B rows
+// (half the bytes per stage => twice the pipeline depth in the same shared memory).  MN-major tiles are always SWIZZLE_128B
+// slabs of 64 MN-elements x BLOCK_K k-rows.
 constexpr int kTcThreads = 192;
 constexpr long long kWaitTimeoutCycles = 4000000000ll;  // ~2 s: trap instead of hanging the GPU
 
@@ -124,13 +125,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- descriptors ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3fff);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
     return d;
 }
 // Instruction descriptor (InstrDescriptor): c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), a_major [15], b_major [16],
@@ -140,19 +141,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool 
            ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int BLOCK_K, int STAGES>
 struct SmemLayout {
+    static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
                const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
-    using L = SmemLayout<BLOCK_N, STAGES>;
+    using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+    constexpr int A_TILE_BYTES = L::A_TILE_BYTES;
     constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered fp32 accumulator: 256 or 512 columns (power of two)
     static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "TMEM columns must be a power of two");
     extern __shared__ uint8_t smem_raw[];
@@ -245,10 +248,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused (=16 B); k-step = +32 B inside the swizzle span.
+            // K-major: rows of BLOCK_K*2 bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row groups SBO = 8 rows apart, LBO unused
+            //          (=16 B); k-step = +32 B inside the swizzle span.
             // MN-major SW128: 64-element MN slabs BLOCK_K*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO); k-step = +2048 B.
-            constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16, A_SBO = 1024, A_KSTEP = A_MN ? 2048 : 32;
-            constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16, B_SBO = 1024, B_KSTEP = B_MN ? 2048 : 32;
+            constexpr uint32_t K_ROW_BYTES = BLOCK_K * 2;
+            constexpr uint32_t K_LAYOUT = (K_ROW_BYTES == 128) ? 2u : 4u;
+            constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16, A_SBO = A_MN ? 1024 : 8 * K_ROW_BYTES, A_KSTEP = A_MN ? 2048 : 32;
+            constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16, B_SBO = B_MN ? 1024 : 8 * K_ROW_BYTES, B_KSTEP = B_MN ? 2048 : 32;
+            constexpr uint32_t A_LAYOUT = A_MN ? 2u : K_LAYOUT, B_LAYOUT = B_MN ? 2u : K_LAYOUT;
             int stage = 0;
             uint32_t phase = 0;
             int local_tile = 0;
@@ -276,8 +283,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         const uint32_t sa = (prod == 2) ? sA_lo : sA_hi;  // hi.hi, hi.lo, lo.hi
                         const uint32_t sb = (prod == 1) ? sB_lo : sB_hi;
                         for (int ks = 0; ks < ksteps; ks++) {
-                            uint64_t adesc = make_smem_desc(sa + ks * A_KSTEP, A_LBO, A_SBO);
-                            uint64_t bdesc = make_smem_desc(sb + ks * B_KSTEP, B_LBO, B_SBO);
+                            uint64_t adesc = make_smem_desc(sa + ks * A_KSTEP, A_LBO, A_SBO, A_LAYOUT);
+                            uint64_t bdesc = make_smem_desc(sb + ks * B_KSTEP, B_LBO, B_SBO, B_LAYOUT);
                             umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
                             accumulate = 1;
                         }
@@ -359,9 +366,9 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 3-D bf16 map: dims {inner, rows, batches}; box {64, box_rows, 1}; SWIZZLE_128B; zero OOB fill.
+// 3-D bf16 map: dims {inner, rows, batches}; box {box_inner (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B), box_rows, 1}; zero OOB fill.
 mb_status make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches, uint64_t row_stride_elems,
-                   uint64_t batch_stride_elems, uint32_t box_rows) {
+                   uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_inner = 64) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -370,14 +377,15 @@ mb_status make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
     cuuint64_t dims[3] = {inner, rows, batches};
     cuuint64_t strides[2] = {row_stride_elems * 2, batch_stride_elems * 2};
     if (batches == 1) strides[1] = strides[0] * rows;
-    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t box[3] = {box_inner, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || (strides[0] & 15u) || (strides[1] & 15u)) {
         set_error("gemm_tc: operand not 16-byte aligned / stride not a multiple of 16 bytes");
         return MB_ERR_INVALID;
     }
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    box_inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
         return MB_ERR_CUDA;
@@ -385,11 +393,11 @@ mb_status make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
     return MB_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN>
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
 mb_status launch_variant(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p,
                          cudaStream_t st) {
-    using L = SmemLayout<BLOCK_N, STAGES>;
-    auto kern = gemm_tc_kernel<BLOCK_N, STAGES, A_MN, B_MN>;
+    using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+    auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, A_MN, B_MN>;
     static bool attr_set = false;
     if (!attr_set) {
         MB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -421,20 +429,23 @@ mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, 
     }
     if (!A_lo || !B_lo) passes = 1;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    const uint32_t bn = (uint32_t)block_n;
+    // tile configurations: block_n 256 -> (BLOCK_N 256, BLOCK_K 32, 4 stages) [default], 2560 -> (256, 64, 2), 128 -> (128, 64, 3)
+    const int bk = (block_n == 256) ? 32 : 64;
+    const int bn_real = (block_n == 2560) ? 256 : block_n;
+    const uint32_t bn = (uint32_t)bn_real;
     if (!a_mn) {
-        MB_TRY(make_map(&ma_hi, A_hi, K, M, batches, lda, sAb, BLOCK_M));
-        if (passes == 3) MB_TRY(make_map(&ma_lo, A_lo, K, M, batches, lda, sAb, BLOCK_M));
+        MB_TRY(make_map(&ma_hi, A_hi, K, M, batches, lda, sAb, BLOCK_M, bk));
+        if (passes == 3) MB_TRY(make_map(&ma_lo, A_lo, K, M, batches, lda, sAb, BLOCK_M, bk));
     } else {
-        MB_TRY(make_map(&ma_hi, A_hi, M, K, batches, lda, sAb, BLOCK_K));
-        if (passes == 3) MB_TRY(make_map(&ma_lo, A_lo, M, K, batches, lda, sAb, BLOCK_K));
+        MB_TRY(make_map(&ma_hi, A_hi, M, K, batches, lda, sAb, bk));
+        if (passes == 3) MB_TRY(make_map(&ma_lo, A_lo, M, K, batches, lda, sAb, bk));
     }
     if (!b_mn) {
-        MB_TRY(make_map(&mb_hi, B_hi, K, N, batches, ldb, sBb, bn));
-        if (passes == 3) MB_TRY(make_map(&mb_lo, B_lo, K, N, batches, ldb, sBb, bn));
+        MB_TRY(make_map(&mb_hi, B_hi, K, N, batches, ldb, sBb, bn, bk));
+        if (passes == 3) MB_TRY(make_map(&mb_lo, B_lo, K, N, batches, ldb, sBb, bn, bk));
     } else {
-        MB_TRY(make_map(&mb_hi, B_hi, N, K, batches, ldb, sBb, BLOCK_K));
-        if (passes == 3) MB_TRY(make_map(&mb_lo, B_lo, N, K, batches, ldb, sBb, BLOCK_K));
+        MB_TRY(make_map(&mb_hi, B_hi, N, K, batches, ldb, sBb, bk));
+        if (passes == 3) MB_TRY(make_map(&mb_lo, B_lo, N, K, batches, ldb, sBb, bk));
     }
     if (passes != 3) {
         ma_lo = ma_hi;
@@ -450,16 +461,18 @@ mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, 
     p.batches = batches;
     p.passes = passes;
     p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-    p.n_tiles = (N + block_n - 1) / block_n;
-#define MB_TC_DISPATCH(BN, ST)                                                                          \
-    if (!a_mn && !b_mn) return launch_variant<BN, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st); \
-    if (!a_mn && b_mn) return launch_variant<BN, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);   \
-    if (a_mn && b_mn) return launch_variant<BN, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);     \
-    return launch_variant<BN, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
+    p.n_tiles = (N + bn_real - 1) / bn_real;
+#define MB_TC_DISPATCH(BN, BK, ST)                                                                          \
+    if (!a_mn && !b_mn) return launch_variant<BN, BK, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st); \
+    if (!a_mn && b_mn) return launch_variant<BN, BK, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);   \
+    if (a_mn && b_mn) return launch_variant<BN, BK, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);     \
+    return launch_variant<BN, BK, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
     if (block_n == 256) {
-        MB_TC_DISPATCH(256, 2)
+        MB_TC_DISPATCH(256, 32, 4)
+    } else if (block_n == 2560) {
+        MB_TC_DISPATCH(256, 64, 2)
     } else if (block_n == 128) {
-        MB_TC_DISPATCH(128, 3)
+        MB_TC_DISPATCH(128, 64, 3)
     }
 #undef MB_TC_DISPATCH
     set_error("gemm_tc: unsupported block_n");
