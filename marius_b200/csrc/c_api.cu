@@ -121,13 +121,14 @@ struct StageTimer {
     }
 };
 
-// tcgen05 tile configuration (gemm_tc.cu): 256 = BLOCK_N 256 / BLOCK_K 32 / 4 stages (default), 2560 = 256 / 64 / 2, 128 = 128 / 64 / 3.
+// tcgen05 tile configuration (gemm_tc.cu): 256 = BLOCK_N 256 / BLOCK_K 32 / 4 stages (default), 2560 = 256 / 64 / 2, 128 = 128 / 64 / 3,
+// 512 / 5120 = 2-CTA pairs (cta_group::2) with BLOCK_K 64 / 3 stages or BLOCK_K 32 / 6 stages.
 // MB_TC_CFG overrides it for A/B measurements.
 static int tc_tile_config() {
     static int cfg = [] {
         const char* e = getenv("MB_TC_CFG");
         int v = e ? atoi(e) : 256;
-        return (v == 256 || v == 2560 || v == 128) ? v : 256;
+        return (v == 256 || v == 2560 || v == 128 || v == 512 || v == 5120) ? v : 256;
     }();
     return cfg;
 }

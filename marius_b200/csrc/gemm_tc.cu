@@ -41,6 +41,7 @@ struct TcParams {
     int M, N, K, batches;
     int passes;       // 1 (hi.hi) or 3 (hi.hi + hi.lo + lo.hi)
     int m_tiles, n_tiles;
+    int debug_flags;  // bit 0: skip the epilogue's global stores (bandwidth experiments only; MB_TC_DEBUG)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -313,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
             float* drow = p.D + (int64_t)b * p.sDb + (int64_t)row * p.ldd;
-            const bool row_ok = row < p.M;
+            const bool row_ok = row < p.M && !(p.debug_flags & 1);
             const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15u) == 0) && ((p.sDb & 3) == 0);
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; c++) {
@@ -410,6 +411,294 @@ mb_status launch_variant(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
     return MB_OK;
 }
 
+
+// =================================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (one TPC) computes a 256 x 256 tile.  Each CTA stages ITS 128 rows
+// of A and ITS 128-column half of B; the leader's single thread issues tcgen05.mma.cta_group::2 (M = 256), the hardware
+// reads the B halves from both CTAs' shared memory and each CTA accumulates its 128 rows in its own TMEM.  Per SM and
+// k-block this moves 2/3 of the bytes of the 1-CTA kernel through L2 -> SMEM and through the SMEM read port (the 1-CTA
+// kernel needs ~96 B/clk of operand reads + ~62 B/clk of TMA fill against a 128 B/clk port: DESIGN.md 4).
+//   - TMA loads use .cta_group::2 and signal the LEADER's full barrier (peer bit 24 of the shared::cluster address cleared)
+//   - tcgen05.commit .multicast::cluster releases the stage in both CTAs and hands the accumulator to both epilogues
+//   - the peer's epilogue warps arrive remotely (mapa) on the leader's tmem-empty barrier
+// =================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `bar` (same offset) in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+template <int BLOCK_K, int STAGES>
+struct SmemLayout2 {
+    static constexpr int HALF_N = 128;                         // this CTA's share of the 256 tile columns
+    static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // this CTA's 128 rows of A
+    static constexpr int B_TILE_BYTES = HALF_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
+                const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+    using L = SmemLayout2<BLOCK_K, STAGES>;
+    constexpr int TILE_M = 256, TILE_N = 256, HALF_N = L::HALF_N;
+    constexpr int A_TILE_BYTES = L::A_TILE_BYTES, B_TILE_BYTES = L::B_TILE_BYTES;
+    constexpr int TMEM_COLS = 2 * TILE_N;  // 512: double-buffered 128-lane x 256-column accumulator per CTA
+    constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // shared::cluster address of the even (leader) CTA of the pair
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_holder = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+    const int tiles_per_batch = p.m_tiles * p.n_tiles;
+    const int num_tiles = tiles_per_batch * p.batches;
+    const uint32_t stage_tx_pair = (uint32_t)(2 * (p.passes == 3 ? 2 : 1) * (A_TILE_BYTES + B_TILE_BYTES));  // both CTAs' bytes
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi);
+        prefetch_tmap(&tmB_hi);
+        if (p.passes == 3) {
+            prefetch_tmap(&tmA_lo);
+            prefetch_tmap(&tmB_lo);
+        }
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // barrier inits of both CTAs are visible before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                const int b = t / tiles_per_batch;
+                const int rem = t - b * tiles_per_batch;
+                const int m0 = (rem / p.n_tiles) * TILE_M + (int)rank * BLOCK_M;
+                const int n_tile0 = (rem % p.n_tiles) * TILE_N;
+                const int n_eff = min(TILE_N, ((p.N - n_tile0 + 31) / 32) * 32);  // multiple of 32: each CTA's half is a multiple of 16
+                const int n0 = n_tile0 + (int)rank * (n_eff / 2);
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA_hi = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
+                    const uint32_t sB_hi = sA_lo + A_TILE_BYTES;
+                    const uint32_t sB_lo = sB_hi + B_TILE_BYTES;
+                    const uint32_t lbar = full_bar(stage) & kPeerMask;
+                    if (leader) mbar_expect_tx(full_bar(stage), stage_tx_pair);
+                    const int k0 = kb * BLOCK_K;
+                    if (!A_MN) {
+                        tma_load_3d_2sm(sA_hi, &tmA_hi, lbar, k0, m0, b);
+                        if (p.passes == 3) tma_load_3d_2sm(sA_lo, &tmA_lo, lbar, k0, m0, b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 64; j++) {
+                            tma_load_3d_2sm(sA_hi + j * (BLOCK_K * 128), &tmA_hi, lbar, m0 + 64 * j, k0, b);
+                            if (p.passes == 3) tma_load_3d_2sm(sA_lo + j * (BLOCK_K * 128), &tmA_lo, lbar, m0 + 64 * j, k0, b);
+                        }
+                    }
+                    if (!B_MN) {
+                        tma_load_3d_2sm(sB_hi, &tmB_hi, lbar, k0, n0, b);
+                        if (p.passes == 3) tma_load_3d_2sm(sB_lo, &tmB_lo, lbar, k0, n0, b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < HALF_N / 64; j++) {
+                            tma_load_3d_2sm(sB_hi + j * (BLOCK_K * 128), &tmB_hi, lbar, n0 + 64 * j, k0, b);
+                            if (p.passes == 3) tma_load_3d_2sm(sB_lo + j * (BLOCK_K * 128), &tmB_lo, lbar, n0 + 64 * j, k0, b);
+                        }
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: one thread of the leader CTA =================
+        if (leader && lane == 0) {
+            constexpr uint32_t K_ROW_BYTES = BLOCK_K * 2;
+            constexpr uint32_t K_LAYOUT = (K_ROW_BYTES == 128) ? 2u : 4u;
+            constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16, A_SBO = A_MN ? 1024 : 8 * K_ROW_BYTES, A_KSTEP = A_MN ? 2048 : 32;
+            constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16, B_SBO = B_MN ? 1024 : 8 * K_ROW_BYTES, B_KSTEP = B_MN ? 2048 : 32;
+            constexpr uint32_t A_LAYOUT = A_MN ? 2u : K_LAYOUT, B_LAYOUT = B_MN ? 2u : K_LAYOUT;
+            int stage = 0;
+            uint32_t phase = 0;
+            int local_tile = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, local_tile++) {
+                const int buf = local_tile & 1;
+                const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
+                const int n_tile0 = ((t % tiles_per_batch) % p.n_tiles) * TILE_N;
+                const int n_eff = min(TILE_N, ((p.N - n_tile0 + 31) / 32) * 32);
+                const uint32_t idesc = make_idesc(TILE_M, n_eff, A_MN, B_MN);
+                mbar_wait(tempty_bar(buf), buf_phase ^ 1u);  // both epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * TILE_N);
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(full_bar(stage), phase);  // both CTAs' tiles have landed
+                    tc_fence_after();
+                    const uint32_t sA_hi = smem_base + stage * L::STAGE_BYTES;
+                    const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
+                    const uint32_t sB_hi = sA_lo + A_TILE_BYTES;
+                    const uint32_t sB_lo = sB_hi + B_TILE_BYTES;
+                    const int k_valid = min(BLOCK_K, p.K - kb * BLOCK_K);
+                    const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
+                    for (int prod = 0; prod < p.passes; prod++) {
+                        const uint32_t sa = (prod == 2) ? sA_lo : sA_hi;
+                        const uint32_t sb = (prod == 1) ? sB_lo : sB_hi;
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            uint64_t adesc = make_smem_desc(sa + ks * A_KSTEP, A_LBO, A_SBO, A_LAYOUT);
+                            uint64_t bdesc = make_smem_desc(sb + ks * B_KSTEP, B_LBO, B_SBO, B_LAYOUT);
+                            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit_2sm(empty_bar(stage));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit_2sm(tfull_bar(buf));
+            }
+        }
+    } else {
+        // ================= epilogue warps 2..5 (both CTAs): this CTA's 128 rows =================
+        const int q = warp & 3;
+        int local_tile = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, local_tile++) {
+            const int buf = local_tile & 1;
+            const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
+            const int b = t / tiles_per_batch;
+            const int rem = t - b * tiles_per_batch;
+            const int m0 = (rem / p.n_tiles) * TILE_M + (int)rank * BLOCK_M;
+            const int n0 = (rem % p.n_tiles) * TILE_N;
+            mbar_wait(tfull_bar(buf), buf_phase);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            float* drow = p.D + (int64_t)b * p.sDb + (int64_t)row * p.ldd;
+            const bool row_ok = row < p.M && !(p.debug_flags & 1);
+            const bool vec_ok = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15u) == 0) && ((p.sDb & 3) == 0);
+#pragma unroll 1
+            for (int c = 0; c < TILE_N / 32; c++) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= p.N) break;
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TILE_N + c * 32), r);
+                tmem_ld_wait();
+                if (row_ok) {
+                    if (vec_ok && col0 + 32 <= p.N) {
+                        float4* dst = reinterpret_cast<float4*>(drow + col0);
+#pragma unroll
+                        for (int v = 0; v < 8; v++)
+                            dst[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]), __uint_as_float(r[4 * v + 2]),
+                                                 __uint_as_float(r[4 * v + 3]));
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 32; v++)
+                            if (col0 + v < p.N) drow[col0 + v] = __uint_as_float(r[v]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);  // the leader's barrier (local for rank 0)
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // neither CTA may free TMEM / exit while the pair can still touch its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
+mb_status launch_variant2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p,
+                          cudaStream_t st) {
+    using L = SmemLayout2<BLOCK_K, STAGES>;
+    auto kern = gemm_tc2_kernel<BLOCK_K, STAGES, A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        attr_set = true;
+    }
+    int tiles = p.m_tiles * p.n_tiles * p.batches;
+    int clusters = sm_count() / 2;
+    if (tiles < clusters) clusters = tiles;
+    kern<<<2 * clusters, kTcThreads, L::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
 }  // namespace
 
 bool gemm_tc_supported(int64_t a_inner, int64_t b_inner) {
@@ -429,10 +718,12 @@ mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, 
     }
     if (!A_lo || !B_lo) passes = 1;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    // tile configurations: block_n 256 -> (BLOCK_N 256, BLOCK_K 32, 4 stages) [default], 2560 -> (256, 64, 2), 128 -> (128, 64, 3)
-    const int bk = (block_n == 256) ? 32 : 64;
-    const int bn_real = (block_n == 2560) ? 256 : block_n;
-    const uint32_t bn = (uint32_t)bn_real;
+    // tile configurations: block_n 256 -> (BLOCK_N 256, BLOCK_K 32, 4 stages), 2560 -> (256, 64, 2), 128 -> (128, 64, 3),
+    // 512 -> 2-CTA pair, 256x256 cluster tile, BLOCK_K 64, 3 stages ; 5120 -> 2-CTA, BLOCK_K 32, 6 stages
+    const bool two_cta = (block_n == 512 || block_n == 5120);
+    const int bk = (block_n == 256 || block_n == 5120) ? 32 : 64;
+    const int bn_real = (block_n == 2560 || two_cta) ? 256 : block_n;
+    const uint32_t bn = two_cta ? 128u : (uint32_t)bn_real;  // TMA box rows of a K-major B tile (a CTA's half in 2-CTA mode)
     if (!a_mn) {
         MB_TRY(make_map(&ma_hi, A_hi, K, M, batches, lda, sAb, BLOCK_M, bk));
         if (passes == 3) MB_TRY(make_map(&ma_lo, A_lo, K, M, batches, lda, sAb, BLOCK_M, bk));
@@ -460,8 +751,25 @@ mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, 
     p.K = K;
     p.batches = batches;
     p.passes = passes;
-    p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    {
+        static int dbg = [] { const char* e = getenv("MB_TC_DEBUG"); return e ? atoi(e) : 0; }();
+        p.debug_flags = dbg;
+    }
+    p.m_tiles = two_cta ? (M + 255) / 256 : (M + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = (N + bn_real - 1) / bn_real;
+    if (two_cta) {
+#define MB_TC2_DISPATCH(BK, ST)                                                                           \
+    if (!a_mn && !b_mn) return launch_variant2<BK, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);  \
+    if (!a_mn && b_mn) return launch_variant2<BK, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);    \
+    if (a_mn && b_mn) return launch_variant2<BK, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);      \
+    return launch_variant2<BK, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
+        if (block_n == 512) {
+            MB_TC2_DISPATCH(64, 3)
+        } else {
+            MB_TC2_DISPATCH(32, 6)
+        }
+#undef MB_TC2_DISPATCH
+    }
 #define MB_TC_DISPATCH(BN, BK, ST)                                                                          \
     if (!a_mn && !b_mn) return launch_variant<BN, BK, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st); \
     if (!a_mn && b_mn) return launch_variant<BN, BK, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);   \

@@ -31,7 +31,8 @@ print("RESULT", err, nan)
 
 def run_gemm_probe():
     cases = []
-    for block_n in (256, 128):
+    cfgs = [int(x) for x in os.environ.get('PROBE_CFGS', '256,2560,128,512,5120').split(',')]
+    for block_n in cfgs:
         for (a_mn, b_mn) in ((False, False), (False, True), (True, True), (True, False)):
             for shape in ((1, 128, 256, 64), (1, 128, 256, 128), (2, 1000, 1000, 400), (2, 1000, 400, 1000), (1, 200, 72, 136)):
                 for prec in (2, 1):
