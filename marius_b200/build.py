@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_SOURCES = ["c_api.cu", "storage_kernels.cu", "radix_sort.cu", "decoder_kernels.cu", "gemm_simt.cu", "gemm_tc.cu"]
+CUDA_SOURCES = ["c_api.cu", "storage_kernels.cu", "radix_sort.cu", "decoder_kernels.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_group.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -31,7 +31,7 @@ def build_cuda(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libmarius_b200.so")
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.h")] + [os.path.join(HERE, "..", "include", "marius_b200.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.h", "decoder_vec.cuh", "gemm_tc_ptx.cuh")] + [os.path.join(HERE, "..", "include", "marius_b200.h")]
     if force or _newer(out, deps):
         cmd = [NVCC] + NVCC_FLAGS + ["-o", out] + srcs
         if verbose:

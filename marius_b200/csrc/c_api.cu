@@ -122,13 +122,14 @@ struct StageTimer {
 };
 
 // tcgen05 tile configuration (gemm_tc.cu): 256 = BLOCK_N 256 / BLOCK_K 32 / 4 stages (default), 2560 = 256 / 64 / 2, 128 = 128 / 64 / 3,
-// 512 / 5120 = 2-CTA pairs (cta_group::2) with BLOCK_K 64 / 3 stages or BLOCK_K 32 / 6 stages.
+// 512 / 5120 = 2-CTA pairs (cta_group::2) with BLOCK_K 64 / 3 stages or BLOCK_K 32 / 6 stages,
+// 1024 (default) = grouped, table-scheduled 2-CTA kernel (gemm_tc_group.cu): dA and dNeg share one launch.
 // MB_TC_CFG overrides it for A/B measurements.
 static int tc_tile_config() {
     static int cfg = [] {
         const char* e = getenv("MB_TC_CFG");
-        int v = e ? atoi(e) : 256;
-        return (v == 256 || v == 2560 || v == 128 || v == 512 || v == 5120) ? v : 256;
+        int v = e ? atoi(e) : 1024;
+        return (v == 256 || v == 2560 || v == 128 || v == 512 || v == 5120 || v == 1024) ? v : 1024;
     }();
     return cfg;
 }
@@ -219,6 +220,15 @@ static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
     p.use_tc = (precision != MB_PREC_FP32) && gemm_tc_supported(p.d, p.N) && p.Bc > 0;
 }
 
+static mb_status tc_contract(int cfg, const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb,
+                             int64_t sBb, bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, cudaStream_t st) {
+    if (cfg == 1024) {
+        TcGroupProblem g{A_hi, A_lo, lda, sAb, a_mn ? 1 : 0, B_hi, B_lo, ldb, sBb, b_mn ? 1 : 0, D, ldd, sDb, M, N, K, batches};
+        return gemm_tc_grouped(&g, 1, passes, st);
+    }
+    return gemm_tc(A_hi, A_lo, lda, sAb, a_mn, B_hi, B_lo, ldb, sBb, b_mn, D, ldd, sDb, M, N, K, batches, passes, cfg, st);
+}
+
 // forward: adjusted rows A, positive scores, negative rows, score GEMM.  S0/S1 are the score outputs per side ([Bp,N] each).
 static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, const int64_t* row_map, int precision,
                              float* pos, float* S0, float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false) {
@@ -244,8 +254,8 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
         float* S = l == 0 ? S0 : S1;
         int64_t aoff = (int64_t)l * p.Bp * d, noff = (int64_t)l * p.CN * d;
         if (p.use_tc) {
-            MB_TRY(gemm_tc(p.A_hl + aoff, p.A_hl + a_half + aoff, d, p.Bc * d, false, p.Neg_hl + noff, p.Neg_hl + n_half + noff, d, (int64_t)p.N * d,
-                           false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, tc_tile_config(), st));
+            MB_TRY(tc_contract(tc_tile_config(), p.A_hl + aoff, p.A_hl + a_half + aoff, d, p.Bc * d, false, p.Neg_hl + noff, p.Neg_hl + n_half + noff, d,
+                               (int64_t)p.N * d, false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, st));
         } else {
             MB_TRY(gemm_simt(p.A + aoff, d, 1, p.Bc * d, p.NegE + noff, 1, d, (int64_t)p.N * d, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, st));
         }
@@ -358,7 +368,15 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     const int tc_cfg = tc_tile_config();
     bool dneg_forked = false;
     float* gneg = p.gcat + 2 * p.B * d;  // d dst_negs | d src_negs, [sides][C][N][d]
-    if (p.Bc > 0) {
+    if (p.Bc > 0 && p.use_tc && tc_cfg == 1024) {
+        // dA = G . Neg and dNeg = G^T . A in ONE grouped, cost-balanced persistent launch (gemm_tc_group.cu)
+        const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
+        StageTimer tm(ctx, ST_GEMM_DA, st);
+        TcGroupProblem g[2] = {
+            {p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, 0, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, 1, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches},
+            {p.G_hl, p.G_hl + g_half, p.N, p.Bc * p.N, 1, p.A_hl, p.A_hl + a_half, d, p.Bc * d, 1, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches}};
+        MB_TRY(gemm_tc_grouped(g, 2, passes, st));
+    } else if (p.Bc > 0) {
         const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
         {
             // dNeg = G^T . A : independent of dA / edge_backward, so it runs on the second side stream; the tail wave of one persistent
@@ -671,8 +689,8 @@ mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* 
     __nv_bfloat16* b_hl = place.take<__nv_bfloat16>(2 * nb);
     MB_TRY(launch_split(A, na, a_hl, a_hl + na, st));
     MB_TRY(launch_split(B, nb, b_hl, b_hl + nb, st));
-    return gemm_tc(a_hl, a_hl + na, a_mn ? M : K, (int64_t)M * K, a_mn != 0, b_hl, b_hl + nb, b_mn ? N : K, (int64_t)N * K, b_mn != 0, D, N,
-                   (int64_t)M * N, M, N, K, batches, precision == MB_PREC_BF16 ? 1 : 3, block_n, st);
+    return tc_contract(block_n, a_hl, a_hl + na, a_mn ? M : K, (int64_t)M * K, a_mn != 0, b_hl, b_hl + nb, b_mn ? N : K, (int64_t)N * K, b_mn != 0, D, N,
+                       (int64_t)M * N, M, N, K, batches, precision == MB_PREC_BF16 ? 1 : 3, st);
 }
 
 static mb_status grow_i64(int64_t** p, size_t* cap, size_t need) {

@@ -15,24 +15,23 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <vector>
 
 #include "common.cuh"
+#include "gemm_tc_ptx.cuh"
 
 namespace mb {
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int UMMA_K = 16;
+using namespace tcptx;
 // BLOCK_K (template parameter, bf16 elements per k-block): 64 -> K-major tiles are SWIZZLE_128B rows, 32 -> SWIZZLE_64B rows
 // (half the bytes per stage => twice the pipeline depth in the same shared memory).  MN-major tiles are always SWIZZLE_128B
 // slabs of 64 MN-elements x BLOCK_K k-rows.
-constexpr int kTcThreads = 192;
-constexpr long long kWaitTimeoutCycles = 4000000000ll;  // ~2 s: trap instead of hanging the GPU
 
 struct TcParams {
     float* D;
@@ -42,119 +41,24 @@ struct TcParams {
     int passes;       // 1 (hi.hi) or 3 (hi.hi + hi.lo + lo.hi)
     int m_tiles, n_tiles;
     int debug_flags;  // bit 0: skip the epilogue's global stores (bandwidth experiments only; MB_TC_DEBUG)
+    int tma_store;    // 1: epilogue stores through shared memory + TMA (needs 16-byte aligned D, ldd % 4 == 0)
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
-        if (clock64() - t0 > kWaitTimeoutCycles) __trap();
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-
-// D[tmem] (+)= A[smem desc] . B[smem desc]
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-          "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ---- descriptors ----------------------------------------------------------------------------------------------
-// Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
-    return d;
-}
-// Instruction descriptor (InstrDescriptor): c_format F32=1 [4,6), a/b_format BF16=1 [7,10)/[10,13), a_major [15], b_major [16],
-// N>>3 [17,23), M>>4 [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
-}
 
 template <int BLOCK_N, int BLOCK_K, int STAGES>
 struct SmemLayout {
     static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + kEpilogueSmemBytes;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+    static_assert(TOTAL <= 232448, "shared memory budget (227 KB)");
 };
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
-               const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmD, const TcParams p) {
     using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
     constexpr int A_TILE_BYTES = L::A_TILE_BYTES;
     constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered fp32 accumulator: 256 or 512 columns (power of two)
@@ -217,6 +121,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
                     const uint32_t sB_hi = sA_lo + A_TILE_BYTES;
                     const uint32_t sB_lo = sB_hi + L::B_TILE_BYTES;
+                    if (p.debug_flags & 2) {  // experiment: no TMA traffic, the MMAs run on whatever is in shared memory
+                        mbar_arrive(full_bar(stage));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
                     mbar_expect_tx(full_bar(stage), stage_tx);
                     const int k0 = kb * BLOCK_K;
                     if (!A_MN) {
@@ -280,7 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint32_t sB_lo = sB_hi + L::B_TILE_BYTES;
                     const int k_valid = min(BLOCK_K, p.K - kb * BLOCK_K);
                     const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
-                    for (int prod = 0; prod < p.passes; prod++) {
+                    for (int prod = 0; prod < ((p.debug_flags & 4) ? 0 : p.passes); prod++) {
                         const uint32_t sa = (prod == 2) ? sA_lo : sA_hi;  // hi.hi, hi.lo, lo.hi
                         const uint32_t sb = (prod == 1) ? sB_lo : sB_hi;
                         for (int ks = 0; ks < ksteps; ks++) {
@@ -303,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // ================= epilogue warps 2..5 =================
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         int local_tile = 0;
+        uint32_t epi_chunk = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, local_tile++) {
             const int buf = local_tile & 1;
             const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
@@ -323,7 +236,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BLOCK_N + c * 32), r);
                 tmem_ld_wait();
-                if (row_ok) {
+                if (p.tma_store) {
+                    if (!(p.debug_flags & 1))
+                        stage_and_store(r, smem_base + L::EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, &tmD, col0,
+                                        m0 + q * 32, b);
+                    epi_chunk++;
+                } else if (row_ok) {
                     if (vec_ok && col0 + 32 <= p.N) {
                         float4* dst = reinterpret_cast<float4*>(drow + col0);
 #pragma unroll
@@ -341,6 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
+        if (p.tma_store && lane == 0) bulk_wait_all();  // all bulk stores of this warp have completed before the CTA exits
     }
 
     tc_fence_before();
@@ -395,8 +314,8 @@ mb_status make_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
 }
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
-mb_status launch_variant(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p,
-                         cudaStream_t st) {
+mb_status launch_variant(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const CUtensorMap& d_map,
+                         const TcParams& p, cudaStream_t st) {
     using L = SmemLayout<BLOCK_N, BLOCK_K, STAGES>;
     auto kern = gemm_tc_kernel<BLOCK_N, BLOCK_K, STAGES, A_MN, B_MN>;
     static bool attr_set = false;
@@ -406,7 +325,7 @@ mb_status launch_variant(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
     }
     int tiles = p.m_tiles * p.n_tiles * p.batches;
     int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, kTcThreads, L::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    kern<<<grid, kTcThreads, L::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, d_map, p);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }
@@ -422,65 +341,22 @@ mb_status launch_variant(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const
 //   - tcgen05.commit .multicast::cluster releases the stage in both CTAs and hands the accumulator to both epilogues
 //   - the peer's epilogue warps arrive remotely (mapa) on the leader's tmem-empty barrier
 // =================================================================================================================
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `bar` (same offset) in both CTAs of the pair
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
-        ::"r"(bar), "r"(cta)
-        : "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-template <int NCOLS>
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
-}
-
 template <int BLOCK_K, int STAGES>
 struct SmemLayout2 {
     static constexpr int HALF_N = 128;                         // this CTA's share of the 256 tile columns
     static constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // this CTA's 128 rows of A
     static constexpr int B_TILE_BYTES = HALF_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + kEpilogueSmemBytes;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static_assert(TOTAL <= 232448, "shared memory budget (227 KB)");
 };
 
 template <int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_hi,
-                const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+                const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmD, const TcParams p) {
     using L = SmemLayout2<BLOCK_K, STAGES>;
     constexpr int TILE_M = 256, TILE_N = 256, HALF_N = L::HALF_N;
     constexpr int A_TILE_BYTES = L::A_TILE_BYTES, B_TILE_BYTES = L::B_TILE_BYTES;
@@ -550,6 +426,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     const uint32_t sB_hi = sA_lo + A_TILE_BYTES;
                     const uint32_t sB_lo = sB_hi + B_TILE_BYTES;
                     const uint32_t lbar = full_bar(stage) & kPeerMask;
+                    if (p.debug_flags & 2) {
+                        if (leader) mbar_arrive(full_bar(stage));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
                     if (leader) mbar_expect_tx(full_bar(stage), stage_tx_pair);
                     const int k0 = kb * BLOCK_K;
                     if (!A_MN) {
@@ -609,7 +493,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                     const uint32_t sB_lo = sB_hi + B_TILE_BYTES;
                     const int k_valid = min(BLOCK_K, p.K - kb * BLOCK_K);
                     const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
-                    for (int prod = 0; prod < p.passes; prod++) {
+                    for (int prod = 0; prod < ((p.debug_flags & 4) ? 0 : p.passes); prod++) {
                         const uint32_t sa = (prod == 2) ? sA_lo : sA_hi;
                         const uint32_t sb = (prod == 1) ? sB_lo : sB_hi;
                         for (int ks = 0; ks < ksteps; ks++) {
@@ -632,6 +516,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         // ================= epilogue warps 2..5 (both CTAs): this CTA's 128 rows =================
         const int q = warp & 3;
         int local_tile = 0;
+        uint32_t epi_chunk = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, local_tile++) {
             const int buf = local_tile & 1;
             const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
@@ -652,7 +537,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TILE_N + c * 32), r);
                 tmem_ld_wait();
-                if (row_ok) {
+                if (p.tma_store) {
+                    if (!(p.debug_flags & 1))
+                        stage_and_store(r, smem_base + L::EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, &tmD, col0,
+                                        m0 + q * 32, b);
+                    epi_chunk++;
+                } else if (row_ok) {
                     if (vec_ok && col0 + 32 <= p.N) {
                         float4* dst = reinterpret_cast<float4*>(drow + col0);
 #pragma unroll
@@ -670,6 +560,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);  // the leader's barrier (local for rank 0)
         }
+        if (p.tma_store && lane == 0) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -682,8 +573,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 }
 
 template <int BLOCK_K, int STAGES, bool A_MN, bool B_MN>
-mb_status launch_variant2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const TcParams& p,
-                          cudaStream_t st) {
+mb_status launch_variant2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo, const CUtensorMap& d_map,
+                          const TcParams& p, cudaStream_t st) {
     using L = SmemLayout2<BLOCK_K, STAGES>;
     auto kern = gemm_tc2_kernel<BLOCK_K, STAGES, A_MN, B_MN>;
     static bool attr_set = false;
@@ -694,7 +585,7 @@ mb_status launch_variant2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, cons
     int tiles = p.m_tiles * p.n_tiles * p.batches;
     int clusters = sm_count() / 2;
     if (tiles < clusters) clusters = tiles;
-    kern<<<2 * clusters, kTcThreads, L::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+    kern<<<2 * clusters, kTcThreads, L::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, d_map, p);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }
@@ -742,7 +633,23 @@ mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, 
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
+    // fp32 output map for the TMA-store epilogue: dims {N, M, batches}, box {32 columns, 32 rows, 1}, SWIZZLE_128B
+    CUtensorMap md;
+    std::memset(&md, 0, sizeof(md));
+    static int want_tma_store = [] { const char* e = getenv("MB_TC_TMA_STORE"); return e ? atoi(e) : 1; }();
+    bool tma_store = want_tma_store && ((reinterpret_cast<uintptr_t>(D) & 15u) == 0) && (ldd % 4 == 0) && (batches == 1 || sDb % 4 == 0);
+    if (tma_store) {
+        EncodeTiledFn fn = get_encode_fn();
+        cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)batches};
+        cuuint64_t strides[2] = {(cuuint64_t)ldd * 4, (cuuint64_t)(batches == 1 ? (int64_t)M * ldd : sDb) * 4};
+        cuuint32_t box[3] = {32, 32, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = fn(&md, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) tma_store = false;
+    }
     TcParams p;
+    p.tma_store = tma_store ? 1 : 0;
     p.D = D;
     p.ldd = ldd;
     p.sDb = sDb;
@@ -759,10 +666,10 @@ mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, 
     p.n_tiles = (N + bn_real - 1) / bn_real;
     if (two_cta) {
 #define MB_TC2_DISPATCH(BK, ST)                                                                           \
-    if (!a_mn && !b_mn) return launch_variant2<BK, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);  \
-    if (!a_mn && b_mn) return launch_variant2<BK, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);    \
-    if (a_mn && b_mn) return launch_variant2<BK, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);      \
-    return launch_variant2<BK, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
+    if (!a_mn && !b_mn) return launch_variant2<BK, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st);  \
+    if (!a_mn && b_mn) return launch_variant2<BK, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st);    \
+    if (a_mn && b_mn) return launch_variant2<BK, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st);      \
+    return launch_variant2<BK, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st);
         if (block_n == 512) {
             MB_TC2_DISPATCH(64, 3)
         } else {
@@ -771,10 +678,10 @@ mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, 
 #undef MB_TC2_DISPATCH
     }
 #define MB_TC_DISPATCH(BN, BK, ST)                                                                          \
-    if (!a_mn && !b_mn) return launch_variant<BN, BK, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st); \
-    if (!a_mn && b_mn) return launch_variant<BN, BK, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);   \
-    if (a_mn && b_mn) return launch_variant<BN, BK, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);     \
-    return launch_variant<BN, BK, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
+    if (!a_mn && !b_mn) return launch_variant<BN, BK, ST, false, false>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st); \
+    if (!a_mn && b_mn) return launch_variant<BN, BK, ST, false, true>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st);   \
+    if (a_mn && b_mn) return launch_variant<BN, BK, ST, true, true>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st);     \
+    return launch_variant<BN, BK, ST, true, false>(ma_hi, ma_lo, mb_hi, mb_lo, md, p, st);
     if (block_n == 256) {
         MB_TC_DISPATCH(256, 32, 4)
     } else if (block_n == 2560) {

@@ -1,0 +1,448 @@
+// gemm_tc_group.cu -- grouped, table-scheduled 2-CTA tcgen05 GEMM.
+//
+// Same CTA-pair kernel as gemm_tc2_kernel (gemm_tc.cu) with two changes that matter at the named shape (ComplEx d=400,
+// 1000 negatives, batch 10k: each backward contraction has only 160 cluster tiles for 74 CTA pairs = 2.16 waves):
+//   (1) up to two independent problems (dA = G.Neg and dNeg = G^T.A) share ONE persistent launch: operand majors, shapes and
+//       tensor maps are per-problem run-time data, so the tail of one contraction is filled with tiles of the other;
+//   (2) tiles are handed out from a host-built table: tiles sorted by cost (ragged N tiles are cheaper), assigned to CTA pairs
+//       in snake order (longest-processing-time-first), so every pair gets the same work within one small tile.
+// All three warp roles read the same table entries, so no in-kernel tile broadcast is needed.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "gemm_tc_ptx.cuh"
+#include "kernels.h"
+
+namespace mb {
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int GBLOCK_K = 64;
+constexpr int GSTAGES = 3;
+constexpr int GTILE_M = 256, GTILE_N = 256, GHALF_N = 128;
+constexpr int G_A_TILE = BLOCK_M * GBLOCK_K * 2;   // 16 KB: this CTA's 128 rows
+constexpr int G_B_TILE = GHALF_N * GBLOCK_K * 2;   // 16 KB: this CTA's half of the tile columns
+constexpr int G_STAGE = 2 * G_A_TILE + 2 * G_B_TILE;
+constexpr int G_EPI_OFFSET = GSTAGES * G_STAGE;
+constexpr int G_BAR_OFFSET = G_EPI_OFFSET + kEpilogueSmemBytes;
+constexpr int G_SMEM_TOTAL = G_BAR_OFFSET + 256 + 1024;
+static_assert(G_SMEM_TOTAL <= 232448, "shared memory budget");
+
+struct GProblem {
+    float* D;
+    int64_t ldd, sDb;
+    int M, N, K, batches;
+    int a_mn, b_mn, tma_store;
+};
+struct GParams {
+    GProblem prob[2];
+    const int4* table;  // [rounds][num_clusters] : (problem | -1, batch, m0, n_tile0)
+    int rounds;
+    int passes;
+    int debug_flags;
+};
+struct GMaps {
+    CUtensorMap m[2][5];  // per problem: A_hi, A_lo, B_hi, B_lo, D
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_tc_group_kernel(const __grid_constant__ GMaps maps, const GParams p) {
+    constexpr int TMEM_COLS = 2 * GTILE_N;
+    constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + G_BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (GSTAGES + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * GSTAGES + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * GSTAGES + 2 + b); };
+    const uint32_t tmem_holder = bar_base + 8u * (2 * GSTAGES + 4);
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int lo_mult = p.passes == 3 ? 2 : 1;
+    const uint32_t stage_tx_pair = (uint32_t)(2 * lo_mult * (G_A_TILE + G_B_TILE));
+
+    if (warp == 0 && lane == 0) {
+        for (int q = 0; q < 2; q++)
+            for (int j = 0; j < 5; j++) prefetch_tmap(&maps.m[q][j]);
+        for (int s = 0; s < GSTAGES; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int r = 0; r < p.rounds; r++) {
+                const int4 e = p.table[r * num_clusters + cluster_id];
+                if (e.x < 0) continue;
+                const GProblem& pr = p.prob[e.x];
+                const CUtensorMap* mA_hi = &maps.m[e.x][0];
+                const CUtensorMap* mA_lo = &maps.m[e.x][1];
+                const CUtensorMap* mB_hi = &maps.m[e.x][2];
+                const CUtensorMap* mB_lo = &maps.m[e.x][3];
+                const int b = e.y;
+                const int m0 = e.z + (int)rank * BLOCK_M;
+                const int n_eff = min(GTILE_N, ((pr.N - e.w + 31) / 32) * 32);
+                const int n0 = e.w + (int)rank * (n_eff / 2);
+                const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sA_hi = smem_base + stage * G_STAGE;
+                    const uint32_t sA_lo = sA_hi + G_A_TILE;
+                    const uint32_t sB_hi = sA_lo + G_A_TILE;
+                    const uint32_t sB_lo = sB_hi + G_B_TILE;
+                    const uint32_t lbar = full_bar(stage) & kPeerMask;
+                    if (leader) mbar_expect_tx(full_bar(stage), stage_tx_pair);
+                    const int k0 = kb * GBLOCK_K;
+                    if (!pr.a_mn) {
+                        tma_load_3d_2sm(sA_hi, mA_hi, lbar, k0, m0, b);
+                        if (p.passes == 3) tma_load_3d_2sm(sA_lo, mA_lo, lbar, k0, m0, b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BLOCK_M / 64; j++) {
+                            tma_load_3d_2sm(sA_hi + j * (GBLOCK_K * 128), mA_hi, lbar, m0 + 64 * j, k0, b);
+                            if (p.passes == 3) tma_load_3d_2sm(sA_lo + j * (GBLOCK_K * 128), mA_lo, lbar, m0 + 64 * j, k0, b);
+                        }
+                    }
+                    if (!pr.b_mn) {
+                        tma_load_3d_2sm(sB_hi, mB_hi, lbar, k0, n0, b);
+                        if (p.passes == 3) tma_load_3d_2sm(sB_lo, mB_lo, lbar, k0, n0, b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < GHALF_N / 64; j++) {
+                            tma_load_3d_2sm(sB_hi + j * (GBLOCK_K * 128), mB_hi, lbar, n0 + 64 * j, k0, b);
+                            if (p.passes == 3) tma_load_3d_2sm(sB_lo + j * (GBLOCK_K * 128), mB_lo, lbar, n0 + 64 * j, k0, b);
+                        }
+                    }
+                    if (++stage == GSTAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: one thread of the leader CTA =================
+        if (leader && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int local_tile = 0;
+            for (int r = 0; r < p.rounds; r++) {
+                const int4 e = p.table[r * num_clusters + cluster_id];
+                if (e.x < 0) continue;
+                const GProblem& pr = p.prob[e.x];
+                const bool a_mn = pr.a_mn != 0, b_mn = pr.b_mn != 0;
+                // K-major SW128: SBO = 1024 (8 rows x 128 B), k-step +32 B.  MN-major SW128: LBO = slab stride, SBO = 1024, k-step +2048 B.
+                const uint32_t A_LBO = a_mn ? GBLOCK_K * 128 : 16, A_KSTEP = a_mn ? 2048 : 32;
+                const uint32_t B_LBO = b_mn ? GBLOCK_K * 128 : 16, B_KSTEP = b_mn ? 2048 : 32;
+                const int buf = local_tile & 1;
+                const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
+                local_tile++;
+                const int n_eff = min(GTILE_N, ((pr.N - e.w + 31) / 32) * 32);
+                const uint32_t idesc = make_idesc(GTILE_M, n_eff, a_mn, b_mn);
+                const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
+                mbar_wait(tempty_bar(buf), buf_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * GTILE_N);
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sA_hi = smem_base + stage * G_STAGE;
+                    const uint32_t sA_lo = sA_hi + G_A_TILE;
+                    const uint32_t sB_hi = sA_lo + G_A_TILE;
+                    const uint32_t sB_lo = sB_hi + G_B_TILE;
+                    const int k_valid = min(GBLOCK_K, pr.K - kb * GBLOCK_K);
+                    const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
+                    for (int prod = 0; prod < p.passes; prod++) {
+                        const uint32_t sa = (prod == 2) ? sA_lo : sA_hi;  // hi.hi, hi.lo, lo.hi
+                        const uint32_t sb = (prod == 1) ? sB_lo : sB_hi;
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            uint64_t adesc = make_smem_desc(sa + ks * A_KSTEP, A_LBO, 1024, 2u);
+                            uint64_t bdesc = make_smem_desc(sb + ks * B_KSTEP, B_LBO, 1024, 2u);
+                            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit_2sm(empty_bar(stage));
+                    if (++stage == GSTAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit_2sm(tfull_bar(buf));
+            }
+        }
+    } else {
+        // ================= epilogue warps 2..5 (both CTAs) =================
+        const int q = warp & 3;
+        int local_tile = 0;
+        uint32_t epi_chunk = 0;
+        for (int r = 0; r < p.rounds; r++) {
+            const int4 e = p.table[r * num_clusters + cluster_id];
+            if (e.x < 0) continue;
+            const GProblem& pr = p.prob[e.x];
+            const CUtensorMap* mD = &maps.m[e.x][4];
+            const int buf = local_tile & 1;
+            const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
+            local_tile++;
+            const int b = e.y;
+            const int m0 = e.z + (int)rank * BLOCK_M;
+            const int n0 = e.w;
+            mbar_wait(tfull_bar(buf), buf_phase);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            float* drow = pr.D + (int64_t)b * pr.sDb + (int64_t)row * pr.ldd;
+            const bool row_ok = row < pr.M && !(p.debug_flags & 1);
+#pragma unroll 1
+            for (int c = 0; c < GTILE_N / 32; c++) {
+                const int col0 = n0 + c * 32;
+                if (col0 >= pr.N) break;
+                uint32_t rg[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GTILE_N + c * 32), rg);
+                tmem_ld_wait();
+                if (pr.tma_store) {
+                    if (!(p.debug_flags & 1))
+                        stage_and_store(rg, smem_base + G_EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, mD, col0,
+                                        m0 + q * 32, b);
+                    epi_chunk++;
+                } else if (row_ok) {
+#pragma unroll
+                    for (int v = 0; v < 32; v++)
+                        if (col0 + v < pr.N) drow[col0 + v] = __uint_as_float(rg[v]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+mb_status bf16_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batches, uint64_t row_stride, uint64_t batch_stride,
+                   uint32_t box_rows) {
+    cuuint64_t dims[3] = {inner, rows, batches};
+    cuuint64_t strides[2] = {row_stride * 2, batch_stride * 2};
+    if (batches == 1) strides[1] = strides[0] * rows;
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (strides[0] & 15u) || (strides[1] & 15u)) {
+        set_error("gemm_tc_grouped: operand not 16-byte aligned / stride not a multiple of 16 bytes");
+        return MB_ERR_INVALID;
+    }
+    CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return MB_ERR_CUDA;
+    }
+    return MB_OK;
+}
+
+// tile tables are pure functions of the shapes: build once, keep on the device
+struct TableKey {
+    int dev, clusters, n;
+    int M[2], N[2], K[2], batches[2];
+    bool operator<(const TableKey& o) const {
+        return std::tie(dev, clusters, n, M[0], N[0], K[0], batches[0], M[1], N[1], K[1], batches[1]) <
+               std::tie(o.dev, o.clusters, o.n, o.M[0], o.N[0], o.K[0], o.batches[0], o.M[1], o.N[1], o.K[1], o.batches[1]);
+    }
+};
+struct TableVal {
+    int4* dev_ptr;
+    int rounds;
+};
+std::map<TableKey, TableVal>& table_cache() {
+    static std::map<TableKey, TableVal> c;
+    return c;
+}
+std::mutex& table_mutex() {
+    static std::mutex m;
+    return m;
+}
+
+}  // namespace
+
+mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st) {
+    if (n < 1 || n > 2) {
+        set_error("gemm_tc_grouped: 1 or 2 problems");
+        return MB_ERR_INVALID;
+    }
+    if (!encode_fn()) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return MB_ERR_CUDA;
+    }
+    int dev = 0;
+    MB_CUDA_TRY(cudaGetDevice(&dev));
+    const int clusters_max = sm_count() / 2;
+    GMaps maps;
+    std::memset(&maps, 0, sizeof(maps));
+    GParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.passes = passes;
+    {
+        static int dbg = [] { const char* e = getenv("MB_TC_DEBUG"); return e ? atoi(e) : 0; }();
+        p.debug_flags = dbg;
+    }
+    TableKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.dev = dev;
+    key.n = n;
+    int64_t total_tiles = 0;
+    for (int i = 0; i < n; i++) {
+        const TcGroupProblem& g = probs[i];
+        if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batches <= 0) {
+            set_error("gemm_tc_grouped: empty problem");
+            return MB_ERR_INVALID;
+        }
+        const bool lo = passes == 3;
+        if (!g.a_mn) {
+            MB_TRY(bf16_map(&maps.m[i][0], g.A_hi, g.K, g.M, g.batches, g.lda, g.sAb, BLOCK_M));
+            MB_TRY(bf16_map(&maps.m[i][1], lo ? g.A_lo : g.A_hi, g.K, g.M, g.batches, g.lda, g.sAb, BLOCK_M));
+        } else {
+            MB_TRY(bf16_map(&maps.m[i][0], g.A_hi, g.M, g.K, g.batches, g.lda, g.sAb, GBLOCK_K));
+            MB_TRY(bf16_map(&maps.m[i][1], lo ? g.A_lo : g.A_hi, g.M, g.K, g.batches, g.lda, g.sAb, GBLOCK_K));
+        }
+        if (!g.b_mn) {
+            MB_TRY(bf16_map(&maps.m[i][2], g.B_hi, g.K, g.N, g.batches, g.ldb, g.sBb, GHALF_N));
+            MB_TRY(bf16_map(&maps.m[i][3], lo ? g.B_lo : g.B_hi, g.K, g.N, g.batches, g.ldb, g.sBb, GHALF_N));
+        } else {
+            MB_TRY(bf16_map(&maps.m[i][2], g.B_hi, g.N, g.K, g.batches, g.ldb, g.sBb, GBLOCK_K));
+            MB_TRY(bf16_map(&maps.m[i][3], lo ? g.B_lo : g.B_hi, g.N, g.K, g.batches, g.ldb, g.sBb, GBLOCK_K));
+        }
+        bool tma_store = ((reinterpret_cast<uintptr_t>(g.D) & 15u) == 0) && (g.ldd % 4 == 0) && (g.batches == 1 || g.sDb % 4 == 0);
+        if (tma_store) {
+            cuuint64_t dims[3] = {(cuuint64_t)g.N, (cuuint64_t)g.M, (cuuint64_t)g.batches};
+            cuuint64_t strides[2] = {(cuuint64_t)g.ldd * 4, (cuuint64_t)(g.batches == 1 ? (int64_t)g.M * g.ldd : g.sDb) * 4};
+            cuuint32_t box[3] = {32, 32, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = encode_fn()(&maps.m[i][4], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, g.D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) tma_store = false;
+        }
+        if (!tma_store) maps.m[i][4] = maps.m[i][0];
+        GProblem& q = p.prob[i];
+        q.D = g.D;
+        q.ldd = g.ldd;
+        q.sDb = g.sDb;
+        q.M = g.M;
+        q.N = g.N;
+        q.K = g.K;
+        q.batches = g.batches;
+        q.a_mn = g.a_mn;
+        q.b_mn = g.b_mn;
+        q.tma_store = tma_store ? 1 : 0;
+        key.M[i] = g.M;
+        key.N[i] = g.N;
+        key.K[i] = g.K;
+        key.batches[i] = g.batches;
+        total_tiles += (int64_t)((g.M + GTILE_M - 1) / GTILE_M) * ((g.N + GTILE_N - 1) / GTILE_N) * g.batches;
+    }
+    if (n == 1) {
+        p.prob[1] = p.prob[0];
+        for (int j = 0; j < 5; j++) maps.m[1][j] = maps.m[0][j];
+    }
+    int clusters = (int)std::min<int64_t>(clusters_max, total_tiles);
+    key.clusters = clusters;
+    TableVal tv;
+    {
+        std::lock_guard<std::mutex> lk(table_mutex());
+        auto it = table_cache().find(key);
+        if (it == table_cache().end()) {
+            struct Tile {
+                int prob, b, m0, n0;
+                int64_t cost;
+            };
+            std::vector<Tile> tiles;
+            for (int i = 0; i < n; i++) {
+                const TcGroupProblem& g = probs[i];
+                const int ksteps = (g.K + 15) / 16;
+                for (int b = 0; b < g.batches; b++)
+                    for (int m0 = 0; m0 < g.M; m0 += GTILE_M)
+                        for (int n0 = 0; n0 < g.N; n0 += GTILE_N) {
+                            int n_eff = std::min(GTILE_N, ((g.N - n0 + 31) / 32) * 32);
+                            tiles.push_back({i, b, m0, n0, (int64_t)n_eff * ksteps + 2048});  // MMA cycles ~ n_eff/2 per k-step, + fixed epilogue
+                        }
+            }
+            // longest first; ties keep (problem, batch, m, n) order so neighbouring CTA pairs share operand tiles in L2
+            std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });
+            int rounds = (int)((tiles.size() + clusters - 1) / clusters);
+            std::vector<int4> host((size_t)rounds * clusters, make_int4(-1, 0, 0, 0));
+            for (size_t t = 0; t < tiles.size(); t++) {
+                int r = (int)(t / clusters), i = (int)(t % clusters);
+                int c = (r & 1) ? clusters - 1 - i : i;  // snake
+                host[(size_t)r * clusters + c] = make_int4(tiles[t].prob, tiles[t].b, tiles[t].m0, tiles[t].n0);
+            }
+            int4* dptr = nullptr;
+            MB_CUDA_TRY(cudaMalloc(&dptr, host.size() * sizeof(int4)));
+            MB_CUDA_TRY(cudaMemcpy(dptr, host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice));
+            tv = {dptr, rounds};
+            table_cache()[key] = tv;
+        } else {
+            tv = it->second;
+        }
+    }
+    p.table = tv.dev_ptr;
+    p.rounds = tv.rounds;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
+        attr_set = true;
+    }
+    gemm_tc_group_kernel<<<2 * clusters, kTcThreads, G_SMEM_TOTAL, st>>>(maps, p);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+}  // namespace mb

@@ -65,4 +65,18 @@ bool gemm_tc_supported(int64_t a_inner, int64_t b_inner);
 mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int64_t sBb,
                   bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, int block_n, cudaStream_t st);
 
+// gemm_tc_group.cu : up to two contractions in one table-scheduled persistent 2-CTA launch
+struct TcGroupProblem {
+    const void *A_hi, *A_lo;
+    int64_t lda, sAb;
+    int a_mn;
+    const void *B_hi, *B_lo;
+    int64_t ldb, sBb;
+    int b_mn;
+    float* D;
+    int64_t ldd, sDb;
+    int M, N, K, batches;
+};
+mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st);
+
 }  // namespace mb

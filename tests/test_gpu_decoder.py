@@ -183,7 +183,7 @@ def test_mean_reduction_and_padding(ops, ctx):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("block_n", [256, 2560, 128])
+@pytest.mark.parametrize("block_n", [1024, 512, 5120, 256, 2560, 128])
 def test_contraction_kernel_layouts(ops, ctx, a_mn, b_mn, block_n):
     """tcgen05 GEMM, every operand-major combination the path uses, ragged M/N/K, vs fp64 matmul."""
     torch.manual_seed(1)
