@@ -59,6 +59,27 @@ def make_batches(rng, num_nodes, n_batches, B):
     return out, C
 
 
+def make_sharded_batches(rng, rows_per_rank, rank, world, n_batches, B):
+    """Bucket-wise routing: sources and both negative pools come from the rank's own partition, destinations are
+    uniform over ALL partitions, so (world-1)/world of the destination rows -- ~22 % of a batch's unique rows at 8 GPUs -- cross
+    NVLink.  Returns [(unique GLOBAL ids sorted, edges local, dst_negs local, src_negs local)]."""
+    from oracle import marius_oracle as O
+
+    C = max(B // CHUNK, 1)
+    lo = rank * rows_per_rank
+    out = []
+    for _ in range(n_batches):
+        src = rng.integers(lo, lo + rows_per_rank, size=B, dtype=np.int64)
+        dst = rng.integers(0, world * rows_per_rank, size=B, dtype=np.int64)
+        relid = rng.integers(0, NUM_REL, size=B, dtype=np.int64)
+        sn = rng.integers(lo, lo + rows_per_rank, size=(C, NEG), dtype=np.int64)
+        dn = rng.integers(lo, lo + rows_per_rank, size=(C, NEG), dtype=np.int64)
+        uniq, inv = O.map_tensors(np.concatenate([src, dst, sn.reshape(-1), dn.reshape(-1)]))
+        edges = np.ascontiguousarray(np.stack([inv[:B], relid, inv[B:2 * B]], axis=1))
+        out.append((uniq, edges, np.ascontiguousarray(inv[2 * B + C * NEG:].reshape(C, NEG)), np.ascontiguousarray(inv[2 * B:2 * B + C * NEG].reshape(C, NEG))))
+    return out, C
+
+
 # ------------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
@@ -208,7 +229,14 @@ def run_ours(args):
 
     rng = np.random.default_rng(1000 + rank)
     n_b = K + W
-    host_batches, _ = make_batches(rng, rows, n_b, B)
+    sharded = None
+    if world > 1:
+        from marius_b200.dist import OpsBackend, ShardedTable
+
+        host_batches, _ = make_sharded_batches(rng, rows, rank, world, n_b, B)
+        sharded = ShardedTable(rows, OpsBackend(table, state, ctx, prec))
+    else:
+        host_batches, _ = make_batches(rng, rows, n_b, B)
     pinned = [tuple(torch.from_numpy(x).pin_memory() for x in b) for b in host_batches]
     resident = [tuple(t.to(dev) for t in b) for b in pinned]
     U_mean = float(np.mean([len(b[0]) for b in host_batches]))
@@ -220,13 +248,30 @@ def run_ours(args):
             dist.all_reduce(rel_grads)
         ops.dense_adagrad_step(rels, rel_states, rel_grads, LR)
 
+    remote_rows = []
+
+    def step_sharded(u, e, dn, sn):
+        # ids -> rows -> gradients exchanged over NCCL all-to-all (marius_b200/dist.py); relation grads all-reduced inside
+        out = sharded.train_step(ops.COMPLEX, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM)
+        rel_grads[0].copy_(out["rel_grad"])
+        rel_grads[1].copy_(out["inv_rel_grad"])
+        ops.dense_adagrad_step(rels, rel_states, rel_grads, LR)
+        remote_rows.append(sharded.last_remote_rows)
+        return out["loss"]
+
     def step_resident(i):
         u, e, dn, sn = resident[i]
+        if sharded is not None:
+            step_sharded(u, e, dn, sn)
+            return
         ops.train_step(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, loss=loss, rel_grad=rg, inv_rel_grad=irg)
         dense_step()
 
     def step_host(i):
         u, e, dn, sn = pinned[i]
+        if sharded is not None:
+            l = step_sharded(*(t.to(dev, non_blocking=True) for t in (u, e, dn, sn)))
+            return float(l.item())  # D2H read of the step's loss
         l = ops.train_step_host(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
         dense_step()
         return l
@@ -314,7 +359,10 @@ def run_ours(args):
                     config=dict(workload=f"BASELINE configs[1] shape: ComplEx d={D}, {NEG} negatives/chunk, batch {B} = {C} chunks x {CHUNK}, both-side "
                                          f"corruption, SoftmaxCE-SUM, sparse Adagrad lr {LR}; table {rows} rows x {D} fp32 + Adagrad state resident per GPU "
                                          f"({2 * rows * D * 4 / 1e9:.0f} GB; 1e8 rows + state = 320 GB does not fit 180 GB)",
-                                precision=args.precision, parallelism=f"node-partition shard per GPU x{world}, relation grads all-reduced",
+                                precision=args.precision,
+                                parallelism=(f"table sharded by node partition over {world} GPUs; per batch: src + negatives local, dst uniform over all "
+                                             f"partitions; ids/rows/gradients exchanged by NCCL all-to-all, relation grads all-reduced; "
+                                             f"remote rows/step/rank {np.mean(remote_rows) if remote_rows else 0:.0f}") if world > 1 else "single GPU, fused gather+score+update step",
                                 l2="inputs larger than L2: every step gathers/updates a fresh uniform-random row set of a table >> 126 MB",
                                 unique_rows_per_step=U_mean, step_hbm_gbs_algorithmic=step_hbm, step_hbm_frac=step_hbm / pk["hbm_gbs"],
                                 stage_ms={k: round(v, 4) for k, v in per_stage.items()}, stage_sum_ms=step_stage_ms, last_loss=last_loss),

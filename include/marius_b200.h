@@ -105,6 +105,12 @@ mb_status mb_adagrad_update_rows(float* table, float* state_table, int64_t num_r
 mb_status mb_map_tensors(mb_context* ctx, const int64_t* all_ids, int64_t n, int64_t max_id, int64_t* unique_out, int64_t* mapped_out,
                          int64_t* num_unique_dev, void* stream);
 
+/* mb_reduce_rows_by_key: rows_out[u,:] = sum of rows[i,:] over all i with ids[i] == unique_out[u]; unique_out sorted ascending,
+ * *num_unique (device).  The owner-side merge of the multi-GPU row exchange: gradient rows for the same table
+ * row arriving from different ranks are summed (fixed order, no atomics) before the Adagrad update.  rows_out must hold n rows. */
+mb_status mb_reduce_rows_by_key(mb_context* ctx, const int64_t* ids, const float* rows, int64_t n, int64_t d, int64_t max_id, int64_t* unique_out,
+                                float* rows_out, int64_t* num_unique_dev, void* stream);
+
 /* ---- decoder + training step ---------------------------------------------------------------------------
  * Batch-local problem, exactly the tensors the reference Batch carries (data/batch.h:49-75):
  *   emb   [U,d]  node_embeddings_            edges [B,3] (or [B,2] when kind == DOT): local src, rel, local dst

@@ -605,6 +605,52 @@ mb_status mb_map_tensors(mb_context* ctx, const int64_t* all_ids, int64_t n, int
     return map_tensors_device(all_ids, n, bits_for((uint64_t)max_id), ka, kb, va, vb, flags, hist, total, unique_out, mapped_out, num_unique_dev, st);
 }
 
+mb_status mb_reduce_rows_by_key(mb_context* ctx, const int64_t* ids, const float* rows, int64_t n, int64_t d, int64_t max_id, int64_t* unique_out,
+                                float* rows_out, int64_t* num_unique_dev, void* stream) {
+    MB_REQUIRE(ctx != nullptr && n >= 0 && d > 0 && max_id >= 0, "bad arguments");
+    MB_REQUIRE(n == 0 || (ids && rows && unique_out && rows_out), "null pointer");
+    MB_REQUIRE(num_unique_dev != nullptr, "num_unique_dev is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n == 0) {
+        MB_CUDA_TRY(cudaMemsetAsync(num_unique_dev, 0, sizeof(int64_t), st));
+        return MB_OK;
+    }
+    uint64_t *ka, *kb;
+    uint32_t *va, *vb, *flags, *hist, *total;
+    int64_t* mapped;
+    uint32_t *k32a, *k32b, *v32a, *v32b, *offsets, *hist2;
+    auto lay = [&](Arena& ar) {
+        ka = ar.take<uint64_t>(n);
+        kb = ar.take<uint64_t>(n);
+        va = ar.take<uint32_t>(n);
+        vb = ar.take<uint32_t>(n);
+        flags = ar.take<uint32_t>(n + 1);
+        hist = reinterpret_cast<uint32_t*>(ar.take<char>(sort_scratch_bytes(n)));
+        total = ar.take<uint32_t>(1);
+        mapped = ar.take<int64_t>(n);
+        k32a = ar.take<uint32_t>(n);
+        k32b = ar.take<uint32_t>(n);
+        v32a = ar.take<uint32_t>(n);
+        v32b = ar.take<uint32_t>(n);
+        offsets = ar.take<uint32_t>(n + 2);
+        hist2 = reinterpret_cast<uint32_t*>(ar.take<char>(sort_scratch_bytes(n)));
+    };
+    Arena sizing(nullptr);
+    lay(sizing);
+    MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+    Arena place(ctx->ws);
+    lay(place);
+    // (1) unique ids + position of every input row in the unique list (== map_tensors)
+    MB_TRY(map_tensors_device(ids, n, bits_for((uint64_t)max_id), ka, kb, va, vb, flags, hist, total, unique_out, mapped, num_unique_dev, st));
+    // (2) slots sorted by unique position -> segmented sum in slot order (deterministic)
+    MB_TRY(launch_i64_to_u32(mapped, k32a, n, st));
+    uint32_t *sk = nullptr, *sv = nullptr;
+    MB_TRY(radix_sort_pairs<uint32_t>(k32a, k32b, v32a, v32b, n, bits_for((uint64_t)n), hist2, &sk, &sv, st));
+    MB_TRY(segment_offsets_u32(sk, n, n, offsets, st));  // segments beyond num_unique are empty and write zeros into unused output rows
+    return launch_seg_reduce(0, rows, sv, offsets, n, (int)d, rows_out, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0.f, st);
+}
+
 mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, float* pos, float* neg,
                              float* inv_pos, float* inv_neg, void* stream) {
     MB_REQUIRE(ctx != nullptr, "context is null");

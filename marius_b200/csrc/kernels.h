@@ -18,6 +18,7 @@ size_t sort_scratch_bytes(int64_t n);
 template <typename K>
 mb_status radix_sort_pairs(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_t* vals_b, int64_t n, int key_bits, uint32_t* hist_scratch, K** keys_sorted,
                            uint32_t** vals_sorted, cudaStream_t st);
+mb_status launch_i64_to_u32(const int64_t* in, uint32_t* out, int64_t n, cudaStream_t st);
 mb_status segment_offsets_u32(const uint32_t* sorted_keys, int64_t n, int64_t num_keys, uint32_t* offsets, cudaStream_t st);
 mb_status map_tensors_device(const int64_t* all_ids, int64_t n, int key_bits, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
                              uint32_t* flags, uint32_t* hist_scratch, uint32_t* total_scratch, int64_t* unique_out, int64_t* mapped_out,

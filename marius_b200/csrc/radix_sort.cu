@@ -161,6 +161,10 @@ __global__ void i64_to_u64_kernel(const int64_t* __restrict__ in, uint64_t* __re
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint64_t)in[i];
 }
 
+__global__ void i64_to_u32_kernel(const int64_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)in[i];
+}
+
 inline int blocks_for(int64_t n, int threads) {
     int64_t b = (n + threads - 1) / threads;
     int64_t cap = (int64_t)sm_count() * 8;
@@ -208,6 +212,13 @@ mb_status radix_sort_pairs(K* keys_a, K* keys_b, uint32_t* vals_a, uint32_t* val
 
 template mb_status radix_sort_pairs<uint32_t>(uint32_t*, uint32_t*, uint32_t*, uint32_t*, int64_t, int, uint32_t*, uint32_t**, uint32_t**, cudaStream_t);
 template mb_status radix_sort_pairs<uint64_t>(uint64_t*, uint64_t*, uint32_t*, uint32_t*, int64_t, int, uint32_t*, uint64_t**, uint32_t**, cudaStream_t);
+
+mb_status launch_i64_to_u32(const int64_t* in, uint32_t* out, int64_t n, cudaStream_t st) {
+    if (n == 0) return MB_OK;
+    i64_to_u32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
 
 mb_status segment_offsets_u32(const uint32_t* sorted_keys, int64_t n, int64_t num_keys, uint32_t* offsets, cudaStream_t st) {
     seg_offsets_kernel<uint32_t><<<blocks_for(n + 1, 256), 256, 0, st>>>(sorted_keys, n, num_keys, offsets);

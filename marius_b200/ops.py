@@ -186,6 +186,24 @@ def map_tensors(ctx: Context, all_ids: torch.Tensor, max_id: Optional[int] = Non
     return uniq[: int(cnt.item())], mapped
 
 
+def reduce_rows_by_key(ctx: Context, ids: torch.Tensor, rows: torch.Tensor, max_id: Optional[int] = None):
+    """(sorted unique ids, per-id sum of rows): the owner-side merge of gradient rows received from several ranks."""
+    _need_cuda(ids, rows)
+    _check_indices(ids)
+    n = ids.numel()
+    if rows.dim() != 2 or rows.size(0) != n:
+        raise MariusB200Error(_INVALID, "rows must be [len(ids), d]")
+    rows = rows.contiguous()
+    if max_id is None:
+        max_id = int(ids.max().item()) if n else 0
+    uniq = torch.empty(n, dtype=torch.int64, device=ids.device)
+    out = torch.empty_like(rows)
+    cnt = torch.zeros(1, dtype=torch.int64, device=ids.device)
+    check(lib.mb_reduce_rows_by_key(ctx.handle, _ptr(ids), _ptr(rows), n, rows.size(1), int(max_id), _ptr(uniq), _ptr(out), _ptr(cnt), _stream()))
+    u = int(cnt.item())
+    return uniq[:u], out[:u]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def _make_batch(kind, U, d, edges, rel, inv_rel, dst_negs, src_negs, host=False):
     if edges.dim() != 2 or edges.size(1) not in (2, 3):

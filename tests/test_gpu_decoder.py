@@ -218,3 +218,31 @@ def test_full_shape_property_checks(ops, ctx):
     zero = torch.zeros_like(dev(rel))
     pos, neg, ipos, ineg = ops.decoder_forward(ctx, ops.COMPLEX, dev(emb), dev(edges), zero, zero, dev(dn), dev(sn))
     assert float(pos.abs().max()) == 0.0 and float(neg.abs().max()) == 0.0 and float(ineg.abs().max()) == 0.0
+
+
+def test_sharded_table_single_rank_matches_fused_step(ops, ctx):
+    """marius_b200.dist.ShardedTable with world_size 1 (all three exchanges degenerate to copies) == the fused mb_train_step:
+    exercises OpsBackend (gather, train_batch, reduce_rows_by_key, adagrad_update_rows) on the GPU."""
+    from marius_b200.dist import OpsBackend, ShardedTable
+
+    rng = np.random.default_rng(17)
+    num_nodes, R, B, C, N, d = 8000, 5, 256, 2, 128, 64
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    uniq, edges, dn, sn = O.make_batch(rng, num_nodes, R, B, C, N)
+    t1, s1 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    t2, s2 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    rg = torch.empty(R, d, device="cuda")
+    l1 = ops.train_step(ctx, ops.COMPLEX, t1, s1, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, rel_grad=rg)
+    st = ShardedTable(num_nodes, OpsBackend(t2, s2, ctx))
+    out = st.train_step(ops.COMPLEX, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, ops.REDUCTION_SUM)
+    assert float(l1.item()) == float(out["loss"].item())
+    assert torch.equal(t1, t2) and torch.equal(s1, s2)
+    assert torch.equal(rg, out["rel_grad"])
+    # reduce_rows_by_key with real duplicates
+    ids = torch.tensor([5, 3, 5, 9, 3, 5], device="cuda")
+    rows = torch.arange(6 * 8, device="cuda", dtype=torch.float32).reshape(6, 8)
+    u, s = ops.reduce_rows_by_key(ctx, ids, rows)
+    assert u.tolist() == [3, 5, 9]
+    assert torch.equal(s, torch.stack([rows[1] + rows[4], rows[0] + rows[2] + rows[5], rows[3]]))
