@@ -234,12 +234,15 @@ def run_ours(args):
         from marius_b200.dist import OpsBackend, ShardedTable
 
         host_batches, _ = make_sharded_batches(rng, rows, rank, world, n_b, B)
-        sharded = ShardedTable(rows, OpsBackend(table, state, ctx, prec))
+        cpu_group = dist.new_group(backend="gloo")
+        sharded = ShardedTable(rows, OpsBackend(table, state, ctx, prec), cpu_group=cpu_group)
     else:
         host_batches, _ = make_batches(rng, rows, n_b, B)
     pinned = [tuple(torch.from_numpy(x).pin_memory() for x in b) for b in host_batches]
     resident = [tuple(t.to(dev) for t in b) for b in pinned]
     U_mean = float(np.mean([len(b[0]) for b in host_batches]))
+    # routing metadata (owner bucket sizes) depends only on the unique ids: prepared with the batches, like sampling + mapping
+    routes = [sharded.make_plan(torch.from_numpy(b[0])) for b in host_batches] if sharded is not None else None
     loss = torch.zeros(1, device=dev)
 
     def dense_step():
@@ -250,9 +253,9 @@ def run_ours(args):
 
     remote_rows = []
 
-    def step_sharded(u, e, dn, sn):
+    def step_sharded(u, e, dn, sn, route):
         # ids -> rows -> gradients exchanged over NCCL all-to-all (marius_b200/dist.py); relation grads all-reduced inside
-        out = sharded.train_step(ops.COMPLEX, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM)
+        out = sharded.train_step(ops.COMPLEX, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, route=route)
         rel_grads[0].copy_(out["rel_grad"])
         rel_grads[1].copy_(out["inv_rel_grad"])
         ops.dense_adagrad_step(rels, rel_states, rel_grads, LR)
@@ -262,7 +265,7 @@ def run_ours(args):
     def step_resident(i):
         u, e, dn, sn = resident[i]
         if sharded is not None:
-            step_sharded(u, e, dn, sn)
+            step_sharded(u, e, dn, sn, routes[i])
             return
         ops.train_step(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, loss=loss, rel_grad=rg, inv_rel_grad=irg)
         dense_step()
@@ -270,7 +273,7 @@ def run_ours(args):
     def step_host(i):
         u, e, dn, sn = pinned[i]
         if sharded is not None:
-            l = step_sharded(*(t.to(dev, non_blocking=True) for t in (u, e, dn, sn)))
+            l = step_sharded(*(t.to(dev, non_blocking=True) for t in (u, e, dn, sn)), routes[i])
             return float(l.item())  # D2H read of the step's loss
         l = ops.train_step_host(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
         dense_step()

@@ -101,13 +101,16 @@ mb_status mb_adagrad_update_rows(float* table, float* state_table, int64_t num_r
  * mb_map_tensors  map_tensors  common/util.cpp:180-205 (cat + torch::_unique2(sorted, inverse)), as used by
  *                 DataLoader::edgeSample (dataloader.cpp:399-409,447-461).  `all_ids` [n] global ids ->
  *                 `unique_out` [<= n] sorted unique ids, `mapped_out` [n] position of each input id, *num_unique
- *                 (device int64).  Stable LSD radix sort on the device; bit-identical to the reference.   */
+ *                 (device int64).  Stable LSD radix sort on the device; bit-identical to the reference.  Entries of
+ *                 unique_out past *num_unique are set to -1.                                                  */
 mb_status mb_map_tensors(mb_context* ctx, const int64_t* all_ids, int64_t n, int64_t max_id, int64_t* unique_out, int64_t* mapped_out,
                          int64_t* num_unique_dev, void* stream);
 
 /* mb_reduce_rows_by_key: rows_out[u,:] = sum of rows[i,:] over all i with ids[i] == unique_out[u]; unique_out sorted ascending,
  * *num_unique (device).  The owner-side merge of the multi-GPU row exchange: gradient rows for the same table
- * row arriving from different ranks are summed (fixed order, no atomics) before the Adagrad update.  rows_out must hold n rows. */
+ * row arriving from different ranks are summed (fixed order, no atomics) before the Adagrad update.  unique_out and rows_out hold n
+ * entries; entries past *num_unique are -1 / zero rows, and mb_adagrad_update_rows skips negative ids, so the pair can be fed to
+ * the update without a host round trip. */
 mb_status mb_reduce_rows_by_key(mb_context* ctx, const int64_t* ids, const float* rows, int64_t n, int64_t d, int64_t max_id, int64_t* unique_out,
                                 float* rows_out, int64_t* num_unique_dev, void* stream);
 

@@ -239,6 +239,7 @@ mb_status map_tensors_device(const int64_t* all_ids, int64_t n, int key_bits, ui
     uint64_t* ks;
     uint32_t* vs;
     MB_TRY(radix_sort_pairs<uint64_t>(keys_a, keys_b, vals_a, vals_b, n, key_bits, hist_scratch, &ks, &vs, st));
+    MB_CUDA_TRY(cudaMemsetAsync(unique_out, 0xFF, sizeof(int64_t) * n, st));  // entries past *num_unique read as -1
     head_flags_kernel<<<blocks_for(n, 256), 256, 0, st>>>(ks, n, flags);
     MB_LAUNCH_CHECK();
     scan_kernel<<<1, 1024, 0, st>>>(flags, n, total_scratch);

@@ -164,6 +164,11 @@ __global__ void __launch_bounds__(kThreads) adagrad_update_rows_kernel(float* __
             ok[u] = it.valid();
             if (ok[u]) {
                 int64_t r = __ldg(idx + it.row);
+                if (r < 0) {  // padding entry (mb_reduce_rows_by_key pads its unique list with -1): nothing to update
+                    ok[u] = false;
+                    it.next();
+                    continue;
+                }
                 pe[u] = reinterpret_cast<V*>(table + r * ld) + it.col;
                 ps[u] = reinterpret_cast<V*>(state_table + r * ld) + it.col;
                 g[u] = vload(reinterpret_cast<const V*>(grad + it.row * grad_ld) + it.col);

@@ -47,17 +47,29 @@ class OpsBackend:
         return self.ops.train_batch(self.ctx, kind, emb, None, edges, rel, inv_rel, dst_negs, src_negs, 0.0, reduction, self.precision)
 
     def merge(self, local_rows: torch.Tensor, grads: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self.ops.reduce_rows_by_key(self.ctx, local_rows, grads, max_id=self.table.size(0))
+        # padded: unique ids past the count are -1 and are skipped by the update kernel -> no host synchronisation
+        return self.ops.reduce_rows_by_key(self.ctx, local_rows, grads, max_id=self.table.size(0), padded=True)
 
     def update(self, local_rows: torch.Tensor, grads: torch.Tensor, lr: float) -> None:
         self.ops.adagrad_update_rows(self.table, self.state, local_rows, grads, lr)
 
 
+class RoutePlan:
+    """Split sizes of one batch's exchanges.  They depend only on the batch's unique ids, so -- like sampling and unique-id mapping --
+    they can be prepared by the loader ahead of the step (on the host, counts exchanged over a CPU group) to keep the GPU step free
+    of host round trips."""
+
+    def __init__(self, send_counts, recv_counts):
+        self.send_counts = [int(x) for x in send_counts]
+        self.recv_counts = [int(x) for x in recv_counts]
+
+
 class ShardedTable:
-    def __init__(self, rows_per_rank: int, backend, group=None):
+    def __init__(self, rows_per_rank: int, backend, group=None, cpu_group=None):
         self.rows_per_rank = int(rows_per_rank)
         self.backend = backend
         self.group = group
+        self.cpu_group = cpu_group  # optional gloo group for the tiny count exchange of make_plan()
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.base = self.rank * self.rows_per_rank
@@ -72,22 +84,35 @@ class ShardedTable:
         dist.all_to_all_single(out, x.contiguous(), output_split_sizes=list(out_splits), input_split_sizes=list(in_splits), group=self.group)
         return out
 
-    def plan(self, unique_ids: torch.Tensor):
-        """(send_counts, recv_counts, requested_local_rows): who needs which of my rows for this batch."""
+    def make_plan(self, unique_ids: torch.Tensor) -> RoutePlan:
+        """Bucket the sorted unique ids by owner and exchange the bucket sizes.  `unique_ids` may be a host tensor (preferred: no
+        device synchronisation; the counts travel over `cpu_group` when one was given) or a device tensor."""
         b = owner_bounds(unique_ids, self.rows_per_rank, self.world)
         send_counts = (b[1:] - b[:-1]).to(torch.int64)
         if self.world == 1:
             recv_counts = send_counts.clone()
-        else:
+        elif not unique_ids.is_cuda and (self.cpu_group is not None or dist.get_backend(self.group) == "gloo"):
             recv_counts = torch.empty_like(send_counts)
-            dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        send_l, recv_l = send_counts.tolist(), recv_counts.tolist()
+            dist.all_to_all_single(recv_counts, send_counts, group=self.cpu_group if self.cpu_group is not None else self.group)
+        else:
+            dev = unique_ids.device if unique_ids.is_cuda else torch.device("cuda", torch.cuda.current_device())
+            sc = send_counts.to(dev)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc, group=self.group)
+            recv_counts = rc.cpu()
+        return RoutePlan(send_counts.tolist(), recv_counts.tolist())
+
+    def plan(self, unique_ids: torch.Tensor, route: Optional[RoutePlan] = None):
+        """(send_counts, recv_counts, requested_local_rows): who needs which of my rows for this batch."""
+        if route is None:
+            route = self.make_plan(unique_ids)
+        send_l, recv_l = route.send_counts, route.recv_counts
         req = self._a2a(unique_ids, send_l, recv_l)  # all-to-all #1
         self.last_remote_rows = int(unique_ids.numel() - send_l[self.rank])
         return send_l, recv_l, req - self.base
 
-    def fetch_rows(self, unique_ids: torch.Tensor):
-        send_l, recv_l, req_local = self.plan(unique_ids)
+    def fetch_rows(self, unique_ids: torch.Tensor, route: Optional[RoutePlan] = None):
+        send_l, recv_l, req_local = self.plan(unique_ids, route)
         rows = self.backend.gather(req_local)
         emb = self._a2a(rows, recv_l, send_l)  # all-to-all #2: rows come back in unique-id order
         return emb, (send_l, recv_l, req_local)
@@ -99,10 +124,11 @@ class ShardedTable:
         self.backend.update(rows, gsum, lr)
 
     # -- one training batch -----------------------------------------------------------------------------------------
-    def train_step(self, kind: int, unique_ids: torch.Tensor, edges: torch.Tensor, rel, inv_rel, dst_negs, src_negs, lr: float, reduction: int = 1):
+    def train_step(self, kind: int, unique_ids: torch.Tensor, edges: torch.Tensor, rel, inv_rel, dst_negs, src_negs, lr: float, reduction: int = 1,
+                   route: Optional[RoutePlan] = None):
         """unique_ids: sorted GLOBAL ids; edges / negatives hold batch-local positions into unique_ids (the reference Batch layout).
         Returns the dict of Model::train_batch outputs (loss, rel_grad, inv_rel_grad); relation gradients are summed over ranks."""
-        emb, plan = self.fetch_rows(unique_ids)
+        emb, plan = self.fetch_rows(unique_ids, route)
         out = self.backend.train_batch(kind, emb, edges, rel, inv_rel, dst_negs, src_negs, reduction)
         self.push_grads(out["grad"], plan, lr)
         if self.world > 1:

@@ -186,8 +186,9 @@ def map_tensors(ctx: Context, all_ids: torch.Tensor, max_id: Optional[int] = Non
     return uniq[: int(cnt.item())], mapped
 
 
-def reduce_rows_by_key(ctx: Context, ids: torch.Tensor, rows: torch.Tensor, max_id: Optional[int] = None):
-    """(sorted unique ids, per-id sum of rows): the owner-side merge of gradient rows received from several ranks."""
+def reduce_rows_by_key(ctx: Context, ids: torch.Tensor, rows: torch.Tensor, max_id: Optional[int] = None, padded: bool = False):
+    """(sorted unique ids, per-id sum of rows): the owner-side merge of gradient rows received from several ranks.
+    padded=True returns the full-length buffers (unique ids padded with -1, zero rows) without any host synchronisation."""
     _need_cuda(ids, rows)
     _check_indices(ids)
     n = ids.numel()
@@ -200,6 +201,8 @@ def reduce_rows_by_key(ctx: Context, ids: torch.Tensor, rows: torch.Tensor, max_
     out = torch.empty_like(rows)
     cnt = torch.zeros(1, dtype=torch.int64, device=ids.device)
     check(lib.mb_reduce_rows_by_key(ctx.handle, _ptr(ids), _ptr(rows), n, rows.size(1), int(max_id), _ptr(uniq), _ptr(out), _ptr(cnt), _stream()))
+    if padded:
+        return uniq, out
     u = int(cnt.item())
     return uniq[:u], out[:u]
 
