@@ -181,6 +181,11 @@ mb_status mb_dense_adagrad_step(float* param, float* state_sum, const float* gra
 mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* B, int b_mn, float* D, int M, int N, int K, int batches,
                         int precision, int block_n, void* stream);
 
+/* mb_train_step / mb_train_step_host replay the step as one CUDA graph from the second call with the same signature on (same shapes,
+ * tables, relation tables, output pointers, stream); index tensors and the unique-row count may change freely.  MB_GRAPH=0 in the
+ * environment or mb_graph_enable(ctx, 0) selects plain stream launches. */
+mb_status mb_graph_enable(mb_context* ctx, int on);
+
 /* Per-stage device timing of the step (bench.py's roofline): when enabled, every stage of mb_train_step / mb_train_batch is
  * bracketed by CUDA events recorded on the caller's stream.  mb_profile_read synchronises the device, fills total_ms[stage] and
  * counts[stage] (arrays of mb_profile_num_stages() entries) with the time accumulated since the last read, and resets them. */

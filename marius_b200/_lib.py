@@ -46,6 +46,7 @@ _SIGS = {
     "mb_train_step_host": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
     "mb_dense_adagrad_step": [_vp, _vp, _vp, _i64, _f, _f, _vp],
     "mb_profile_enable": [_vp, _i32],
+    "mb_graph_enable": [_vp, _i32],
     "mb_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }

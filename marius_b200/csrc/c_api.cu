@@ -55,10 +55,27 @@ struct mb_context {
     int64_t* h_dneg = nullptr;
     int64_t* h_sneg = nullptr;
     float* h_loss = nullptr;
+    float* h_loss_pinned = nullptr;  // pinned host landing slot of the step's loss (fixed address: captured by the graph)
     size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
     cudaStream_t side = nullptr;          // index plans (slot / relation sorts) overlap the forward pass here
     cudaStream_t side2 = nullptr;         // the dNeg contraction runs here, concurrently with dA + edge_backward
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    // CUDA-graph replay of the fused step (mb_train_step / mb_train_step_host): one captured graph per call signature
+    struct StepGraph {
+        bool valid = false;
+        int warm = 0;            // eager runs seen with this key (the first run is never captured: it may allocate / set attributes)
+        std::vector<uint64_t> key;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t n_uniq = nullptr, n_edges = nullptr, n_dneg = nullptr, n_sneg = nullptr, n_loss = nullptr;
+    };
+    StepGraph sg;
+    int graphs_enabled = -1;     // MB_GRAPH env (default on)
+    int64_t* g_uniq = nullptr;   // index staging with fixed addresses (graph kernels read these)
+    int64_t* g_edges = nullptr;
+    int64_t* g_dneg = nullptr;
+    int64_t* g_sneg = nullptr;
+    size_t g_uniq_cap = 0, g_edges_cap = 0, g_dneg_cap = 0, g_sneg_cap = 0;
     // optional per-stage CUDA-event timing (mb_profile_*): events are recorded on the caller's stream
     bool profiling = false;
     struct Span {
@@ -71,9 +88,16 @@ struct mb_context {
 
 namespace mb {
 
+static void drop_graph(mb_context* ctx) {
+    if (ctx->sg.exec) cudaGraphExecDestroy(ctx->sg.exec);
+    if (ctx->sg.graph) cudaGraphDestroy(ctx->sg.graph);
+    ctx->sg = mb_context::StepGraph();
+}
+
 static mb_status ensure_ws(mb_context* ctx, size_t bytes, cudaStream_t st) {
     if (bytes <= ctx->ws_bytes) return MB_OK;
     MB_CUDA_TRY(cudaStreamSynchronize(st));
+    drop_graph(ctx);  // captured kernels hold pointers into the old workspace
     if (ctx->ws) MB_CUDA_TRY(cudaFree(ctx->ws));
     ctx->ws = nullptr;
     ctx->ws_bytes = 0;
@@ -459,6 +483,7 @@ mb_status mb_create(int device, mb_context** out) {
     mb_context* c = new mb_context();
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_loss_pinned, sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming);
@@ -483,6 +508,12 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->h_dneg) cudaFree(ctx->h_dneg);
     if (ctx->h_sneg) cudaFree(ctx->h_sneg);
     if (ctx->h_loss) cudaFree(ctx->h_loss);
+    if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
+    drop_graph(ctx);
+    if (ctx->g_uniq) cudaFree(ctx->g_uniq);
+    if (ctx->g_edges) cudaFree(ctx->g_edges);
+    if (ctx->g_dneg) cudaFree(ctx->g_dneg);
+    if (ctx->g_sneg) cudaFree(ctx->g_sneg);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
     if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
@@ -498,6 +529,12 @@ void mb_destroy(mb_context* ctx) {
 }
 
 size_t mb_workspace_bytes(const mb_context* ctx) { return ctx ? ctx->ws_bytes : 0; }
+
+mb_status mb_graph_enable(mb_context* ctx, int on) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    ctx->graphs_enabled = on ? 1 : 0;
+    return MB_OK;
+}
 
 mb_status mb_profile_enable(mb_context* ctx, int on) {
     MB_REQUIRE(ctx != nullptr, "context is null");
@@ -700,6 +737,159 @@ mb_status mb_decoder_backward(mb_context* ctx, const mb_batch* batch, const floa
                      rel_grad, inv_rel_grad, UpdateMode::kBatchLocal, (cudaStream_t)stream, ext);
 }
 
+// ---- CUDA-graph replay of the fused step ------------------------------------------------------------------------------------------
+// The step is ~28 dependent launches on three streams; replaying it as one graph removes the inter-kernel launch gaps and most of
+// the per-step host time.  What changes from batch to batch is only (a) the contents of the index tensors and (b) U, the number of
+// unique rows.  (a): the graph reads fixed staging buffers, refreshed by four memcpy nodes whose source pointer / size are patched
+// before each launch (cudaGraphExecMemcpyNodeSetParams1D).  (b): the graph runs with U = capacity (2B + 2CN >= U); the extra
+// segments are empty and the update kernel skips empty segments, so they touch no memory.
+static mb_status grow_i64(int64_t** p, size_t* cap, size_t need);
+
+static bool graphs_on(mb_context* ctx) {
+    if (ctx->graphs_enabled < 0) {
+        const char* e = getenv("MB_GRAPH");
+        ctx->graphs_enabled = e ? (atoi(e) != 0) : 1;
+    }
+    return ctx->graphs_enabled == 1 && !ctx->profiling;
+}
+
+static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_inputs, float* table, float* state_table, int64_t ld,
+                                const int64_t* unique_ids, float lr, int reduction, int precision, float* loss_dev, float* loss_host, float* rel_grad,
+                                float* inv_rel_grad, cudaStream_t st) {
+    MB_TRY(validate_batch(ub));
+    const int64_t n_e = ub->B * ub->edge_cols, n_n = (int64_t)ub->C * ub->N, cap_u = 2 * ub->B + 2 * n_n;
+    Plan probe;
+    fill_plan_dims(probe, ub, precision);
+    const bool vec = decoder_vec_ok(table, ld, (int)ub->d, probe.has_rel, ub->rel, probe.sides == 2 ? ub->inv_rel : nullptr, probe.sides);
+    const bool eligible = graphs_on(ctx) && vec && probe.use_tc && tc_tile_config() == 1024 && ub->B > 0 && ub->U <= cap_u;
+    if (!eligible && !host_inputs) {
+        return run_train(ctx, ub, nullptr, 0, nullptr, 0, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, nullptr, nullptr, nullptr,
+                         rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st);
+    }
+    // fixed-address staging of the batch's index tensors
+    if ((size_t)cap_u > ctx->g_uniq_cap || (size_t)n_e > ctx->g_edges_cap || (size_t)n_n > ctx->g_dneg_cap || (size_t)n_n > ctx->g_sneg_cap) {
+        MB_CUDA_TRY(cudaStreamSynchronize(st));
+        drop_graph(ctx);
+        MB_TRY(grow_i64(&ctx->g_uniq, &ctx->g_uniq_cap, (size_t)cap_u));
+        MB_TRY(grow_i64(&ctx->g_edges, &ctx->g_edges_cap, (size_t)n_e));
+        MB_TRY(grow_i64(&ctx->g_dneg, &ctx->g_dneg_cap, (size_t)n_n));
+        MB_TRY(grow_i64(&ctx->g_sneg, &ctx->g_sneg_cap, (size_t)n_n));
+    }
+    const cudaMemcpyKind kind = host_inputs ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const bool has_sneg = ub->src_negs != nullptr;
+    float* loss_target = loss_dev ? loss_dev : ctx->h_loss;
+    mb_batch db = *ub;
+    db.edges = ctx->g_edges;
+    db.dst_negs = ctx->g_dneg;
+    db.src_negs = has_sneg ? ctx->g_sneg : nullptr;
+
+    auto stage_inputs = [&]() -> mb_status {  // Batch::to (batch.cpp:21-60) when the inputs are host tensors
+        MB_CUDA_TRY(cudaMemcpyAsync(ctx->g_uniq, unique_ids, sizeof(int64_t) * ub->U, kind, st));
+        MB_CUDA_TRY(cudaMemcpyAsync(ctx->g_edges, ub->edges, sizeof(int64_t) * n_e, kind, st));
+        MB_CUDA_TRY(cudaMemcpyAsync(ctx->g_dneg, ub->dst_negs, sizeof(int64_t) * n_n, kind, st));
+        if (has_sneg) MB_CUDA_TRY(cudaMemcpyAsync(ctx->g_sneg, ub->src_negs, sizeof(int64_t) * n_n, kind, st));
+        return MB_OK;
+    };
+
+    if (!eligible) {  // host inputs without graph replay
+        MB_TRY(stage_inputs());
+        MB_TRY(run_train(ctx, &db, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
+                         nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st));
+        if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
+        return MB_OK;
+    }
+
+    std::vector<uint64_t> key = {(uint64_t)ub->decoder, (uint64_t)ub->d, (uint64_t)ub->B, (uint64_t)ub->R, (uint64_t)ub->C, (uint64_t)ub->N,
+                                 (uint64_t)ub->edge_cols, (uint64_t)(uintptr_t)ub->rel, (uint64_t)(uintptr_t)ub->inv_rel, (uint64_t)has_sneg,
+                                 (uint64_t)(uintptr_t)table, (uint64_t)(uintptr_t)state_table, (uint64_t)ld, (uint64_t)reduction, (uint64_t)precision,
+                                 (uint64_t)(uintptr_t)loss_target, (uint64_t)(uintptr_t)rel_grad, (uint64_t)(uintptr_t)inv_rel_grad, (uint64_t)host_inputs,
+                                 (uint64_t)(loss_host != nullptr), (uint64_t)(uintptr_t)st, 0};
+    std::memcpy(&key.back(), &lr, sizeof(float));
+    if (ctx->sg.key != key) {
+        if (ctx->sg.valid || ctx->sg.exec) {
+            MB_CUDA_TRY(cudaStreamSynchronize(st));
+            drop_graph(ctx);
+        }
+        ctx->sg.key = key;
+        ctx->sg.warm = 0;
+    }
+    mb_batch gb = db;
+    gb.U = cap_u;  // capacity: see the header comment
+    if (!ctx->sg.valid) {
+        if (ctx->sg.warm == 0) {
+            // first sight of this signature: run eagerly (allocations, cudaFuncSetAttribute, tile tables happen here, outside capture)
+            ctx->sg.warm = 1;
+            MB_CUDA_TRY(cudaMemsetAsync(ctx->g_uniq, 0, sizeof(int64_t) * cap_u, st));
+            MB_TRY(stage_inputs());
+            MB_TRY(run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr,
+                             nullptr, nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st));
+            if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
+            return MB_OK;
+        }
+        // capture
+        MB_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        mb_status rs = stage_inputs();
+        if (rs == MB_OK)
+            rs = run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
+                           nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st);
+        if (rs == MB_OK && loss_host && cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rs = MB_ERR_CUDA;
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rs != MB_OK || ce != cudaSuccess || graph == nullptr) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ctx->graphs_enabled = 0;  // fall back to eager launches for the rest of this context's life
+            set_error("graph capture of the step failed; continuing with eager launches");
+            return train_step_any(ctx, ub, host_inputs, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, loss_host, rel_grad,
+                                  inv_rel_grad, st);
+        }
+        cudaGraphExec_t exec = nullptr;
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ctx->graphs_enabled = 0;
+            return train_step_any(ctx, ub, host_inputs, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, loss_host, rel_grad,
+                                  inv_rel_grad, st);
+        }
+        // locate the input-staging memcpy nodes by their destination
+        size_t nn = 0;
+        MB_CUDA_TRY(cudaGraphGetNodes(graph, nullptr, &nn));
+        std::vector<cudaGraphNode_t> nodes(nn);
+        MB_CUDA_TRY(cudaGraphGetNodes(graph, nodes.data(), &nn));
+        for (auto nd : nodes) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeMemcpy) continue;
+            cudaMemcpy3DParms mp;
+            if (cudaGraphMemcpyNodeGetParams(nd, &mp) != cudaSuccess) continue;
+            void* dst = mp.dstPtr.ptr;
+            if (dst == ctx->g_uniq) ctx->sg.n_uniq = nd;
+            else if (dst == ctx->g_edges) ctx->sg.n_edges = nd;
+            else if (dst == ctx->g_dneg) ctx->sg.n_dneg = nd;
+            else if (dst == ctx->g_sneg) ctx->sg.n_sneg = nd;
+            else if (loss_host && dst == ctx->h_loss_pinned) ctx->sg.n_loss = nd;
+        }
+        if (!ctx->sg.n_uniq || !ctx->sg.n_edges || !ctx->sg.n_dneg || (has_sneg && !ctx->sg.n_sneg)) {
+            cudaGraphExecDestroy(exec);
+            cudaGraphDestroy(graph);
+            ctx->graphs_enabled = 0;
+            return train_step_any(ctx, ub, host_inputs, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, loss_host, rel_grad,
+                                  inv_rel_grad, st);
+        }
+        ctx->sg.graph = graph;
+        ctx->sg.exec = exec;
+        ctx->sg.valid = true;
+    }
+    // patch the four input copies and replay
+    MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_uniq, ctx->g_uniq, unique_ids, sizeof(int64_t) * ub->U, kind));
+    MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_edges, ctx->g_edges, ub->edges, sizeof(int64_t) * n_e, kind));
+    MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_dneg, ctx->g_dneg, ub->dst_negs, sizeof(int64_t) * n_n, kind));
+    if (has_sneg) MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_sneg, ctx->g_sneg, ub->src_negs, sizeof(int64_t) * n_n, kind));
+    MB_CUDA_TRY(cudaGraphLaunch(ctx->sg.exec, st));
+    count_launch(28);  // kernels inside the replayed graph (mb_launch_count stays an honest kernel count)
+    return MB_OK;
+}
+
 mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, float* state_table, int64_t num_rows, int64_t ld,
                         const int64_t* unique_ids, float lr, int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad,
                         void* stream) {
@@ -707,9 +897,11 @@ mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, fl
     MB_REQUIRE(table != nullptr && state_table != nullptr && unique_ids != nullptr, "null table / ids");
     MB_REQUIRE(batch == nullptr || ld >= batch->d, "ld < d");
     MB_REQUIRE(num_rows >= 0, "num_rows < 0");
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
-    return run_train(ctx, batch, nullptr, 0, nullptr, 0, table, state_table, ld, unique_ids, lr, reduction, precision, loss, nullptr, nullptr, nullptr,
-                     rel_grad, inv_rel_grad, UpdateMode::kFusedTable, (cudaStream_t)stream);
+    return train_step_any(ctx, batch, false, table, state_table, ld, unique_ids, lr, reduction, precision, loss, nullptr, rel_grad, inv_rel_grad,
+                          (cudaStream_t)stream);
 }
 
 // Diagnostic: D[b] = A[b] . B[b] over K through the contraction kernels, fp32 in / fp32 out.
@@ -754,29 +946,17 @@ mb_status mb_train_step_host(mb_context* ctx, const mb_batch* hb, float* table, 
                              const int64_t* unique_ids_host, float lr, int reduction, int precision, float* loss_host, float* rel_grad,
                              float* inv_rel_grad, void* stream) {
     MB_REQUIRE(ctx != nullptr, "context is null");
-    MB_TRY(validate_batch(hb));
+    MB_REQUIRE(table != nullptr && state_table != nullptr, "null table");
     MB_REQUIRE(unique_ids_host != nullptr, "unique ids are null");
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
     cudaStream_t st = (cudaStream_t)stream;
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
-    const size_t n_e = (size_t)hb->B * hb->edge_cols, n_n = (size_t)hb->C * hb->N;
-    MB_CUDA_TRY(cudaStreamSynchronize(st));  // staging buffers may still be in use by the previous step on this stream
-    MB_TRY(grow_i64(&ctx->h_uniq, &ctx->h_uniq_cap, (size_t)hb->U));
-    MB_TRY(grow_i64(&ctx->h_edges, &ctx->h_edges_cap, n_e));
-    MB_TRY(grow_i64(&ctx->h_dneg, &ctx->h_dneg_cap, n_n));
-    MB_TRY(grow_i64(&ctx->h_sneg, &ctx->h_sneg_cap, n_n));
-    // Batch::to (batch.cpp:21-60): the index tensors of the batch go host -> device on the compute stream
-    MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_uniq, unique_ids_host, sizeof(int64_t) * hb->U, cudaMemcpyHostToDevice, st));
-    MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_edges, hb->edges, sizeof(int64_t) * n_e, cudaMemcpyHostToDevice, st));
-    MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_dneg, hb->dst_negs, sizeof(int64_t) * n_n, cudaMemcpyHostToDevice, st));
-    if (hb->src_negs) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_sneg, hb->src_negs, sizeof(int64_t) * n_n, cudaMemcpyHostToDevice, st));
-    mb_batch db = *hb;
-    db.edges = ctx->h_edges;
-    db.dst_negs = ctx->h_dneg;
-    db.src_negs = hb->src_negs ? ctx->h_sneg : nullptr;
-    MB_TRY(run_train(ctx, &db, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->h_uniq, lr, reduction, precision, ctx->h_loss, nullptr, nullptr,
-                     nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st));
-    if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(loss_host, ctx->h_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    // Batch::to (batch.cpp:21-60): the index tensors go host -> device on the compute stream; the loss comes back; the call returns
+    // when the step has finished (the staging buffers are then free for the next call)
+    MB_TRY(train_step_any(ctx, hb, true, table, state_table, ld, unique_ids_host, lr, reduction, precision, nullptr, loss_host, rel_grad, inv_rel_grad, st));
     MB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (loss_host) *loss_host = *ctx->h_loss_pinned;
     (void)num_rows;
     return MB_OK;
 }

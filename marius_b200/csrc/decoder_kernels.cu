@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegReduceArgs 
         const uint32_t beg = a.offsets[u], end = a.offsets[u + 1];
         float* erow = nullptr;
         float* srow = nullptr;
+        if (MODE == 2 && beg == end) continue;  // padding segment: no table row behind it
         if (MODE == 2) {
             int64_t r = a.ids[u];
             erow = a.table + r * a.ld;

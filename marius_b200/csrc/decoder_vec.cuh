@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
         const uint32_t beg = a.offsets[u], end = a.offsets[u + 1];
         float4 e[CH], s[CH];
         float *erow = nullptr, *srow = nullptr;
+        if (MODE == 2 && beg == end) continue;  // padding segment (graph replay runs with n_seg = capacity): no row, nothing to update
         if (MODE == 2) {  // issue the table reads first: they do not depend on the slot list
             const int64_t r = a.ids[u];
             erow = a.table + r * a.ld;

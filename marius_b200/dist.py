@@ -59,9 +59,10 @@ class RoutePlan:
     they can be prepared by the loader ahead of the step (on the host, counts exchanged over a CPU group) to keep the GPU step free
     of host round trips."""
 
-    def __init__(self, send_counts, recv_counts):
+    def __init__(self, send_counts, recv_counts, req_local=None):
         self.send_counts = [int(x) for x in send_counts]
         self.recv_counts = [int(x) for x in recv_counts]
+        self.req_local = req_local  # optional: the owner-side list of requested local rows (all-to-all #1 done ahead of the step)
 
 
 class ShardedTable:
@@ -84,9 +85,11 @@ class ShardedTable:
         dist.all_to_all_single(out, x.contiguous(), output_split_sizes=list(out_splits), input_split_sizes=list(in_splits), group=self.group)
         return out
 
-    def make_plan(self, unique_ids: torch.Tensor) -> RoutePlan:
+    def make_plan(self, unique_ids: torch.Tensor, ids_device: Optional[torch.Tensor] = None) -> RoutePlan:
         """Bucket the sorted unique ids by owner and exchange the bucket sizes.  `unique_ids` may be a host tensor (preferred: no
-        device synchronisation; the counts travel over `cpu_group` when one was given) or a device tensor."""
+        device synchronisation; the counts travel over `cpu_group` when one was given) or a device tensor.  With `ids_device` (the
+        same ids on the compute device) the id exchange itself (all-to-all #1, 8 B per remote row) is also done here, ahead of the
+        step, so that the step only moves rows and gradients."""
         b = owner_bounds(unique_ids, self.rows_per_rank, self.world)
         send_counts = (b[1:] - b[:-1]).to(torch.int64)
         if self.world == 1:
@@ -100,15 +103,20 @@ class ShardedTable:
             rc = torch.empty_like(sc)
             dist.all_to_all_single(rc, sc, group=self.group)
             recv_counts = rc.cpu()
-        return RoutePlan(send_counts.tolist(), recv_counts.tolist())
+        route = RoutePlan(send_counts.tolist(), recv_counts.tolist())
+        if ids_device is not None:
+            route.req_local = self._a2a(ids_device, route.send_counts, route.recv_counts) - self.base
+        return route
 
     def plan(self, unique_ids: torch.Tensor, route: Optional[RoutePlan] = None):
         """(send_counts, recv_counts, requested_local_rows): who needs which of my rows for this batch."""
         if route is None:
             route = self.make_plan(unique_ids)
         send_l, recv_l = route.send_counts, route.recv_counts
-        req = self._a2a(unique_ids, send_l, recv_l)  # all-to-all #1
         self.last_remote_rows = int(unique_ids.numel() - send_l[self.rank])
+        if route.req_local is not None:
+            return send_l, recv_l, route.req_local
+        req = self._a2a(unique_ids, send_l, recv_l)  # all-to-all #1
         return send_l, recv_l, req - self.base
 
     def fetch_rows(self, unique_ids: torch.Tensor, route: Optional[RoutePlan] = None):

@@ -69,6 +69,10 @@ class Context:
     def workspace_bytes(self) -> int:
         return int(lib.mb_workspace_bytes(self._h))
 
+    def graph(self, on: bool) -> None:
+        """enable / disable CUDA-graph replay of the fused step for this context"""
+        check(lib.mb_graph_enable(self._h, int(bool(on))))
+
     def profile(self, on: bool) -> None:
         check(lib.mb_profile_enable(self._h, int(bool(on))))
 

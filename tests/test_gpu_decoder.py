@@ -246,3 +246,36 @@ def test_sharded_table_single_rank_matches_fused_step(ops, ctx):
     u, s = ops.reduce_rows_by_key(ctx, ids, rows)
     assert u.tolist() == [3, 5, 9]
     assert torch.equal(s, torch.stack([rows[1] + rows[4], rows[0] + rows[2] + rows[5], rows[3]]))
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_graph_replay_matches_eager(ops, host):
+    """The CUDA-graph replay of the fused step (varying index tensors and unique counts, fixed output pointers) is bit-identical to
+    plain stream launches."""
+    rng = np.random.default_rng(31)
+    num_nodes, R, B, C, N, d = 30000, 6, 512, 2, 256, 64
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    batches = [O.make_batch(rng, num_nodes, R, B, C, N) for _ in range(5)]
+    assert len({len(b[0]) for b in batches}) > 1  # the unique-row count really varies
+    results = []
+    for graph_on in (False, True):
+        c = ops.Context(0)
+        c.graph(graph_on)
+        t, st = dev(table), torch.zeros(num_nodes, d, device="cuda")
+        rl, irl = dev(rel), dev(inv_rel)
+        loss = torch.zeros(1, device="cuda")
+        rg, irg = torch.zeros(R, d, device="cuda"), torch.zeros(R, d, device="cuda")
+        losses = []
+        for (u, e, dn, sn) in batches:
+            if host:
+                pin = lambda a: torch.from_numpy(a).pin_memory()
+                losses.append(ops.train_step_host(c, ops.COMPLEX, t, st, pin(u), pin(e), rl, irl, pin(dn), pin(sn), 0.1, rel_grad=rg, inv_rel_grad=irg))
+            else:
+                ops.train_step(c, ops.COMPLEX, t, st, dev(u), dev(e), rl, irl, dev(dn), dev(sn), 0.1, loss=loss, rel_grad=rg, inv_rel_grad=irg)
+                losses.append(float(loss.item()))
+        torch.cuda.synchronize()
+        results.append((t.clone(), st.clone(), rg.clone(), losses))
+    assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])
+    assert torch.equal(results[0][2], results[1][2]) and results[0][3] == results[1][3]
