@@ -243,6 +243,8 @@ def run_ours(args):
     U_mean = float(np.mean([len(b[0]) for b in host_batches]))
     # routing metadata (owner bucket sizes) depends only on the unique ids: prepared with the batches, like sampling + mapping
     routes = [sharded.make_plan(torch.from_numpy(b[0]), ids_device=r[0]) for b, r in zip(host_batches, resident)] if sharded is not None else None
+    if sharded is not None:
+        torch.cuda.synchronize()
     loss = torch.zeros(1, device=dev)
 
     def dense_step():

@@ -59,6 +59,9 @@ struct mb_context {
     size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
     cudaStream_t side = nullptr;          // index plans (slot / relation sorts) overlap the forward pass here
     cudaStream_t side2 = nullptr;         // the dNeg contraction runs here, concurrently with dA + edge_backward
+    cudaStream_t gstream = nullptr;       // graphs are captured / replayed here (the caller's stream may be the legacy default stream,
+                                          // which cannot be captured); ordered against the caller's stream with ev_in / ev_out
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     // CUDA-graph replay of the fused step (mb_train_step / mb_train_step_host): one captured graph per call signature
     struct StepGraph {
@@ -486,6 +489,9 @@ mb_status mb_create(int device, mb_context** out) {
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_loss_pinned, sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -516,6 +522,9 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->g_sneg) cudaFree(ctx->g_sneg);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    if (ctx->gstream) cudaStreamDestroy(ctx->gstream);
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+    if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
     if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -826,16 +835,24 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
             return MB_OK;
         }
-        // capture
-        MB_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        mb_status rs = stage_inputs();
+        // capture (on the context's own stream)
+        cudaStream_t gs = ctx->gstream;
+        MB_CUDA_TRY(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+        mb_status rs = MB_OK;
+        {
+            cudaError_t c1 = cudaMemcpyAsync(ctx->g_uniq, unique_ids, sizeof(int64_t) * ub->U, kind, gs);
+            cudaError_t c2 = cudaMemcpyAsync(ctx->g_edges, ub->edges, sizeof(int64_t) * n_e, kind, gs);
+            cudaError_t c3 = cudaMemcpyAsync(ctx->g_dneg, ub->dst_negs, sizeof(int64_t) * n_n, kind, gs);
+            cudaError_t c4 = has_sneg ? cudaMemcpyAsync(ctx->g_sneg, ub->src_negs, sizeof(int64_t) * n_n, kind, gs) : cudaSuccess;
+            if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess) rs = MB_ERR_CUDA;
+        }
         if (rs == MB_OK)
             rs = run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
-                           nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st);
-        if (rs == MB_OK && loss_host && cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                           nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, gs);
+        if (rs == MB_OK && loss_host && cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, gs) != cudaSuccess)
             rs = MB_ERR_CUDA;
         cudaGraph_t graph = nullptr;
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        cudaError_t ce = cudaStreamEndCapture(gs, &graph);
         if (rs != MB_OK || ce != cudaSuccess || graph == nullptr) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
@@ -885,7 +902,11 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_edges, ctx->g_edges, ub->edges, sizeof(int64_t) * n_e, kind));
     MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_dneg, ctx->g_dneg, ub->dst_negs, sizeof(int64_t) * n_n, kind));
     if (has_sneg) MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_sneg, ctx->g_sneg, ub->src_negs, sizeof(int64_t) * n_n, kind));
-    MB_CUDA_TRY(cudaGraphLaunch(ctx->sg.exec, st));
+    MB_CUDA_TRY(cudaEventRecord(ctx->ev_in, st));
+    MB_CUDA_TRY(cudaStreamWaitEvent(ctx->gstream, ctx->ev_in, 0));
+    MB_CUDA_TRY(cudaGraphLaunch(ctx->sg.exec, ctx->gstream));
+    MB_CUDA_TRY(cudaEventRecord(ctx->ev_out, ctx->gstream));
+    MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out, 0));
     count_launch(28);  // kernels inside the replayed graph (mb_launch_count stays an honest kernel count)
     return MB_OK;
 }

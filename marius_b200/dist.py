@@ -7,8 +7,8 @@ Adagrad-state shard.  One batch on rank r, given its SORTED unique global ids (w
   2. all-to-all #1: ids (int64)            -> every owner learns which of its rows each peer needs;
   3. owner gather (mb_gather_rows) + all-to-all #2: rows (d x fp32) back  -> the batch's [U, d] embedding matrix, in unique order;
   4. local forward / loss / backward on the fused kernels -> gradient rows [U, d] (Adagrad state is NOT shipped: the owner applies it);
-  5. all-to-all #3: gradient rows to the owners; the owner sums rows that arrived for the same table row from different ranks
-     (mb_reduce_rows_by_key: sorted, no atomics) and runs the fused Adagrad read-modify-write (mb_adagrad_update_rows);
+  5. all-to-all #3: gradient rows to the owners; the owner applies the contributions rank by rank with the fused Adagrad
+     read-modify-write (mb_adagrad_update_rows; ids are unique within one contribution, so no atomics and a fixed order);
   6. dense relation gradients: all-reduce (the reference's only collective, nn/model.cpp:136-159).
 
 torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the plumbing for the three exchanges; every byte of table data is
@@ -40,29 +40,29 @@ class OpsBackend:
         self.table, self.state, self.ctx = table, state, ctx
         self.precision = ops.PREC_BF16X3 if precision is None else precision
 
-    def gather(self, local_rows: torch.Tensor) -> torch.Tensor:
-        return self.ops.gather_rows(self.table, local_rows)
+    def gather(self, local_rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.ops.gather_rows(self.table, local_rows, out)
 
     def train_batch(self, kind, emb, edges, rel, inv_rel, dst_negs, src_negs, reduction):
         return self.ops.train_batch(self.ctx, kind, emb, None, edges, rel, inv_rel, dst_negs, src_negs, 0.0, reduction, self.precision)
-
-    def merge(self, local_rows: torch.Tensor, grads: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        # padded: unique ids past the count are -1 and are skipped by the update kernel -> no host synchronisation
-        return self.ops.reduce_rows_by_key(self.ctx, local_rows, grads, max_id=self.table.size(0), padded=True)
 
     def update(self, local_rows: torch.Tensor, grads: torch.Tensor, lr: float) -> None:
         self.ops.adagrad_update_rows(self.table, self.state, local_rows, grads, lr)
 
 
 class RoutePlan:
-    """Split sizes of one batch's exchanges.  They depend only on the batch's unique ids, so -- like sampling and unique-id mapping --
-    they can be prepared by the loader ahead of the step (on the host, counts exchanged over a CPU group) to keep the GPU step free
-    of host round trips."""
+    """Routing metadata of one batch.  It depends only on the batch's sorted unique ids, so -- like sampling and unique-id mapping --
+    the loader can prepare it ahead of the step (on the host; bucket sizes and the 8-byte ids travel first) to keep the GPU step
+    free of host round trips: the step itself then only moves rows and gradient rows."""
 
-    def __init__(self, send_counts, recv_counts, req_local=None):
-        self.send_counts = [int(x) for x in send_counts]
-        self.recv_counts = [int(x) for x in recv_counts]
-        self.req_local = req_local  # optional: the owner-side list of requested local rows (all-to-all #1 done ahead of the step)
+    def __init__(self, bounds, recv_counts, req_local):
+        self.bounds = [int(x) for x in bounds]            # owner j's slice of the unique list is [bounds[j], bounds[j+1])
+        self.recv_counts = [int(x) for x in recv_counts]  # rows peer j needs from me (0 for myself)
+        self.req_local = req_local                        # my local row ids requested by the peers, concatenated in rank order
+
+    @property
+    def send_counts(self):
+        return [self.bounds[j + 1] - self.bounds[j] for j in range(len(self.bounds) - 1)]
 
 
 class ShardedTable:
@@ -74,71 +74,98 @@ class ShardedTable:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.base = self.rank * self.rows_per_rank
-        self.last_remote_rows = 0  # rows of the last batch that crossed a rank boundary (either direction is symmetric in size)
+        self.last_remote_rows = 0  # rows of the last batch fetched from other ranks
 
     # -- exchanges ------------------------------------------------------------------------------------------------
-    def _a2a(self, x: torch.Tensor, in_splits, out_splits) -> torch.Tensor:
-        out = x.new_empty((int(sum(out_splits)),) + tuple(x.shape[1:]))
+    def _exchange(self, send_parts, recv_parts):
+        """all-to-all over lists of (possibly empty) contiguous tensors; entry `rank` is ignored (local rows never enter NCCL)."""
         if self.world == 1:
-            out.copy_(x)
-            return out
-        dist.all_to_all_single(out, x.contiguous(), output_split_sizes=list(out_splits), input_split_sizes=list(in_splits), group=self.group)
-        return out
+            return
+        # grouped point-to-point (ncclGroupStart/End under NCCL, plain isend/irecv under gloo); empty parts are skipped on both ends
+        ops_ = []
+        for j in range(self.world):
+            if j == self.rank:
+                continue
+            if recv_parts[j].numel() > 0:
+                ops_.append(dist.P2POp(dist.irecv, recv_parts[j], j, self.group))
+            if send_parts[j].numel() > 0:
+                ops_.append(dist.P2POp(dist.isend, send_parts[j].contiguous(), j, self.group))
+        if ops_:
+            for w in dist.batch_isend_irecv(ops_):
+                w.wait()
 
     def make_plan(self, unique_ids: torch.Tensor, ids_device: Optional[torch.Tensor] = None) -> RoutePlan:
-        """Bucket the sorted unique ids by owner and exchange the bucket sizes.  `unique_ids` may be a host tensor (preferred: no
-        device synchronisation; the counts travel over `cpu_group` when one was given) or a device tensor.  With `ids_device` (the
-        same ids on the compute device) the id exchange itself (all-to-all #1, 8 B per remote row) is also done here, ahead of the
-        step, so that the step only moves rows and gradients."""
-        b = owner_bounds(unique_ids, self.rows_per_rank, self.world)
+        """Bucket the sorted unique ids by owner (contiguous slices), exchange the bucket sizes and the ids (all-to-all #1).
+        `unique_ids`: host tensor preferred (no device sync; counts over `cpu_group` when given).  `ids_device`: the same ids on the
+        compute device (defaults to unique_ids)."""
+        if ids_device is None:
+            ids_device = unique_ids
+        b = owner_bounds(unique_ids, self.rows_per_rank, self.world).cpu()
         send_counts = (b[1:] - b[:-1]).to(torch.int64)
+        send_counts[self.rank] = 0  # my own slice is served locally
         if self.world == 1:
             recv_counts = send_counts.clone()
         elif not unique_ids.is_cuda and (self.cpu_group is not None or dist.get_backend(self.group) == "gloo"):
             recv_counts = torch.empty_like(send_counts)
             dist.all_to_all_single(recv_counts, send_counts, group=self.cpu_group if self.cpu_group is not None else self.group)
         else:
-            dev = unique_ids.device if unique_ids.is_cuda else torch.device("cuda", torch.cuda.current_device())
-            sc = send_counts.to(dev)
+            sc = send_counts.to(ids_device.device)
             rc = torch.empty_like(sc)
             dist.all_to_all_single(rc, sc, group=self.group)
             recv_counts = rc.cpu()
-        route = RoutePlan(send_counts.tolist(), recv_counts.tolist())
-        if ids_device is not None:
-            route.req_local = self._a2a(ids_device, route.send_counts, route.recv_counts) - self.base
-        return route
+        bl, rl = b.tolist(), recv_counts.tolist()
+        req = ids_device.new_empty(int(sum(rl)))
+        send_parts = [ids_device[bl[j]:bl[j + 1]] if j != self.rank else ids_device[:0] for j in range(self.world)]
+        recv_parts = list(torch.split(req, rl)) if self.world > 1 else []
+        self._exchange(send_parts, recv_parts)  # all-to-all #1: ids
+        return RoutePlan(bl, rl, req - self.base)
 
-    def plan(self, unique_ids: torch.Tensor, route: Optional[RoutePlan] = None):
-        """(send_counts, recv_counts, requested_local_rows): who needs which of my rows for this batch."""
-        if route is None:
-            route = self.make_plan(unique_ids)
-        send_l, recv_l = route.send_counts, route.recv_counts
-        self.last_remote_rows = int(unique_ids.numel() - send_l[self.rank])
-        if route.req_local is not None:
-            return send_l, recv_l, route.req_local
-        req = self._a2a(unique_ids, send_l, recv_l)  # all-to-all #1
-        return send_l, recv_l, req - self.base
+    def fetch_rows(self, unique_ids: torch.Tensor, route: RoutePlan) -> torch.Tensor:
+        r, bl = self.rank, route.bounds
+        own = unique_ids[bl[r]:bl[r + 1]] - self.base
+        if self.world == 1:
+            self.last_remote_rows = 0
+            return self.backend.gather(own)
+        rows = self.backend.gather(route.req_local)  # what the peers asked of me
+        emb = rows.new_empty((unique_ids.numel(), rows.size(1)))
+        self.backend.gather(own, emb[bl[r]:bl[r + 1]])  # local rows: gathered straight into their slice of the batch matrix
+        send_parts = list(torch.split(rows, route.recv_counts))
+        recv_parts = [emb[bl[j]:bl[j + 1]] if j != r else emb[:0] for j in range(self.world)]
+        self._exchange(send_parts, recv_parts)  # all-to-all #2: rows land in unique-id order
+        self.last_remote_rows = int(unique_ids.numel() - (bl[r + 1] - bl[r]))
+        return emb
 
-    def fetch_rows(self, unique_ids: torch.Tensor, route: Optional[RoutePlan] = None):
-        send_l, recv_l, req_local = self.plan(unique_ids, route)
-        rows = self.backend.gather(req_local)
-        emb = self._a2a(rows, recv_l, send_l)  # all-to-all #2: rows come back in unique-id order
-        return emb, (send_l, recv_l, req_local)
-
-    def push_grads(self, grads: torch.Tensor, plan, lr: float) -> None:
-        send_l, recv_l, req_local = plan
-        g = self._a2a(grads, send_l, recv_l)  # all-to-all #3
-        rows, gsum = self.backend.merge(req_local, g)
-        self.backend.update(rows, gsum, lr)
+    def push_grads(self, unique_ids: torch.Tensor, grads: torch.Tensor, route: RoutePlan, lr: float) -> None:
+        """Gradient rows go to their owners (all-to-all #3).  The owner applies the contributions in rank order, each with the fused
+        Adagrad read-modify-write (ids are unique within one contribution) -- the per-batch update the reference applies,
+        dataloader.cpp:550-557."""
+        r, bl = self.rank, route.bounds
+        recv = grads.new_empty((int(sum(route.recv_counts)), grads.size(1)))
+        if self.world > 1:
+            send_parts = [grads[bl[j]:bl[j + 1]] if j != r else grads[:0] for j in range(self.world)]
+            recv_parts = list(torch.split(recv, route.recv_counts))
+            self._exchange(send_parts, recv_parts)
+        own = unique_ids[bl[r]:bl[r + 1]] - self.base
+        off = 0
+        for j in range(self.world):
+            if j == r:
+                self.backend.update(own, grads[bl[r]:bl[r + 1]], lr)
+            elif route.recv_counts[j] > 0:
+                n = route.recv_counts[j]
+                self.backend.update(route.req_local[off:off + n], recv[off:off + n], lr)
+            if j != r:
+                off += route.recv_counts[j]
 
     # -- one training batch -----------------------------------------------------------------------------------------
     def train_step(self, kind: int, unique_ids: torch.Tensor, edges: torch.Tensor, rel, inv_rel, dst_negs, src_negs, lr: float, reduction: int = 1,
                    route: Optional[RoutePlan] = None):
         """unique_ids: sorted GLOBAL ids; edges / negatives hold batch-local positions into unique_ids (the reference Batch layout).
         Returns the dict of Model::train_batch outputs (loss, rel_grad, inv_rel_grad); relation gradients are summed over ranks."""
-        emb, plan = self.fetch_rows(unique_ids, route)
+        if route is None:
+            route = self.make_plan(unique_ids)
+        emb = self.fetch_rows(unique_ids, route)
         out = self.backend.train_batch(kind, emb, edges, rel, inv_rel, dst_negs, src_negs, reduction)
-        self.push_grads(out["grad"], plan, lr)
+        self.push_grads(unique_ids, out["grad"], route, lr)
         if self.world > 1:
             for k in ("rel_grad", "inv_rel_grad"):
                 if out.get(k) is not None:

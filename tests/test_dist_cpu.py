@@ -22,21 +22,18 @@ class OracleBackend:
 
         self.O, self.table, self.state = O, table, state
 
-    def gather(self, local_rows):
-        return torch.from_numpy(self.O.index_read(self.table, local_rows.numpy()))
+    def gather(self, local_rows, out=None):
+        rows = torch.from_numpy(self.O.index_read(self.table, local_rows.numpy()))
+        if out is not None:
+            out.copy_(rows)
+            return out
+        return rows
 
     def train_batch(self, kind, emb, edges, rel, inv_rel, dn, sn, reduction):
         r = self.O.train_batch(kind, emb.numpy(), np.zeros_like(emb.numpy()), edges.numpy(), rel.numpy(), inv_rel.numpy(), dn.numpy(), sn.numpy(), 0.0,
                                reduction)
         return dict(loss=torch.tensor([float(r.loss)]), grad=torch.from_numpy(r.grad), rel_grad=torch.from_numpy(r.rel_grad),
                     inv_rel_grad=torch.from_numpy(r.inv_rel_grad))
-
-    def merge(self, local_rows, grads):
-        ids = local_rows.numpy()
-        u, inv = np.unique(ids, return_inverse=True)
-        out = np.zeros((len(u), grads.shape[1]), np.float32)
-        np.add.at(out, inv, grads.numpy())  # arrival order = sender rank order
-        return torch.from_numpy(u.astype(np.int64)), torch.from_numpy(out)
 
     def update(self, local_rows, grads, lr):
         idx = local_rows.numpy()
@@ -98,8 +95,8 @@ def test_sharded_train_step_world2(tmp_path):
 
     world, rows_per_rank, d, R, B, C, N = 2, 150, 16, 3, 40, 2, 24
     mp.spawn(_worker, args=(world, _free_port(), rows_per_rank, d, R, B, C, N, str(tmp_path)), nprocs=world, join=True)
-    # single-process reference: both batches read the same pre-update table, gradients of shared rows are summed in rank order,
-    # one Adagrad update per touched row
+    # single-process reference: both batches read the same pre-update table; every owner then applies the contributions rank by
+    # rank, each as one sparse Adagrad update (Batch::accumulateGradients + indexAdd x2)
     table, state, rel, inv_rel, batches = _problem(world, rows_per_rank, d, R, B, C, N)
     total = world * rows_per_rank
     gsum = np.zeros((total, d), np.float32)
@@ -116,14 +113,10 @@ def test_sharded_train_step_world2(tmp_path):
             per_owner[o].append((uniq[m], res.grad[m]))
     exp_table, exp_state = table.copy(), state.copy()
     for o in range(world):
-        ids = np.concatenate([x[0] for x in per_owner[o]])
-        g = np.concatenate([x[1] for x in per_owner[o]])
-        u, inv = np.unique(ids, return_inverse=True)
-        acc = np.zeros((len(u), d), np.float32)
-        np.add.at(acc, inv, g)
-        de, ds = O.accumulate_gradients(acc, exp_state[u], 0.1)
-        exp_table[u] += de
-        exp_state[u] += ds
+        for ids, g in per_owner[o]:  # sender rank order
+            de, ds = O.accumulate_gradients(g, exp_state[ids], 0.1)
+            exp_table[ids] += de
+            exp_state[ids] += ds
     for r in range(world):
         got = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
         lo, hi = r * rows_per_rank, (r + 1) * rows_per_rank

@@ -240,7 +240,7 @@ def test_sharded_table_single_rank_matches_fused_step(ops, ctx):
     assert float(l1.item()) == float(out["loss"].item())
     assert torch.equal(t1, t2) and torch.equal(s1, s2)
     assert torch.equal(rg, out["rel_grad"])
-    # reduce_rows_by_key with real duplicates
+    # reduce_rows_by_key (owner-side merge primitive) with real duplicates
     ids = torch.tensor([5, 3, 5, 9, 3, 5], device="cuda")
     rows = torch.arange(6 * 8, device="cuda", dtype=torch.float32).reshape(6, 8)
     u, s = ops.reduce_rows_by_key(ctx, ids, rows)
