@@ -230,12 +230,17 @@ def run_ours(args):
     rng = np.random.default_rng(1000 + rank)
     n_b = K + W
     sharded = None
+    peer = None
     if world > 1:
-        from marius_b200.dist import OpsBackend, ShardedTable
+        from marius_b200.dist import OpsBackend, PeerShardedTable, ShardedTable
 
         host_batches, _ = make_sharded_batches(rng, rows, rank, world, n_b, B)
-        cpu_group = dist.new_group(backend="gloo")
-        sharded = ShardedTable(rows, OpsBackend(table, state, ctx, prec), cpu_group=cpu_group)
+        if args.exchange == "peer":
+            # peers' shards mapped over NVLink (CUDA IPC): the fused, graph-replayed step reads / updates remote rows directly
+            peer = PeerShardedTable(table, state, ctx)
+        else:
+            cpu_group = dist.new_group(backend="gloo")
+            sharded = ShardedTable(rows, OpsBackend(table, state, ctx, prec), cpu_group=cpu_group)
     else:
         host_batches, _ = make_batches(rng, rows, n_b, B)
     pinned = [tuple(torch.from_numpy(x).pin_memory() for x in b) for b in host_batches]
@@ -269,6 +274,10 @@ def run_ours(args):
         if sharded is not None:
             step_sharded(u, e, dn, sn, routes[i])
             return
+        if peer is not None:
+            peer.train_step(ops.COMPLEX, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, loss=loss, rel_grad=rg, inv_rel_grad=irg)
+            dense_step()
+            return
         ops.train_step(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, loss=loss, rel_grad=rg, inv_rel_grad=irg)
         dense_step()
 
@@ -277,6 +286,10 @@ def run_ours(args):
         if sharded is not None:
             l = step_sharded(*(t.to(dev, non_blocking=True) for t in (u, e, dn, sn)), routes[i])
             return float(l.item())  # D2H read of the step's loss
+        if peer is not None:
+            l = peer.train_step_host(ops.COMPLEX, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
+            dense_step()
+            return l
         l = ops.train_step_host(ctx, ops.COMPLEX, table, state, u, e, rel, inv_rel, dn, sn, LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
         dense_step()
         return l
@@ -366,8 +379,11 @@ def run_ours(args):
                                          f"({2 * rows * D * 4 / 1e9:.0f} GB; 1e8 rows + state = 320 GB does not fit 180 GB)",
                                 precision=args.precision,
                                 parallelism=(f"table sharded by node partition over {world} GPUs; per batch: src + negatives local, dst uniform over all "
-                                             f"partitions; ids/rows/gradients exchanged by NCCL all-to-all, relation grads all-reduced; "
-                                             f"remote rows/step/rank {np.mean(remote_rows) if remote_rows else 0:.0f}") if world > 1 else "single GPU, fused gather+score+update step",
+                                             f"partitions (~{(world - 1) / world * 25:.0f}% of a batch's rows are remote); "
+                                             + ("remote rows read and Adagrad-updated over NVLink-mapped peer memory (CUDA IPC) inside the fused step"
+                                                if peer is not None else
+                                                f"rows / gradient rows exchanged by grouped NCCL send/recv, remote rows/step/rank {np.mean(remote_rows) if remote_rows else 0:.0f}")
+                                             + "; relation grads all-reduced (NCCL)") if world > 1 else "single GPU, fused gather+score+update step",
                                 l2="inputs larger than L2: every step gathers/updates a fresh uniform-random row set of a table >> 126 MB",
                                 unique_rows_per_step=U_mean, step_hbm_gbs_algorithmic=step_hbm, step_hbm_frac=step_hbm / pk["hbm_gbs"],
                                 stage_ms={k: round(v, 4) for k, v in per_stage.items()}, stage_sum_ms=step_stage_ms, last_loss=last_loss),
@@ -392,6 +408,9 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=10000)
     ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = remote rows read / updated over NVLink-mapped peer memory inside the fused step; "
+                         "'nccl' = rows and gradient rows exchanged with grouped NCCL send/recv (marius_b200/dist.py ShardedTable)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -166,6 +166,26 @@ mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, fl
                         const int64_t* unique_ids, float lr, int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad,
                         void* stream);
 
+/* The same fused step on a table SHARDED BY NODE PARTITION over the GPUs of one box (replaces the reference's
+ * replicas-plus-shared-host-table scheme, nn/model.cpp:136-159, pipeline/pipeline_gpu.cpp:23).  Rank o owns global rows
+ * [o * rows_per_rank, (o+1) * rows_per_rank); tables[o] / states[o] are the owners' base pointers as seen from THIS process: its
+ * own allocation for o == rank, CUDA-IPC mappings of the peers' allocations otherwise (peer access over NVLink enabled).
+ * `unique_ids` are GLOBAL row ids.  The kernels of mb_train_step read remote rows with plain loads and apply the Adagrad
+ * read-modify-write to remote rows with plain stores: the only cross-GPU traffic is the rows a batch needs, and there is no
+ * staging buffer or collective on the row path.  Rows touched concurrently by two ranks follow the reference's unlocked
+ * (bounded-staleness) update semantics (storage/buffer.cpp:459).  Up to 8 shards. */
+typedef struct mb_shards {
+    float* tables[8];
+    float* states[8];
+    int world;
+    int64_t rows_per_rank;
+} mb_shards;
+mb_status mb_train_step_sharded(mb_context* ctx, const mb_batch* batch, const mb_shards* shards, int64_t ld, const int64_t* unique_ids, float lr,
+                                int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad, void* stream);
+mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* host_batch, const mb_shards* shards, int64_t ld,
+                                     const int64_t* unique_ids_host, float lr, int reduction, int precision, float* loss_host, float* rel_grad,
+                                     float* inv_rel_grad, void* stream);
+
 /* Same call with HOST index buffers (pinned or pageable) -- what a reference-side caller holding a CPU Batch would pass
  * (Batch::to, data/batch.cpp:21-60, moves exactly these tensors): copies unique_ids / edges / negatives to the device on
  * `stream`, runs mb_train_step, copies the loss back into *loss_host and synchronises the stream.          */

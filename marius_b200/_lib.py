@@ -28,6 +28,10 @@ class mb_batch(C.Structure):
                 ("inv_rel", C.c_void_p)]
 
 
+class mb_shards(C.Structure):
+    _fields_ = [("tables", C.c_void_p * 8), ("states", C.c_void_p * 8), ("world", C.c_int), ("rows_per_rank", C.c_int64)]
+
+
 _vp, _i64, _i32, _f = C.c_void_p, C.c_int64, C.c_int, C.c_float
 _SIGS = {
     "mb_create": [_i32, C.POINTER(_vp)],
@@ -43,6 +47,8 @@ _SIGS = {
     "mb_decoder_backward": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mb_train_batch": [_vp, C.POINTER(mb_batch), _vp, _i64, _vp, _i64, _f, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mb_train_step": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
+    "mb_train_step_sharded": [_vp, C.POINTER(mb_batch), C.POINTER(mb_shards), _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
+    "mb_train_step_sharded_host": [_vp, C.POINTER(mb_batch), C.POINTER(mb_shards), _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
     "mb_train_step_host": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],
     "mb_dense_adagrad_step": [_vp, _vp, _vp, _i64, _f, _f, _vp],
     "mb_profile_enable": [_vp, _i32],

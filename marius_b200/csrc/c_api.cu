@@ -258,7 +258,7 @@ static mb_status tc_contract(int cfg, const void* A_hi, const void* A_lo, int64_
 
 // forward: adjusted rows A, positive scores, negative rows, score GEMM.  S0/S1 are the score outputs per side ([Bp,N] each).
 static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, const int64_t* row_map, int precision,
-                             float* pos, float* S0, float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false) {
+                             float* pos, float* S0, float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false, const mb_shards* sh = nullptr) {
     const int d = (int)p.d;
     const int64_t a_half = p.sides * p.Bp * d;  // hi block then lo block, each [sides][Bp][d]
     const int64_t n_half = p.sides * p.CN * d;
@@ -266,7 +266,7 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
         StageTimer tm(ctx, ST_PREP, st);
         // the fp32 adjusted rows are only read by the SIMT GEMM and by the scalar (general-d) backward kernel
         const bool need_A = !p.use_tc || !decoder_vec_ok(emb, emb_ld, d, p.has_rel, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.sides);
-        MB_TRY(launch_prep(emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, p.CN, d, b->decoder, p.sides,
+        MB_TRY(launch_prep(sh, emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, p.CN, d, b->decoder, p.sides,
                            b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, need_A ? p.A : nullptr, pos, p.use_tc ? (void*)p.A_hl : nullptr,
                            p.use_tc ? (void*)(p.A_hl + a_half) : nullptr, p.NegE, p.use_tc ? (void*)p.Neg_hl : nullptr,
                            p.use_tc ? (void*)(p.Neg_hl + n_half) : nullptr, st));
@@ -316,7 +316,8 @@ static mb_status run_index_plans(mb_context* ctx, const Plan& p, const mb_batch*
 static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_in, int64_t emb_ld, const float* state, int64_t state_ld, float* table,
                            float* state_table, int64_t ld, const int64_t* unique_ids, float lr, int reduction, int precision, float* loss,
                            float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad, UpdateMode mode, cudaStream_t st,
-                           const float* const* ext = nullptr /* {gpos, gneg, ginv_pos, ginv_neg}: upstream gradients instead of the fused loss */) {
+                           const float* const* ext = nullptr /* {gpos, gneg, ginv_pos, ginv_neg}: upstream gradients instead of the fused loss */,
+                           const mb_shards* sh = nullptr /* table sharded over peer GPUs: unique_ids are global rows */) {
     MB_TRY(validate_batch(b));
     MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
     MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
@@ -355,6 +356,9 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
             emb = table;
             emb_ld = ld;
             row_map = unique_ids;
+        } else if (sh != nullptr && sh->world > 1) {
+            set_error("the sharded step needs the vector kernels (d % 8 == 0, 16-byte aligned tables)");
+            return MB_ERR_UNSUPPORTED;
         } else {
             StageTimer tm(ctx, ST_GATHER, st);
             MB_TRY(gather_rows(table, ld, d, unique_ids, p.U, p.emb_u, d, st));
@@ -363,7 +367,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         }
     }
 
-    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, row_map, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr));
+    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, row_map, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr, sh));
 
     // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
     const int64_t rows = p.sides * p.Bp;
@@ -435,7 +439,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     }
     {
         StageTimer tm(ctx, ST_EDGE_BWD, st);
-        MB_TRY(launch_edge_bwd(emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, p.sides, p.A, p.dA,
+        MB_TRY(launch_edge_bwd(sh, emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, p.sides, p.A, p.dA,
                                p.gpos, p.gcat, p.has_rel ? p.drel : nullptr, st));
     }
     // ---- join: the slot / relation plans and the negative-row gradients are needed from here on
@@ -445,12 +449,12 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         // node gradients: segmented sum over sorted slots (+ Adagrad)
         StageTimer tm(ctx, ST_UPDATE, st);
         if (fused) {
-            MB_TRY(launch_seg_reduce(2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st));
+            MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st));
         } else if (delta_e != nullptr || delta_s != nullptr) {
             MB_REQUIRE(state != nullptr && delta_e != nullptr && delta_s != nullptr, "delta_e/delta_s need state and both outputs");
-            MB_TRY(launch_seg_reduce(1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
+            MB_TRY(launch_seg_reduce(nullptr, 1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
         } else if (grad != nullptr) {
-            MB_TRY(launch_seg_reduce(0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
+            MB_TRY(launch_seg_reduce(nullptr, 0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
         }
     }
     if (need_rel) {
@@ -694,7 +698,7 @@ mb_status mb_reduce_rows_by_key(mb_context* ctx, const int64_t* ids, const float
     uint32_t *sk = nullptr, *sv = nullptr;
     MB_TRY(radix_sort_pairs<uint32_t>(k32a, k32b, v32a, v32b, n, bits_for((uint64_t)n), hist2, &sk, &sv, st));
     MB_TRY(segment_offsets_u32(sk, n, n, offsets, st));  // segments beyond num_unique are empty and write zeros into unused output rows
-    return launch_seg_reduce(0, rows, sv, offsets, n, (int)d, rows_out, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0.f, st);
+    return launch_seg_reduce(nullptr, 0, rows, sv, offsets, n, (int)d, rows_out, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0.f, st);
 }
 
 mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, float* pos, float* neg,
@@ -764,7 +768,7 @@ static bool graphs_on(mb_context* ctx) {
 
 static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_inputs, float* table, float* state_table, int64_t ld,
                                 const int64_t* unique_ids, float lr, int reduction, int precision, float* loss_dev, float* loss_host, float* rel_grad,
-                                float* inv_rel_grad, cudaStream_t st) {
+                                float* inv_rel_grad, cudaStream_t st, const mb_shards* sh = nullptr) {
     MB_TRY(validate_batch(ub));
     const int64_t n_e = ub->B * ub->edge_cols, n_n = (int64_t)ub->C * ub->N, cap_u = 2 * ub->B + 2 * n_n;
     Plan probe;
@@ -773,7 +777,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     const bool eligible = graphs_on(ctx) && vec && probe.use_tc && tc_tile_config() == 1024 && ub->B > 0 && ub->U <= cap_u;
     if (!eligible && !host_inputs) {
         return run_train(ctx, ub, nullptr, 0, nullptr, 0, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, nullptr, nullptr, nullptr,
-                         rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st);
+                         rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh);
     }
     // fixed-address staging of the batch's index tensors
     if ((size_t)cap_u > ctx->g_uniq_cap || (size_t)n_e > ctx->g_edges_cap || (size_t)n_n > ctx->g_dneg_cap || (size_t)n_n > ctx->g_sneg_cap) {
@@ -814,6 +818,14 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
                                  (uint64_t)(uintptr_t)loss_target, (uint64_t)(uintptr_t)rel_grad, (uint64_t)(uintptr_t)inv_rel_grad, (uint64_t)host_inputs,
                                  (uint64_t)(loss_host != nullptr), (uint64_t)(uintptr_t)st, 0};
     std::memcpy(&key.back(), &lr, sizeof(float));
+    if (sh != nullptr) {
+        key.push_back((uint64_t)sh->world);
+        key.push_back((uint64_t)sh->rows_per_rank);
+        for (int i = 0; i < sh->world && i < 8; i++) {
+            key.push_back((uint64_t)(uintptr_t)sh->tables[i]);
+            key.push_back((uint64_t)(uintptr_t)sh->states[i]);
+        }
+    }
     if (ctx->sg.key != key) {
         if (ctx->sg.valid || ctx->sg.exec) {
             MB_CUDA_TRY(cudaStreamSynchronize(st));
@@ -848,7 +860,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
         }
         if (rs == MB_OK)
             rs = run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
-                           nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, gs);
+                           nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, gs, nullptr, sh);
         if (rs == MB_OK && loss_host && cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, gs) != cudaSuccess)
             rs = MB_ERR_CUDA;
         cudaGraph_t graph = nullptr;
@@ -859,7 +871,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             ctx->graphs_enabled = 0;  // fall back to eager launches for the rest of this context's life
             set_error("graph capture of the step failed; continuing with eager launches");
             return train_step_any(ctx, ub, host_inputs, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, loss_host, rel_grad,
-                                  inv_rel_grad, st);
+                                  inv_rel_grad, st, sh);
         }
         cudaGraphExec_t exec = nullptr;
         if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
@@ -867,7 +879,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             cudaGetLastError();
             ctx->graphs_enabled = 0;
             return train_step_any(ctx, ub, host_inputs, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, loss_host, rel_grad,
-                                  inv_rel_grad, st);
+                                  inv_rel_grad, st, sh);
         }
         // locate the input-staging memcpy nodes by their destination
         size_t nn = 0;
@@ -891,7 +903,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             cudaGraphDestroy(graph);
             ctx->graphs_enabled = 0;
             return train_step_any(ctx, ub, host_inputs, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, loss_host, rel_grad,
-                                  inv_rel_grad, st);
+                                  inv_rel_grad, st, sh);
         }
         ctx->sg.graph = graph;
         ctx->sg.exec = exec;
@@ -923,6 +935,39 @@ mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, fl
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
     return train_step_any(ctx, batch, false, table, state_table, ld, unique_ids, lr, reduction, precision, loss, nullptr, rel_grad, inv_rel_grad,
                           (cudaStream_t)stream);
+}
+
+static mb_status check_shards(const mb_shards* sh) {
+    MB_REQUIRE(sh != nullptr && sh->world >= 1 && sh->world <= 8 && sh->rows_per_rank > 0, "bad shard description");
+    for (int i = 0; i < sh->world; i++) MB_REQUIRE(sh->tables[i] != nullptr && sh->states[i] != nullptr, "null shard pointer");
+    return MB_OK;
+}
+
+mb_status mb_train_step_sharded(mb_context* ctx, const mb_batch* batch, const mb_shards* shards, int64_t ld, const int64_t* unique_ids, float lr,
+                                int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad, void* stream) {
+    MB_REQUIRE(ctx != nullptr && unique_ids != nullptr, "null context / ids");
+    MB_TRY(check_shards(shards));
+    MB_REQUIRE(batch == nullptr || ld >= batch->d, "ld < d");
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    return train_step_any(ctx, batch, false, shards->tables[0], shards->states[0], ld, unique_ids, lr, reduction, precision, loss, nullptr, rel_grad,
+                          inv_rel_grad, (cudaStream_t)stream, shards);
+}
+
+mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* hb, const mb_shards* shards, int64_t ld, const int64_t* unique_ids_host, float lr,
+                                     int reduction, int precision, float* loss_host, float* rel_grad, float* inv_rel_grad, void* stream) {
+    MB_REQUIRE(ctx != nullptr && unique_ids_host != nullptr, "null context / ids");
+    MB_TRY(check_shards(shards));
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    MB_TRY(train_step_any(ctx, hb, true, shards->tables[0], shards->states[0], ld, unique_ids_host, lr, reduction, precision, nullptr, loss_host, rel_grad,
+                          inv_rel_grad, st, shards));
+    MB_CUDA_TRY(cudaStreamSynchronize(st));
+    if (loss_host) *loss_host = *ctx->h_loss_pinned;
+    return MB_OK;
 }
 
 // Diagnostic: D[b] = A[b] . B[b] over K through the contraction kernels, fp32 in / fp32 out.

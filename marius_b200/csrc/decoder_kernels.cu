@@ -10,6 +10,8 @@
 // One warp per row everywhere: d=400 -> 100 float4 per row, 3.1 per lane; shuffles for the dots.
 #include <cuda_bf16.h>
 
+#include <cstring>
+
 #include "common.cuh"
 #include "decoder_vec.cuh"
 
@@ -497,7 +499,21 @@ bool decoder_vec_ok(const float* emb, int64_t emb_ld, int d, bool has_rel, const
     return (d % 8 == 0) && (emb_ld % 4 == 0) && al16(emb) && (!has_rel || (al16(rel) && (sides == 1 || al16(inv_rel))));
 }
 
-mb_status launch_prep(const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+static vec::ShardPtrs make_sp(const mb_shards* sh) {
+    vec::ShardPtrs sp;
+    std::memset(&sp, 0, sizeof(sp));
+    if (sh != nullptr && sh->world > 1) {
+        sp.world = sh->world;
+        sp.rows_per_rank = sh->rows_per_rank;
+        for (int i = 0; i < sh->world && i < 8; i++) {
+            sp.table[i] = sh->tables[i];
+            sp.state[i] = sh->states[i];
+        }
+    }
+    return sp;
+}
+
+mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                       int64_t CN, int d, int decoder, int sides, const int64_t* dst_negs, const int64_t* src_negs, float* A /*[sides][Bp][d] or null*/,
                       float* pos /*[sides][Bp]*/, void* A_hi, void* A_lo /*[sides][Bp][d] or null*/, float* Neg /*[sides][CN][d] or null*/,
                       void* Neg_hi, void* Neg_lo, cudaStream_t st) {
@@ -509,6 +525,7 @@ mb_status launch_prep(const float* emb, int64_t emb_ld, const int64_t* row_map, 
         a.emb = emb;
         a.emb_ld = emb_ld;
         a.row_map = row_map;
+        a.sp = make_sp(sh);
         a.edges = edges;
         a.cols = cols;
         a.rel = rel;
@@ -580,7 +597,7 @@ mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, f
     return launch_loss_grad(G, pos, gpos, row_loss, G_hi, G_lo, rows, N, w, st);
 }
 
-mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                           int d, int decoder, int sides, const float* A /*[sides][Bp][d], scalar path only*/, const float* dA, const float* gpos,
                           float* gcat, float* drel /*[sides][B][d] or null*/, cudaStream_t st) {
     if (B == 0) return MB_OK;
@@ -592,6 +609,7 @@ mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* row_m
         a.emb = emb;
         a.emb_ld = emb_ld;
         a.row_map = row_map;
+        a.sp = make_sp(sh);
         a.edges = edges;
         a.cols = cols;
         a.rel = rel;
@@ -626,15 +644,19 @@ mb_status launch_edge_bwd(const float* emb, int64_t emb_ld, const int64_t* row_m
                                 (drel && has_rel && sides == 2) ? drel + B * d : nullptr, st);
 }
 
-mb_status launch_seg_reduce(int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
+mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                             const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
                             const int64_t* ids, float lr, cudaStream_t st) {
     if (n_seg == 0) return MB_OK;
     const bool vec_ok = (d % 4 == 0) && d <= 512 && al16(rows) && (!out || (al16(out) && out_ld % 4 == 0)) && (!state || (al16(state) && state_ld % 4 == 0)) &&
                         (!delta_e || (al16(delta_e) && al16(delta_s))) && (!table || (al16(table) && al16(state_table) && ld % 4 == 0));
+    if (!vec_ok && sh != nullptr && sh->world > 1) {
+        set_error("sharded update needs the vector kernels (d % 4 == 0, aligned tables)");
+        return MB_ERR_UNSUPPORTED;
+    }
     if (!vec_ok)
         return launch_segment_reduce(mode, rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, lr, st);
-    vec::SegVArgs a{rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, -lr};
+    vec::SegVArgs a{rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, -lr, make_sp(sh)};
     int grid = warp_grid(n_seg);
 #define MB_SEG(MODE)                                                                      \
     if (d <= 128)                                                                         \

@@ -36,6 +36,22 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 }
 __device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
 
+// Node-partition-sharded table: rank o owns global rows [o * rows_per_rank, (o+1) * rows_per_rank).  table[o] / state[o]
+// are the owners' base pointers -- local HBM for o == this rank, peer HBM mapped over NVLink (CUDA IPC) otherwise -- so the same fused
+// kernels gather remote rows with plain loads and apply the Adagrad read-modify-write with plain stores: no staging, no collective.
+struct ShardPtrs {
+    float* table[8];
+    float* state[8];
+    int64_t rows_per_rank;
+    int world;  // <= 1: unsharded, `emb` / `table` arguments are used directly
+};
+
+__device__ __forceinline__ const float* shard_row(const ShardPtrs& sp, const float* emb, int64_t emb_ld, int64_t g) {
+    if (sp.world <= 1) return emb + g * emb_ld;
+    const int64_t o = g / sp.rows_per_rank;
+    return sp.table[o] + (g - o * sp.rows_per_rank) * emb_ld;
+}
+
 // x -> (hi, lo) bf16 with x ~= hi + lo ; 4 elements packed into two 8-byte stores
 __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t elem_off, const float4& x) {
     __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
@@ -56,6 +72,7 @@ struct PrepArgs {
     const float* emb;
     int64_t emb_ld;
     const int64_t* row_map;  // null: emb is the batch-local matrix; else emb is the table and row_map = unique ids (gather fused away)
+    ShardPtrs sp;            // with row_map: where global row g lives
     const int64_t* edges;
     int cols;
     const float* rel;      // null: no relation operator
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(kThreads) prep_kernel(PrepArgs a) {
             const int side = q >= a.CN ? 1 : 0;
             const int64_t j = q - (int64_t)side * a.CN;
             const int64_t nid = a.negs[side][j];
-            const float* src = a.emb + (a.row_map ? a.row_map[nid] : nid) * a.emb_ld;
+            const float* src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[nid]) : a.emb + nid * a.emb_ld;
             for (int v = lane; v < dv; v += 32) {
                 float4 x = ld4(src, v);
                 if (a.Neg[side]) st4(a.Neg[side] + j * d, v, x);
@@ -104,13 +121,9 @@ __global__ void __launch_bounds__(kThreads) prep_kernel(PrepArgs a) {
             }
             continue;
         }
-        int64_t si = a.edges[p * a.cols], ti = a.edges[p * a.cols + a.cols - 1];
-        if (a.row_map) {
-            si = a.row_map[si];
-            ti = a.row_map[ti];
-        }
-        const float* src = a.emb + si * a.emb_ld;
-        const float* dst = a.emb + ti * a.emb_ld;
+        const int64_t si = a.edges[p * a.cols], ti = a.edges[p * a.cols + a.cols - 1];
+        const float* src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[si]) : a.emb + si * a.emb_ld;
+        const float* dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[ti]) : a.emb + ti * a.emb_ld;
         const int64_t rid = (DEC != MB_DECODER_DOT) ? a.edges[p * a.cols + 1] : 0;
         const float* r = (DEC != MB_DECODER_DOT) ? a.rel + rid * d : nullptr;
         const float* ri = (DEC != MB_DECODER_DOT && a.sides == 2) ? a.inv_rel + rid * d : nullptr;
@@ -234,6 +247,7 @@ struct EdgeBwdVArgs {
     const float* emb;
     int64_t emb_ld;
     const int64_t* row_map;
+    ShardPtrs sp;
     const int64_t* edges;
     int cols;
     const float* rel;
@@ -254,13 +268,9 @@ __global__ void __launch_bounds__(kThreads) edge_backward_kernel(EdgeBwdVArgs a)
     const int d = a.d, dv = d >> 2, hv = d >> 3;
     const bool inverse = a.sides == 2;
     for (int64_t i = warp0; i < a.B; i += nwarps) {
-        int64_t si = a.edges[i * a.cols], ti = a.edges[i * a.cols + a.cols - 1];
-        if (a.row_map) {
-            si = a.row_map[si];
-            ti = a.row_map[ti];
-        }
-        const float* src = a.emb + si * a.emb_ld;
-        const float* dst = a.emb + ti * a.emb_ld;
+        const int64_t si = a.edges[i * a.cols], ti = a.edges[i * a.cols + a.cols - 1];
+        const float* src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[si]) : a.emb + si * a.emb_ld;
+        const float* dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[ti]) : a.emb + ti * a.emb_ld;
         const int64_t rid = (DEC != MB_DECODER_DOT) ? a.edges[i * a.cols + 1] : 0;
         const float* r = (DEC != MB_DECODER_DOT) ? a.rel + rid * d : nullptr;
         const float* ri = (DEC != MB_DECODER_DOT && inverse) ? a.inv_rel + rid * d : nullptr;
@@ -342,6 +352,7 @@ struct SegVArgs {
     int64_t ld;
     const int64_t* ids;
     float neg_lr;
+    ShardPtrs sp;
 };
 
 __device__ __forceinline__ void adagrad4(const float4& g, const float4& s, float neg_lr, float4& de, float4& ds, float4& sn) {
@@ -364,8 +375,14 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
         if (MODE == 2 && beg == end) continue;  // padding segment (graph replay runs with n_seg = capacity): no row, nothing to update
         if (MODE == 2) {  // issue the table reads first: they do not depend on the slot list
             const int64_t r = a.ids[u];
-            erow = a.table + r * a.ld;
-            srow = a.state_table + r * a.ld;
+            if (a.sp.world <= 1) {
+                erow = a.table + r * a.ld;
+                srow = a.state_table + r * a.ld;
+            } else {  // the owner's HBM (peer-mapped when remote): Adagrad read-modify-write straight over NVLink
+                const int64_t o = r / a.sp.rows_per_rank, lr_ = r - o * a.sp.rows_per_rank;
+                erow = a.sp.table[o] + lr_ * a.ld;
+                srow = a.sp.state[o] + lr_ * a.ld;
+            }
 #pragma unroll
             for (int c = 0; c < CH; c++) {
                 int v = lane + 32 * c;

@@ -171,3 +171,49 @@ class ShardedTable:
                 if out.get(k) is not None:
                     dist.all_reduce(out[k], group=self.group)
         return out
+
+
+class PeerShardedTable:
+    """The sharded table with the rows of the peers mapped into this process (CUDA IPC over NVLink): the fused step
+    (mb_train_step_sharded) gathers remote rows with plain loads and applies their Adagrad update with plain stores -- no staging,
+    no collective on the row path.  Only the dense relation gradients are all-reduced (the caller does that, as in the reference).
+
+    One process per GPU; every process must see all GPUs of the box (torchrun's default)."""
+
+    def __init__(self, table: torch.Tensor, state: torch.Tensor, ctx, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        from . import ops
+
+        self.ops, self.ctx, self.group = ops, ctx, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rows_per_rank = table.size(0)
+        self.d = table.size(1)
+        self.ld = table.stride(0)
+        self.table, self.state = table, state
+        tables, states = [None] * self.world, [None] * self.world
+        tables[self.rank], states[self.rank] = table, state
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (reduce_tensor(table), reduce_tensor(state)), group=group)
+            for r, (ht, hs) in enumerate(handles):
+                if r == self.rank:
+                    continue
+                tables[r] = ht[0](*ht[1])  # cudaIpcOpenMemHandle with lazy peer-access enable
+                states[r] = hs[0](*hs[1])
+            dist.barrier(group=group)
+        self._peers = (tables, states)  # keep the mappings alive
+        self.shards = ops.make_shards(tables, states, self.rows_per_rank)
+
+    def train_step(self, kind, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr, reduction=1, precision=None, loss=None, rel_grad=None,
+                   inv_rel_grad=None):
+        p = self.ops.PREC_BF16X3 if precision is None else precision
+        return self.ops.train_step_sharded(self.ctx, kind, self.shards, self.ld, self.d, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr,
+                                           reduction, p, loss=loss, rel_grad=rel_grad, inv_rel_grad=inv_rel_grad)
+
+    def train_step_host(self, kind, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, lr, reduction=1, precision=None, rel_grad=None,
+                        inv_rel_grad=None) -> float:
+        p = self.ops.PREC_BF16X3 if precision is None else precision
+        return self.ops.train_step_sharded_host(self.ctx, kind, self.shards, self.ld, self.d, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h,
+                                                src_negs_h, lr, reduction, p, rel_grad=rel_grad, inv_rel_grad=inv_rel_grad)

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MariusB200Error, check, lib, mb_batch
+from ._lib import MariusB200Error, check, lib, mb_batch, mb_shards
 
 DOT, DISTMULT, COMPLEX = 0, 1, 2
 REDUCTION_MEAN, REDUCTION_SUM = 0, 1
@@ -304,6 +304,46 @@ def train_step_host(ctx: Context, kind: int, table, state_table, unique_ids_h, e
     check(lib.mb_train_step_host(ctx.handle, C.byref(b), _ptr(table), _ptr(state_table), table.size(0), _rowmajor(table, "table"),
                                  C.c_void_p(uid.data_ptr()), float(lr), int(reduction), int(precision), C.cast(C.pointer(loss), C.c_void_p), _ptr(rel_grad),
                                  _ptr(inv_rel_grad), _stream()))
+    return float(loss.value)
+
+
+def make_shards(tables, states, rows_per_rank: int):
+    """mb_shards from per-owner table / state tensors (this rank's own allocation + CUDA-IPC views of the peers')."""
+    if len(tables) != len(states) or not (1 <= len(tables) <= 8):
+        raise MariusB200Error(_INVALID, "1..8 shards")
+    sh = mb_shards()
+    for i, (t, s_) in enumerate(zip(tables, states)):
+        _need_cuda(t, s_)
+        if t.shape != tables[0].shape or s_.shape != t.shape or _rowmajor(t, "table") != _rowmajor(tables[0], "table"):
+            raise MariusB200Error(_INVALID, "all shards must have the same shape and stride")
+        sh.tables[i] = t.data_ptr()
+        sh.states[i] = s_.data_ptr()
+    sh.world = len(tables)
+    sh.rows_per_rank = int(rows_per_rank)
+    return sh
+
+
+def train_step_sharded(ctx: Context, kind: int, shards, ld: int, d: int, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr: float,
+                       reduction: int = REDUCTION_SUM, precision: int = PREC_BF16X3, loss=None, rel_grad=None, inv_rel_grad=None):
+    """mb_train_step on a table sharded over peer GPUs (global unique ids; remote rows over NVLink loads/stores)."""
+    _need_cuda(unique_ids, edges, rel, inv_rel, dst_negs, src_negs)
+    _check_indices(unique_ids)
+    b, keep = _make_batch(kind, unique_ids.numel(), d, edges, rel, inv_rel, dst_negs, src_negs)
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=unique_ids.device)
+    check(lib.mb_train_step_sharded(ctx.handle, C.byref(b), C.byref(shards), int(ld), _ptr(unique_ids), float(lr), int(reduction), int(precision),
+                                    _ptr(loss), _ptr(rel_grad), _ptr(inv_rel_grad), _stream()))
+    return loss
+
+
+def train_step_sharded_host(ctx: Context, kind: int, shards, ld: int, d: int, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, lr: float,
+                            reduction: int = REDUCTION_SUM, precision: int = PREC_BF16X3, rel_grad=None, inv_rel_grad=None) -> float:
+    _need_cuda(rel, inv_rel)
+    b, keep = _make_batch(kind, unique_ids_h.numel(), d, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, host=True)
+    loss = C.c_float(0.0)
+    uid = unique_ids_h.contiguous()
+    check(lib.mb_train_step_sharded_host(ctx.handle, C.byref(b), C.byref(shards), int(ld), C.c_void_p(uid.data_ptr()), float(lr), int(reduction),
+                                         int(precision), C.cast(C.pointer(loss), C.c_void_p), _ptr(rel_grad), _ptr(inv_rel_grad), _stream()))
     return float(loss.value)
 
 

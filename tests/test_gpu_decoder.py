@@ -279,3 +279,20 @@ def test_graph_replay_matches_eager(ops, host):
         results.append((t.clone(), st.clone(), rg.clone(), losses))
     assert torch.equal(results[0][0], results[1][0]) and torch.equal(results[0][1], results[1][1])
     assert torch.equal(results[0][2], results[1][2]) and results[0][3] == results[1][3]
+
+
+def test_sharded_entry_point_with_one_shard_equals_fused_step(ops, ctx):
+    """mb_train_step_sharded with world == 1 is the plain fused step (same kernels, pointer table of one)."""
+    rng = np.random.default_rng(23)
+    num_nodes, R, B, C, N, d = 6000, 4, 200, 2, 96, 48
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    uniq, edges, dn, sn = O.make_batch(rng, num_nodes, R, B, C, N)
+    t1, s1 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    t2, s2 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    l1 = ops.train_step(ctx, ops.COMPLEX, t1, s1, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1)
+    sh = ops.make_shards([t2], [s2], num_nodes)
+    l2 = ops.train_step_sharded(ctx, ops.COMPLEX, sh, t2.stride(0), d, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1)
+    assert float(l1.item()) == float(l2.item())
+    assert torch.equal(t1, t2) and torch.equal(s1, s2)
