@@ -180,6 +180,13 @@ typedef struct mb_shards {
     int world;
     int64_t rows_per_rank;
 } mb_shards;
+/* CUDA IPC plumbing for one-process-per-GPU deployments: mb_ipc_export returns the 64-byte handle of the allocation containing
+ * `dev_ptr` and the offset of `dev_ptr` inside it; mb_ipc_import opens a peer's handle with the context's device current (lazy peer
+ * access over NVLink) and returns the peer pointer usable in mb_shards.  Mappings are closed by mb_destroy. */
+mb_status mb_ipc_export(const void* dev_ptr, void* handle_out /* 64 bytes */, int64_t* offset_out);
+mb_status mb_ipc_import(mb_context* ctx, const void* handle /* 64 bytes */, int64_t offset, void** ptr_out);
+/* cudaDeviceEnablePeerAccess from the context's device to `peer_device` (idempotent): required before kernels dereference shards of that peer */
+mb_status mb_enable_peer_access(mb_context* ctx, int peer_device);
 mb_status mb_train_step_sharded(mb_context* ctx, const mb_batch* batch, const mb_shards* shards, int64_t ld, const int64_t* unique_ids, float lr,
                                 int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad, void* stream);
 mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* host_batch, const mb_shards* shards, int64_t ld,

@@ -53,6 +53,9 @@ _SIGS = {
     "mb_dense_adagrad_step": [_vp, _vp, _vp, _i64, _f, _f, _vp],
     "mb_profile_enable": [_vp, _i32],
     "mb_graph_enable": [_vp, _i32],
+    "mb_enable_peer_access": [_vp, _i32],
+    "mb_ipc_export": [_vp, _vp, C.POINTER(C.c_int64)],
+    "mb_ipc_import": [_vp, _vp, _i64, C.POINTER(_vp)],
     "mb_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }

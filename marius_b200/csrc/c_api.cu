@@ -57,6 +57,7 @@ struct mb_context {
     float* h_loss = nullptr;
     float* h_loss_pinned = nullptr;  // pinned host landing slot of the step's loss (fixed address: captured by the graph)
     size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
+    std::vector<void*> ipc_mappings;      // peer shards opened with mb_ipc_import (closed in mb_destroy)
     cudaStream_t side = nullptr;          // index plans (slot / relation sorts) overlap the forward pass here
     cudaStream_t side2 = nullptr;         // the dNeg contraction runs here, concurrently with dA + edge_backward
     cudaStream_t gstream = nullptr;       // graphs are captured / replayed here (the caller's stream may be the legacy default stream,
@@ -520,6 +521,7 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->h_loss) cudaFree(ctx->h_loss);
     if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
     drop_graph(ctx);
+    for (void* m : ctx->ipc_mappings) cudaIpcCloseMemHandle(m);
     if (ctx->g_uniq) cudaFree(ctx->g_uniq);
     if (ctx->g_edges) cudaFree(ctx->g_edges);
     if (ctx->g_dneg) cudaFree(ctx->g_dneg);
@@ -542,6 +544,64 @@ void mb_destroy(mb_context* ctx) {
 }
 
 size_t mb_workspace_bytes(const mb_context* ctx) { return ctx ? ctx->ws_bytes : 0; }
+
+mb_status mb_enable_peer_access(mb_context* ctx, int peer_device) {
+    MB_REQUIRE(ctx != nullptr && peer_device >= 0, "bad arguments");
+    if (peer_device == ctx->device) return MB_OK;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    int can = 0;
+    MB_CUDA_TRY(cudaDeviceCanAccessPeer(&can, ctx->device, peer_device));
+    if (!can) {
+        set_error("device " + std::to_string(ctx->device) + " cannot access peer " + std::to_string(peer_device));
+        return MB_ERR_UNSUPPORTED;
+    }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return MB_OK;
+    }
+    MB_CUDA_TRY(e);
+    return MB_OK;
+}
+
+// ---- CUDA IPC for the peer-sharded table -------------------------------------------------------------------------------------
+// The importer must open the handle with ITS OWN device current (the mapping is created for the current device; memory imported
+// under another device's context is not reachable through cudaDeviceEnablePeerAccess), so this is done here rather than through
+// torch's tensor sharing, which opens handles under the exporting device's index.
+mb_status mb_ipc_export(const void* dev_ptr, void* handle_out, int64_t* offset_out) {
+    MB_REQUIRE(dev_ptr != nullptr && handle_out != nullptr && offset_out != nullptr, "null argument");
+    typedef int (*GetRangeFn)(unsigned long long*, size_t*, unsigned long long);
+    static GetRangeFn get_range = [] {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fp = nullptr;
+        return reinterpret_cast<GetRangeFn>(fp);
+    }();
+    unsigned long long base = (unsigned long long)(uintptr_t)dev_ptr;
+    size_t size = 0;
+    if (get_range != nullptr) {
+        unsigned long long b = 0;
+        if (get_range(&b, &size, (unsigned long long)(uintptr_t)dev_ptr) == 0 && b != 0) base = b;
+    }
+    cudaIpcMemHandle_t h;
+    MB_CUDA_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle_out, &h, sizeof(h));
+    *offset_out = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+    return MB_OK;
+}
+
+mb_status mb_ipc_import(mb_context* ctx, const void* handle, int64_t offset, void** ptr_out) {
+    MB_REQUIRE(ctx != nullptr && handle != nullptr && ptr_out != nullptr && offset >= 0, "bad arguments");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* base = nullptr;
+    MB_CUDA_TRY(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->ipc_mappings.push_back(base);
+    *ptr_out = static_cast<char*>(base) + offset;
+    return MB_OK;
+}
 
 mb_status mb_graph_enable(mb_context* ctx, int on) {
     MB_REQUIRE(ctx != nullptr, "context is null");
@@ -807,7 +867,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     if (!eligible) {  // host inputs without graph replay
         MB_TRY(stage_inputs());
         MB_TRY(run_train(ctx, &db, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
-                         nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st));
+                         nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh));
         if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
         return MB_OK;
     }
@@ -843,7 +903,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             MB_CUDA_TRY(cudaMemsetAsync(ctx->g_uniq, 0, sizeof(int64_t) * cap_u, st));
             MB_TRY(stage_inputs());
             MB_TRY(run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr,
-                             nullptr, nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st));
+                             nullptr, nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh));
             if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
             return MB_OK;
         }

@@ -181,8 +181,6 @@ class PeerShardedTable:
     One process per GPU; every process must see all GPUs of the box (torchrun's default)."""
 
     def __init__(self, table: torch.Tensor, state: torch.Tensor, ctx, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
-
         from . import ops
 
         self.ops, self.ctx, self.group = ops, ctx, group
@@ -192,19 +190,21 @@ class PeerShardedTable:
         self.d = table.size(1)
         self.ld = table.stride(0)
         self.table, self.state = table, state
-        tables, states = [None] * self.world, [None] * self.world
-        tables[self.rank], states[self.rank] = table, state
+        tptr, sptr = [0] * self.world, [0] * self.world
+        tptr[self.rank], sptr[self.rank] = table.data_ptr(), state.data_ptr()
         if self.world > 1:
             handles = [None] * self.world
-            dist.all_gather_object(handles, (reduce_tensor(table), reduce_tensor(state)), group=group)
-            for r, (ht, hs) in enumerate(handles):
+            dist.all_gather_object(handles, (ops.ipc_export(table), ops.ipc_export(state), tuple(table.shape), table.stride(0)), group=group)
+            for r, (ht, hs, shape, ld) in enumerate(handles):
+                if shape != tuple(table.shape) or ld != self.ld:
+                    raise ValueError("all shards must have the same shape and stride")
                 if r == self.rank:
                     continue
-                tables[r] = ht[0](*ht[1])  # cudaIpcOpenMemHandle with lazy peer-access enable
-                states[r] = hs[0](*hs[1])
+                # opened with MY device current (mb_ipc_import): loads / stores from my kernels reach the peer's HBM over NVLink
+                tptr[r] = ops.ipc_import(ctx, *ht)
+                sptr[r] = ops.ipc_import(ctx, *hs)
             dist.barrier(group=group)
-        self._peers = (tables, states)  # keep the mappings alive
-        self.shards = ops.make_shards(tables, states, self.rows_per_rank)
+        self.shards = ops.make_shards_raw(tptr, sptr, self.rows_per_rank)
 
     def train_step(self, kind, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr, reduction=1, precision=None, loss=None, rel_grad=None,
                    inv_rel_grad=None):

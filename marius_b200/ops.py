@@ -69,6 +69,9 @@ class Context:
     def workspace_bytes(self) -> int:
         return int(lib.mb_workspace_bytes(self._h))
 
+    def enable_peer_access(self, peer_device: int) -> None:
+        check(lib.mb_enable_peer_access(self._h, int(peer_device)))
+
     def graph(self, on: bool) -> None:
         """enable / disable CUDA-graph replay of the fused step for this context"""
         check(lib.mb_graph_enable(self._h, int(bool(on))))
@@ -305,6 +308,32 @@ def train_step_host(ctx: Context, kind: int, table, state_table, unique_ids_h, e
                                  C.c_void_p(uid.data_ptr()), float(lr), int(reduction), int(precision), C.cast(C.pointer(loss), C.c_void_p), _ptr(rel_grad),
                                  _ptr(inv_rel_grad), _stream()))
     return float(loss.value)
+
+
+def ipc_export(t: torch.Tensor):
+    """(64-byte CUDA IPC handle, byte offset) of a device tensor's storage -- picklable, for torch.distributed.all_gather_object."""
+    _need_cuda(t)
+    h = C.create_string_buffer(64)
+    off = C.c_int64(0)
+    check(lib.mb_ipc_export(_ptr(t), h, C.byref(off)))
+    return bytes(h.raw), int(off.value)
+
+
+def ipc_import(ctx: Context, handle: bytes, offset: int) -> int:
+    """device pointer (int) of a peer's tensor opened in this process with this context's GPU current"""
+    out = C.c_void_p()
+    check(lib.mb_ipc_import(ctx.handle, C.create_string_buffer(handle, 64), int(offset), C.byref(out)))
+    return int(out.value)
+
+
+def make_shards_raw(table_ptrs, state_ptrs, rows_per_rank: int):
+    sh = mb_shards()
+    for i, (t, s_) in enumerate(zip(table_ptrs, state_ptrs)):
+        sh.tables[i] = int(t)
+        sh.states[i] = int(s_)
+    sh.world = len(table_ptrs)
+    sh.rows_per_rank = int(rows_per_rank)
+    return sh
 
 
 def make_shards(tables, states, rows_per_rank: int):

@@ -296,3 +296,30 @@ def test_sharded_entry_point_with_one_shard_equals_fused_step(ops, ctx):
     l2 = ops.train_step_sharded(ctx, ops.COMPLEX, sh, t2.stride(0), d, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1)
     assert float(l1.item()) == float(l2.item())
     assert torch.equal(t1, t2) and torch.equal(s1, s2)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_step_with_local_shards_vs_oracle(ops, ctx, world):
+    """Shard arithmetic of mb_train_step_sharded without any IPC: the `world` shards are separate tensors on ONE GPU; global unique ids
+    address rows across them.  Must equal the oracle on the concatenated table (and the unsharded fused step)."""
+    rng = np.random.default_rng(40 + world)
+    rows, R, B, C, N, d = 3000, 4, 200, 2, 96, 48
+    total = rows * world
+    full = rng.uniform(-0.3, 0.3, (total, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    uniq, edges, dn, sn = O.make_batch(rng, total, R, B, C, N)
+    tables = [dev(full[r * rows:(r + 1) * rows].copy()) for r in range(world)]
+    states = [torch.zeros(rows, d, device="cuda") for _ in range(world)]
+    sh = ops.make_shards(tables, states, rows)
+    rg = torch.empty(R, d, device="cuda")
+    for step in range(3):  # step 0 eager, step 1 captures the graph, step 2 replays it
+        loss = ops.train_step_sharded(ctx, ops.COMPLEX, sh, tables[0].stride(0), d, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1,
+                                      loss=torch.zeros(1, device="cuda") if step == 0 else loss, rel_grad=rg)
+    exp_t, exp_s = full.copy(), np.zeros_like(full)
+    for step in range(3):
+        res = O.train_step_on_table(O.COMPLEX, exp_t, exp_s, uniq, edges, rel, inv_rel, dn, sn, 0.1, O.REDUCTION_SUM, acc=np.float64)
+    got_t = np.concatenate([t.cpu().numpy() for t in tables])
+    got_s = np.concatenate([s.cpu().numpy() for s in states])
+    assert rel_err(got_t, exp_t) < 3e-4 and rel_err(got_s, exp_s) < 3e-4
+    assert abs(float(loss.item()) - float(res.loss)) < 3e-4 * abs(float(res.loss))
