@@ -82,17 +82,45 @@ def make_sharded_batches(rng, rows_per_rank, rank, world, n_batches, B):
 
 # ------------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  NVML is polled from a thread
+    every few ms (the nvidia-smi CLI needs ~0.2 s to start, longer than a short timed region); nvidia-smi -lms is the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("hw_power_brake", 0x80))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.004):
         self.gpu = gpu_index
+        self.period = period_s
         self.proc = None
         self.lines = []
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.nvml = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except TypeError:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, h
 
     def start(self):
+        try:
+            self.nvml, self.h = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -101,11 +129,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for name, bit in self.BITS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            if not self.sm:
+                return dict(sm_mhz=None, sm_max_mhz=self.mx, reasons=["no samples"])
+            sm = sorted(self.sm)
+            return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=self.mx, reasons=sorted(self.reasons), samples=len(sm), source="nvml")
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -129,7 +178,7 @@ class ClockSampler:
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
 
 
 # ------------------------------------------------------------------------------------------------------ reference arm
@@ -398,7 +447,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=10000, help="positives per step (chunks of 1000)")

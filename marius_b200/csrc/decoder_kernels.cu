@@ -157,10 +157,11 @@ struct LossArgs {
     const float* pos;   // [rows]
     float* gpos;        // [rows]
     float* row_loss;    // [rows]
-    __nv_bfloat16 *G_hi, *G_lo;  // optional [rows, N]
+    __nv_bfloat16 *G_hi, *G_lo;  // optional [rows, ldg]
     int64_t rows;
     int N;
     float w;            // 1 (SUM) or 1/rows_per_side (MEAN)
+    int64_t ldg;        // leading dimension of G_hi / G_lo (>= N; padded so that rows start on 128-byte lines)
 };
 
 __global__ void __launch_bounds__(kThreads) loss_grad_kernel(LossArgs a) {
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) loss_grad_kernel(LossArgs a) {
         for (int j = lane; j < a.N; j += 32) {
             float g = expf(s[j] - z) * a.w;
             s[j] = g;
-            if (a.G_hi) split_bf16(g, a.G_hi[i * a.N + j], a.G_lo[i * a.N + j]);
+            if (a.G_hi) split_bf16(g, a.G_hi[i * a.ldg + j], a.G_lo[i * a.ldg + j]);
         }
         if (lane == 0) {
             a.gpos[i] = (expf(p - z) - 1.0f) * a.w;
@@ -392,8 +393,12 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegReduceArgs 
     }
 }
 
-__global__ void split_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) split_bf16(x[i], hi[i], lo[i]);
+__global__ void split_kernel(const float* __restrict__ x, int64_t n, int64_t cols, int64_t ld_out, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = (i / cols) * ld_out + (i % cols);
+        split_bf16(x[i], hi[o], lo[o]);
+    }
 }
 
 inline int warp_grid(int64_t rows) {
@@ -425,18 +430,19 @@ mb_status launch_gather_split(const float* emb, int64_t emb_ld, const int64_t* i
     return MB_OK;
 }
 
-mb_status launch_split(const float* x, int64_t n, void* hi, void* lo, cudaStream_t st) {
+mb_status launch_split(const float* x, int64_t n, void* hi, void* lo, cudaStream_t st, int64_t cols, int64_t ld_out) {
     if (n == 0) return MB_OK;
+    if (cols <= 0) cols = ld_out = n;  // flat
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-    split_kernel<<<(int)blocks, 256, 0, st>>>(x, n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    split_kernel<<<(int)blocks, 256, 0, st>>>(x, n, cols, ld_out, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }
 
 mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w,
-                           cudaStream_t st) {
-    LossArgs a{S, pos, gpos, row_loss, (__nv_bfloat16*)G_hi, (__nv_bfloat16*)G_lo, rows, N, w};
+                           cudaStream_t st, int64_t ldg) {
+    LossArgs a{S, pos, gpos, row_loss, (__nv_bfloat16*)G_hi, (__nv_bfloat16*)G_lo, rows, N, w, ldg > 0 ? ldg : N};
     loss_grad_kernel<<<warp_grid(rows), kThreads, 0, st>>>(a);
     MB_LAUNCH_CHECK();
     return MB_OK;
@@ -576,10 +582,11 @@ mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, con
 
 // S -> G (fp32, may be in place or null) and/or bf16 hi/lo
 mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w,
-                      cudaStream_t st) {
+                      cudaStream_t st, int64_t ldg) {
     if (rows == 0) return MB_OK;
-    if ((N % 4 == 0) && N <= 1024 && al16(S) && (!G || al16(G))) {
-        vec::LossVArgs a{S, G, pos, gpos, row_loss, (__nv_bfloat16*)G_hi, (__nv_bfloat16*)G_lo, rows, N, w};
+    if (ldg <= 0) ldg = N;
+    if ((N % 4 == 0) && (ldg % 4 == 0) && N <= 1024 && al16(S) && (!G || al16(G))) {
+        vec::LossVArgs a{S, G, pos, gpos, row_loss, (__nv_bfloat16*)G_hi, (__nv_bfloat16*)G_lo, rows, N, w, ldg};
         int grid = warp_grid(rows);
         if (N <= 256)
             vec::loss_kernel<2><<<grid, vec::kThreads, 0, st>>>(a);
@@ -594,7 +601,7 @@ mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, f
         return MB_ERR_INVALID;
     }
     if (G != S) MB_CUDA_TRY(cudaMemcpyAsync(G, S, sizeof(float) * rows * N, cudaMemcpyDeviceToDevice, st));
-    return launch_loss_grad(G, pos, gpos, row_loss, G_hi, G_lo, rows, N, w, st);
+    return launch_loss_grad(G, pos, gpos, row_loss, G_hi, G_lo, rows, N, w, st, ldg);
 }
 
 mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,

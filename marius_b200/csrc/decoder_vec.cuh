@@ -196,6 +196,7 @@ struct LossVArgs {
     int64_t rows;
     int N;
     float w;
+    int64_t ldg;  // leading dimension of G_hi / G_lo
 };
 
 template <int MAXV>
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kThreads) loss_kernel(LossVArgs a) {
             if (v < nv) {
                 float4 g = make_float4(expf(x[c].x - z) * a.w, expf(x[c].y - z) * a.w, expf(x[c].z - z) * a.w, expf(x[c].w - z) * a.w);
                 if (a.G) st4(a.G + i * a.N, v, g);
-                if (a.G_hi) store_split4(a.G_hi, a.G_lo, i * a.N + 4 * v, g);
+                if (a.G_hi) store_split4(a.G_hi, a.G_lo, i * a.ldg + 4 * v, g);
             }
         }
         if (lane == 0) {

@@ -259,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
-        if (p.tma_store && lane == 0) bulk_wait_all();  // all bulk stores of this warp have completed before the CTA exits
+        if (p.tma_store && elect_one()) bulk_wait_all();  // all bulk stores of this warp have completed before the CTA exits
     }
 
     tc_fence_before();
@@ -560,7 +560,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);  // the leader's barrier (local for rank 0)
         }
-        if (p.tma_store && lane == 0) bulk_wait_all();
+        if (p.tma_store && elect_one()) bulk_wait_all();
     }
 
     tc_fence_before();

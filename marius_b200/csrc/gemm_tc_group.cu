@@ -42,7 +42,7 @@ struct GProblem {
 };
 struct GParams {
     GProblem prob[2];
-    const int4* table;  // [rounds][num_clusters] : (problem | -1, batch, m0, n_tile0)
+    const int4* table;  // [rounds][num_clusters] : (problem | width << 8, or -1; batch; m0; n0), width = tile columns (multiple of 32 off the N edge)
     int rounds;
     int passes;
     int debug_flags;
@@ -94,77 +94,91 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
     const uint32_t tmem_base = *tmem_holder_ptr;
 
     if (warp == 0) {
-        // ================= TMA producer (both CTAs) =================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int r = 0; r < p.rounds; r++) {
-                const int4 e = p.table[r * num_clusters + cluster_id];
-                if (e.x < 0) continue;
-                const GProblem& pr = p.prob[e.x];
-                const CUtensorMap* mA_hi = &maps.m[e.x][0];
-                const CUtensorMap* mA_lo = &maps.m[e.x][1];
-                const CUtensorMap* mB_hi = &maps.m[e.x][2];
-                const CUtensorMap* mB_lo = &maps.m[e.x][3];
-                const int b = e.y;
-                const int m0 = e.z + (int)rank * BLOCK_M;
-                const int n_eff = min(GTILE_N, ((pr.N - e.w + 31) / 32) * 32);
-                const int n0 = e.w + (int)rank * (n_eff / 2);
-                const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
-                for (int kb = 0; kb < num_k_blocks; kb++) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t sA_hi = smem_base + stage * G_STAGE;
-                    const uint32_t sA_lo = sA_hi + G_A_TILE;
-                    const uint32_t sB_hi = sA_lo + G_A_TILE;
-                    const uint32_t sB_lo = sB_hi + G_B_TILE;
-                    const uint32_t lbar = full_bar(stage) & kPeerMask;
-                    if (leader) mbar_expect_tx(full_bar(stage), stage_tx_pair);
-                    const int k0 = kb * GBLOCK_K;
-                    if (!pr.a_mn) {
-                        tma_load_3d_2sm(sA_hi, mA_hi, lbar, k0, m0, b);
-                        if (p.passes == 3) tma_load_3d_2sm(sA_lo, mA_lo, lbar, k0, m0, b);
+        // ================= TMA producer (both CTAs): the whole warp runs the loop, one elected lane issues =================
+        int stage = 0;
+        uint32_t phase = 0;
+        int4 e_next = p.table[cluster_id];  // the next table entry is fetched one tile ahead: its latency never sits between two tiles
+        for (int r = 0; r < p.rounds; r++) {
+            const int4 e = e_next;
+            if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+            if (e.x < 0) continue;
+            const int pi = e.x & 0xff;
+            const GProblem& pr = p.prob[pi];
+            const CUtensorMap* mA_hi = &maps.m[pi][0];
+            const CUtensorMap* mA_lo = &maps.m[pi][1];
+            const CUtensorMap* mB_hi = &maps.m[pi][2];
+            const CUtensorMap* mB_lo = &maps.m[pi][3];
+            const int b = e.y;
+            const int m0 = e.z + (int)rank * BLOCK_M;
+            const int n_eff = ((min(e.x >> 8, pr.N - e.w) + 31) / 32) * 32;
+            const int n0 = e.w + (int)rank * (n_eff / 2);
+            const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
+            const bool a_mn = pr.a_mn != 0, b_mn = pr.b_mn != 0, three = p.passes == 3;
+            for (int kb = 0; kb < num_k_blocks; kb++) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sA_hi = smem_base + stage * G_STAGE;
+                const uint32_t sA_lo = sA_hi + G_A_TILE;
+                const uint32_t sB_hi = sA_lo + G_A_TILE;
+                const uint32_t sB_lo = sB_hi + G_B_TILE;
+                const uint32_t lbar = full_bar(stage) & kPeerMask;
+                const int k0 = kb * GBLOCK_K;
+                if (elect_one()) {
+                    if (p.debug_flags & 2) {  // ablation: no TMA loads, the MMAs run on whatever is in shared memory
+                        if (leader) mbar_arrive(full_bar(stage));
                     } else {
+                        if (leader) mbar_expect_tx(full_bar(stage), stage_tx_pair);
+                        if (!a_mn) {
+                            tma_load_3d_2sm(sA_hi, mA_hi, lbar, k0, m0, b);
+                            if (three) tma_load_3d_2sm(sA_lo, mA_lo, lbar, k0, m0, b);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BLOCK_M / 64; j++) {
-                            tma_load_3d_2sm(sA_hi + j * (GBLOCK_K * 128), mA_hi, lbar, m0 + 64 * j, k0, b);
-                            if (p.passes == 3) tma_load_3d_2sm(sA_lo + j * (GBLOCK_K * 128), mA_lo, lbar, m0 + 64 * j, k0, b);
+                            for (int j = 0; j < BLOCK_M / 64; j++) {
+                                tma_load_3d_2sm(sA_hi + j * (GBLOCK_K * 128), mA_hi, lbar, m0 + 64 * j, k0, b);
+                                if (three) tma_load_3d_2sm(sA_lo + j * (GBLOCK_K * 128), mA_lo, lbar, m0 + 64 * j, k0, b);
+                            }
+                        }
+                        if (!b_mn) {
+                            tma_load_3d_2sm(sB_hi, mB_hi, lbar, k0, n0, b);
+                            if (three) tma_load_3d_2sm(sB_lo, mB_lo, lbar, k0, n0, b);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < GHALF_N / 64; j++) {
+                                tma_load_3d_2sm(sB_hi + j * (GBLOCK_K * 128), mB_hi, lbar, n0 + 64 * j, k0, b);
+                                if (three) tma_load_3d_2sm(sB_lo + j * (GBLOCK_K * 128), mB_lo, lbar, n0 + 64 * j, k0, b);
+                            }
                         }
                     }
-                    if (!pr.b_mn) {
-                        tma_load_3d_2sm(sB_hi, mB_hi, lbar, k0, n0, b);
-                        if (p.passes == 3) tma_load_3d_2sm(sB_lo, mB_lo, lbar, k0, n0, b);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < GHALF_N / 64; j++) {
-                            tma_load_3d_2sm(sB_hi + j * (GBLOCK_K * 128), mB_hi, lbar, n0 + 64 * j, k0, b);
-                            if (p.passes == 3) tma_load_3d_2sm(sB_lo + j * (GBLOCK_K * 128), mB_lo, lbar, n0 + 64 * j, k0, b);
-                        }
-                    }
-                    if (++stage == GSTAGES) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                }
+                __syncwarp();
+                if (++stage == GSTAGES) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer: one thread of the leader CTA =================
-        if (leader && lane == 0) {
+        // ================= MMA issuer: warp 1 of the leader CTA, warp-uniform loop, one elected lane issues =================
+        if (leader) {
             int stage = 0;
             uint32_t phase = 0;
             int local_tile = 0;
+            // descriptor words that never change: SBO = 1024 B (8 rows x 128 B), version 1, SWIZZLE_128B
+            constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
+            const uint32_t npass = (p.debug_flags & 4) ? 0u : (uint32_t)p.passes;  // bit 2: ablation, no MMAs
+            int4 e_next = p.table[cluster_id];
             for (int r = 0; r < p.rounds; r++) {
-                const int4 e = p.table[r * num_clusters + cluster_id];
+                const int4 e = e_next;
+                if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
                 if (e.x < 0) continue;
-                const GProblem& pr = p.prob[e.x];
+                const GProblem& pr = p.prob[e.x & 0xff];
                 const bool a_mn = pr.a_mn != 0, b_mn = pr.b_mn != 0;
-                // K-major SW128: SBO = 1024 (8 rows x 128 B), k-step +32 B.  MN-major SW128: LBO = slab stride, SBO = 1024, k-step +2048 B.
-                const uint32_t A_LBO = a_mn ? GBLOCK_K * 128 : 16, A_KSTEP = a_mn ? 2048 : 32;
-                const uint32_t B_LBO = b_mn ? GBLOCK_K * 128 : 16, B_KSTEP = b_mn ? 2048 : 32;
+                // K-major SW128: LBO unused (16), k-step +32 B.  MN-major SW128: LBO = slab stride, k-step +2048 B.  (units of 16 B below)
+                const uint32_t a_lbo = (a_mn ? (uint32_t)(GBLOCK_K * 128) >> 4 : 1u) << 16, a_kstep = a_mn ? 2048u >> 4 : 32u >> 4;
+                const uint32_t b_lbo = (b_mn ? (uint32_t)(GBLOCK_K * 128) >> 4 : 1u) << 16, b_kstep = b_mn ? 2048u >> 4 : 32u >> 4;
                 const int buf = local_tile & 1;
                 const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
                 local_tile++;
-                const int n_eff = min(GTILE_N, ((pr.N - e.w + 31) / 32) * 32);
+                const int n_eff = ((min(e.x >> 8, pr.N - e.w) + 31) / 32) * 32;
                 const uint32_t idesc = make_idesc(GTILE_M, n_eff, a_mn, b_mn);
                 const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
                 mbar_wait(tempty_bar(buf), buf_phase ^ 1u);
@@ -174,29 +188,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
                 for (int kb = 0; kb < num_k_blocks; kb++) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t sA_hi = smem_base + stage * G_STAGE;
-                    const uint32_t sA_lo = sA_hi + G_A_TILE;
-                    const uint32_t sB_hi = sA_lo + G_A_TILE;
-                    const uint32_t sB_lo = sB_hi + G_B_TILE;
+                    const uint32_t sA_hi = (smem_base + stage * G_STAGE) >> 4;  // 16-byte units, < 2^14
+                    const uint32_t sA_lo = sA_hi + (G_A_TILE >> 4);
+                    const uint32_t sB_hi = sA_lo + (G_A_TILE >> 4);
+                    const uint32_t sB_lo = sB_hi + (G_B_TILE >> 4);
                     const int k_valid = min(GBLOCK_K, pr.K - kb * GBLOCK_K);
                     const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
-                    for (int prod = 0; prod < p.passes; prod++) {
-                        const uint32_t sa = (prod == 2) ? sA_lo : sA_hi;  // hi.hi, hi.lo, lo.hi
-                        const uint32_t sb = (prod == 1) ? sB_lo : sB_hi;
-                        for (int ks = 0; ks < ksteps; ks++) {
-                            uint64_t adesc = make_smem_desc(sa + ks * A_KSTEP, A_LBO, 1024, 2u);
-                            uint64_t bdesc = make_smem_desc(sb + ks * B_KSTEP, B_LBO, 1024, 2u);
-                            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
-                            accumulate = 1;
+                    if (elect_one()) {
+#pragma unroll
+                        for (uint32_t prod = 0; prod < 3; prod++) {  // hi.hi, hi.lo, lo.hi
+                            if (prod < npass) {
+                                const uint32_t sa = a_lbo | ((prod == 2) ? sA_lo : sA_hi);
+                                const uint32_t sb = b_lbo | ((prod == 1) ? sB_lo : sB_hi);
+#pragma unroll
+                                for (int ks = 0; ks < GBLOCK_K / UMMA_K; ks++) {
+                                    if (ks < ksteps) {
+                                        const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(sa + ks * a_kstep);
+                                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(sb + ks * b_kstep);
+                                        umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
+                                        accumulate = 1;
+                                    }
+                                }
+                            }
                         }
+                        umma_commit_2sm(empty_bar(stage));
+                        if (kb == num_k_blocks - 1) umma_commit_2sm(tfull_bar(buf));
                     }
-                    umma_commit_2sm(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == GSTAGES) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit_2sm(tfull_bar(buf));
             }
         }
     } else {
@@ -204,11 +227,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
         const int q = warp & 3;
         int local_tile = 0;
         uint32_t epi_chunk = 0;
+        int4 e_next = p.table[cluster_id];
         for (int r = 0; r < p.rounds; r++) {
-            const int4 e = p.table[r * num_clusters + cluster_id];
+            const int4 e = e_next;
+            if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
             if (e.x < 0) continue;
-            const GProblem& pr = p.prob[e.x];
-            const CUtensorMap* mD = &maps.m[e.x][4];
+            const GProblem& pr = p.prob[e.x & 0xff];
+            const CUtensorMap* mD = &maps.m[e.x & 0xff][4];
             const int buf = local_tile & 1;
             const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
             local_tile++;
@@ -220,13 +245,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
             const int row = m0 + q * 32 + lane;
             float* drow = pr.D + (int64_t)b * pr.sDb + (int64_t)row * pr.ldd;
             const bool row_ok = row < pr.M && !(p.debug_flags & 1);
-#pragma unroll 1
-            for (int c = 0; c < GTILE_N / 32; c++) {
+            // 32-column chunks of this warp's 32 accumulator rows; the TMEM load of chunk c+1 is in flight while chunk c is staged / stored
+            const int n_lim = min(pr.N, n0 + (e.x >> 8));
+            const int n_chunks = (p.debug_flags & 8) ? 0 : (n_lim - n0 + 31) / 32;  // bit 3: ablation, no epilogue at all
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GTILE_N);
+            uint32_t ra[32], rb[32];
+            auto emit = [&](const uint32_t (&rg)[32], int c) {
                 const int col0 = n0 + c * 32;
-                if (col0 >= pr.N) break;
-                uint32_t rg[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GTILE_N + c * 32), rg);
-                tmem_ld_wait();
                 if (pr.tma_store) {
                     if (!(p.debug_flags & 1))
                         stage_and_store(rg, smem_base + G_EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, mD, col0,
@@ -237,12 +262,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
                     for (int v = 0; v < 32; v++)
                         if (col0 + v < pr.N) drow[col0 + v] = __uint_as_float(rg[v]);
                 }
+            };
+            if (n_chunks > 0) tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; c += 2) {
+                tmem_ld_wait();
+                if (c + 1 < n_chunks) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), rb);
+                emit(ra, c);
+                if (c + 1 < n_chunks) {
+                    tmem_ld_wait();
+                    if (c + 2 < n_chunks) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 2) * 32), ra);
+                    emit(rb, c + 1);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);
         }
-        if (lane == 0) bulk_wait_all();
+        if (elect_one()) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -400,30 +437,84 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
         std::lock_guard<std::mutex> lk(table_mutex());
         auto it = table_cache().find(key);
         if (it == table_cache().end()) {
+            // Tiles in batch-major order (both problems of a batch next to each other: they read the same G / Neg / A blocks, which
+            // then come from L2 instead of HBM), handed to the least-loaded CTA pair (list scheduling).  The last tiles of the list
+            // are split into narrower column pieces so the tail is filled to within one small piece; the split is chosen by
+            // simulating the schedule with the cost model below.
             struct Tile {
-                int prob, b, m0, n0;
+                int prob, b, m0, n0, width;
                 int64_t cost;
             };
-            std::vector<Tile> tiles;
+            int ksteps[2] = {0, 0}, max_batches = 0;
             for (int i = 0; i < n; i++) {
-                const TcGroupProblem& g = probs[i];
-                const int ksteps = (g.K + 15) / 16;
-                for (int b = 0; b < g.batches; b++)
+                ksteps[i] = (probs[i].K + 15) / 16;
+                max_batches = std::max(max_batches, probs[i].batches);
+            }
+            auto cost_of = [&](int prob, int width) {  // MMA time ~ n_eff per k-step; + pipeline fill / epilogue drain per tile
+                return (int64_t)(((width + 31) / 32) * 32) * ksteps[prob] + 1024;
+            };
+            std::vector<Tile> base;
+            for (int b = 0; b < max_batches; b++)
+                for (int i = 0; i < n; i++) {
+                    const TcGroupProblem& g = probs[i];
+                    if (b >= g.batches) continue;
                     for (int m0 = 0; m0 < g.M; m0 += GTILE_M)
                         for (int n0 = 0; n0 < g.N; n0 += GTILE_N) {
-                            int n_eff = std::min(GTILE_N, ((g.N - n0 + 31) / 32) * 32);
-                            tiles.push_back({i, b, m0, n0, (int64_t)n_eff * ksteps + 2048});  // MMA cycles ~ n_eff/2 per k-step, + fixed epilogue
+                            const int w = std::min(GTILE_N, g.N - n0);
+                            base.push_back({i, b, m0, n0, w, cost_of(i, w)});
                         }
-            }
-            // longest first; ties keep (problem, batch, m, n) order so neighbouring CTA pairs share operand tiles in L2
-            std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& a, const Tile& b) { return a.cost > b.cost; });
-            int rounds = (int)((tiles.size() + clusters - 1) / clusters);
+                }
+            auto build = [&](int tail, int piece) {
+                std::vector<Tile> out;
+                const size_t keep = base.size() - std::min<size_t>(base.size(), (size_t)tail);
+                for (size_t t = 0; t < base.size(); t++) {
+                    const Tile& x = base[t];
+                    if (t < keep || x.width <= piece) {
+                        out.push_back(x);
+                        continue;
+                    }
+                    for (int o = 0; o < x.width; o += piece) {
+                        const int w = std::min(piece, x.width - o);
+                        out.push_back({x.prob, x.b, x.m0, x.n0 + o, w, cost_of(x.prob, w)});
+                    }
+                }
+                return out;
+            };
+            auto schedule = [&](const std::vector<Tile>& tiles, std::vector<std::vector<int>>* per_pair) {
+                std::vector<int64_t> load((size_t)clusters, 0);
+                if (per_pair) per_pair->assign((size_t)clusters, {});
+                for (size_t t = 0; t < tiles.size(); t++) {
+                    int best = 0;
+                    for (int c = 1; c < clusters; c++)
+                        if (load[c] < load[best]) best = c;
+                    load[best] += tiles[t].cost;
+                    if (per_pair) (*per_pair)[best].push_back((int)t);
+                }
+                return *std::max_element(load.begin(), load.end());
+            };
+            int best_tail = 0, best_piece = GTILE_N;
+            int64_t best_span = schedule(base, nullptr);
+            for (int piece : {192, 128, 96, 64})
+                for (int k = 1; k <= 16; k++) {
+                    const int tail = clusters * k / 4;
+                    const int64_t span = schedule(build(tail, piece), nullptr);
+                    if (span < best_span) {
+                        best_span = span;
+                        best_tail = tail;
+                        best_piece = piece;
+                    }
+                }
+            const std::vector<Tile> tiles = build(best_tail, best_piece);
+            std::vector<std::vector<int>> per_pair;
+            schedule(tiles, &per_pair);
+            int rounds = 0;
+            for (auto& v : per_pair) rounds = std::max(rounds, (int)v.size());
             std::vector<int4> host((size_t)rounds * clusters, make_int4(-1, 0, 0, 0));
-            for (size_t t = 0; t < tiles.size(); t++) {
-                int r = (int)(t / clusters), i = (int)(t % clusters);
-                int c = (r & 1) ? clusters - 1 - i : i;  // snake
-                host[(size_t)r * clusters + c] = make_int4(tiles[t].prob, tiles[t].b, tiles[t].m0, tiles[t].n0);
-            }
+            for (int c = 0; c < clusters; c++)
+                for (size_t r = 0; r < per_pair[c].size(); r++) {
+                    const Tile& x = tiles[per_pair[c][r]];
+                    host[r * clusters + c] = make_int4(x.prob | (x.width << 8), x.b, x.m0, x.n0);
+                }
             int4* dptr = nullptr;
             MB_CUDA_TRY(cudaMalloc(&dptr, host.size() * sizeof(int4)));
             MB_CUDA_TRY(cudaMemcpy(dptr, host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice));

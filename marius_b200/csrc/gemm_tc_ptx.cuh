@@ -40,6 +40,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > kWaitTimeoutCycles) __trap();
     }
 }
+// one lane of a converged warp (always the same one for the full mask): lets loops and address arithmetic stay warp-uniform, so
+// the operands of UTMALDG / UTCHMMA live in uniform registers instead of being moved there by a per-instruction ELECT loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -114,7 +125,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 // registers r[32] = 32 consecutive columns of this lane's row -> staging tile `stg` (shared address) -> global via TMA
 __device__ __forceinline__ void stage_and_store(const uint32_t (&r)[32], uint32_t stg, int lane, const CUtensorMap* tmD, int col0, int row0, int b) {
-    if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago (same tile) has finished reading shared memory
+    if (elect_one()) bulk_wait_read<1>();  // the store issued two chunks ago (same tile) has finished reading shared memory
     __syncwarp();
     const uint32_t row_base = stg + (uint32_t)lane * 128u;
 #pragma unroll
@@ -125,7 +136,7 @@ __device__ __forceinline__ void stage_and_store(const uint32_t (&r)[32], uint32_
     }
     fence_proxy_async();  // generic-proxy writes -> visible to the async (TMA) proxy
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {  // same lane every time (bulk groups are per-thread state); operands stay in uniform registers
         tma_store_3d(tmD, stg, col0, row0, b);
         bulk_commit();
     }

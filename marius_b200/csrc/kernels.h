@@ -29,8 +29,9 @@ mb_status launch_edge_prep(const float* emb, int64_t emb_ld, const int64_t* edge
                            int d, int decoder, float* A0, float* A1, float* pos0, float* pos1, void* A0_hi, void* A0_lo, void* A1_hi, void* A1_lo,
                            cudaStream_t st);
 mb_status launch_gather_split(const float* emb, int64_t emb_ld, const int64_t* idx, int64_t n, int d, float* out, void* hi, void* lo, cudaStream_t st);
-mb_status launch_split(const float* x, int64_t n, void* hi, void* lo, cudaStream_t st);
-mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w, cudaStream_t st);
+mb_status launch_split(const float* x, int64_t n, void* hi, void* lo, cudaStream_t st, int64_t cols = 0, int64_t ld_out = 0);
+mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w, cudaStream_t st,
+                           int64_t ldg = 0);
 mb_status launch_loss_reduce(const float* row_loss, int64_t n, float* loss, cudaStream_t st);
 mb_status launch_edge_backward(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int d,
                                int decoder, const float* A0, const float* A1, const float* dA0, const float* dA1, const float* gpos0,
@@ -47,7 +48,7 @@ mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, con
                       int64_t CN, int d, int decoder, int sides, const int64_t* dst_negs, const int64_t* src_negs, float* A, float* pos, void* A_hi,
                       void* A_lo, float* Neg, void* Neg_hi, void* Neg_lo, cudaStream_t st);
 mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w,
-                      cudaStream_t st);
+                      cudaStream_t st, int64_t ldg = 0);
 mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                           int d, int decoder, int sides, const float* A, const float* dA, const float* gpos, float* gcat, float* drel, cudaStream_t st);
 mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
