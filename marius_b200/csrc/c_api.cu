@@ -449,6 +449,20 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     // ---- join: the slot / relation plans and the negative-row gradients are needed from here on
     if (overlap) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     if (dneg_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+    // relation gradients (segmented sum of per-edge gradients by relation id) touch nothing the node update touches: they run on the
+    // side stream next to it
+    const bool rel_forked = need_rel && overlap;
+    if (rel_forked) {
+        MB_CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+        MB_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    }
+    if (need_rel) {
+        cudaStream_t rs = rel_forked ? ctx->side : st;
+        StageTimer tm(ctx, ST_REL_GRAD, rs);
+        MB_TRY(launch_rel_reduce(p.drel, p.sides == 2 ? p.drel + p.B * d : nullptr, rel_grad, p.sides == 2 ? inv_rel_grad : nullptr, rvals, p.roffsets, p.R,
+                                 d, rs));
+        if (rel_forked) MB_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+    }
     {
         // node gradients: segmented sum over sorted slots (+ Adagrad)
         StageTimer tm(ctx, ST_UPDATE, st);
@@ -461,12 +475,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
             MB_TRY(launch_seg_reduce(nullptr, 0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
         }
     }
-    if (need_rel) {
-        // relation gradients: segmented sum of per-edge gradients by relation id
-        StageTimer tm(ctx, ST_REL_GRAD, st);
-        MB_TRY(launch_rel_reduce(p.drel, p.sides == 2 ? p.drel + p.B * d : nullptr, rel_grad, p.sides == 2 ? inv_rel_grad : nullptr, rvals, p.roffsets, p.R,
-                                 d, st));
-    }
+    if (rel_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     return MB_OK;
 }
 
