@@ -33,10 +33,23 @@ def build_cuda(force: bool = False, verbose: bool = True) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "kernels.h", "decoder_vec.cuh", "gemm_tc_ptx.cuh")] + [os.path.join(HERE, "..", "include", "marius_b200.h")]
     if force or _newer(out, deps):
-        cmd = [NVCC] + NVCC_FLAGS + ["-o", out] + srcs
-        if verbose:
-            print("[marius_b200.build]", " ".join(cmd), flush=True)
-        subprocess.check_call(cmd, cwd=CSRC)
+        # one nvcc process per translation unit (parallel, objects cached under lib/obj), then one link
+        objdir = os.path.join(LIBDIR, "obj")
+        os.makedirs(objdir, exist_ok=True)
+        hdrs = deps[len(srcs):]
+        flags = [f for f in NVCC_FLAGS if f != "-shared"]
+        objs, procs = [], []
+        for s in srcs:
+            o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
+            objs.append(o)
+            if force or _newer(o, [s] + hdrs):
+                cmd = [NVCC] + flags + ["-c", s, "-o", o]
+                if verbose:
+                    print("[marius_b200.build]", " ".join(cmd), flush=True)
+                procs.append(subprocess.Popen(cmd, cwd=CSRC))
+        if any(p.wait() != 0 for p in procs):
+            raise RuntimeError("nvcc failed")
+        subprocess.check_call([NVCC, "-shared", "-o", out] + objs, cwd=CSRC)
     return out
 
 

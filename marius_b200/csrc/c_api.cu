@@ -1,8 +1,13 @@
 // c_api.cu -- the extern "C" boundary (include/marius_b200.h) and the per-batch orchestration of the hot path.
 #include <cuda_bf16.h>
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -15,6 +20,23 @@ static thread_local std::string g_error;
 std::atomic<uint64_t> g_launches{0};
 
 void set_error(const std::string& msg) { g_error = msg; }
+
+// Process teardown: once exit() has started the CUDA runtime may already be unloading, and destroying streams / events / graphs then
+// is undefined.  The handler is registered after the first CUDA call of mb_create, so it runs BEFORE the runtime's own exit hooks
+// (atexit is LIFO); from then on mb_destroy only drops the host object and leaves device resources to the driver.
+static std::atomic<bool> g_exiting{false};
+static void on_process_exit() { g_exiting.store(true); }
+
+// MB_SEGV_TRACE=1: print a native backtrace on SIGSEGV / SIGABRT (debugging aid, off by default)
+static void segv_trace(int sig) {
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    const char msg[] = "[marius_b200] fatal signal, native backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
@@ -500,6 +522,16 @@ mb_status mb_create(int device, mb_context** out) {
     }
     MB_REQUIRE(device >= 0 && device < count, "device out of range");
     MB_CUDA_TRY(cudaSetDevice(device));
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFree(nullptr);  // force runtime initialisation so that its exit hooks are registered before ours
+        std::atexit(on_process_exit);
+        const char* e = getenv("MB_SEGV_TRACE");
+        if (e && atoi(e) != 0) {
+            signal(SIGSEGV, segv_trace);
+            signal(SIGABRT, segv_trace);
+        }
+    });
     mb_context* c = new mb_context();
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
@@ -524,6 +556,10 @@ mb_status mb_create(int device, mb_context** out) {
 
 void mb_destroy(mb_context* ctx) {
     if (!ctx) return;
+    if (g_exiting.load()) {  // see on_process_exit
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->h_uniq) cudaFree(ctx->h_uniq);

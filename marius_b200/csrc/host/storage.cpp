@@ -30,10 +30,20 @@ void* mb_current_stream(const torch::Device& device) {
 
 mb_context* mb_context_for(const torch::Device& device) {
     if (!device.is_cuda()) throw MariusRuntimeException("marius_b200: the embedding hot path runs on CUDA devices only (no CPU fallback)");
+    // A context (workspace, side streams, captured step graph) serves one host thread at a time.  Threads check contexts out of a
+    // process-wide pool and hand them back when they exit; the thread-exit hook makes NO CUDA call (the autograd engine's worker
+    // threads are torn down after the CUDA runtime's own thread state, so destroying device resources there is a use-after-free),
+    // and the pool itself is never destroyed: the driver reclaims everything at process exit.
+    struct Pool {
+        std::mutex mu;
+        std::multimap<int, mb_context*> idle;
+    };
+    static Pool* pool = new Pool();
     struct Holder {
         std::map<int, mb_context*> ctx;
         ~Holder() {
-            for (auto& kv : ctx) mb_destroy(kv.second);
+            std::lock_guard<std::mutex> lock(pool->mu);
+            for (auto& kv : ctx) pool->idle.emplace(kv.first, kv.second);
         }
     };
     static thread_local Holder holder;
@@ -41,7 +51,15 @@ mb_context* mb_context_for(const torch::Device& device) {
     auto it = holder.ctx.find(idx);
     if (it != holder.ctx.end()) return it->second;
     mb_context* c = nullptr;
-    mb_throw_on_error(mb_create(idx, &c));
+    {
+        std::lock_guard<std::mutex> lock(pool->mu);
+        auto idle = pool->idle.find(idx);
+        if (idle != pool->idle.end()) {
+            c = idle->second;
+            pool->idle.erase(idle);
+        }
+    }
+    if (c == nullptr) mb_throw_on_error(mb_create(idx, &c));
     holder.ctx[idx] = c;
     return c;
 }

@@ -6,6 +6,7 @@ C-ABI call into the hand-written sm_100a kernels.  There is no eager / CPU fallb
 from __future__ import annotations
 
 import ctypes as C
+import sys
 from typing import Optional
 
 import torch
@@ -94,6 +95,8 @@ class Context:
 
     def __del__(self):
         try:
+            if sys.is_finalizing():  # interpreter shutdown: leave device resources to the driver
+                return
             self.close()
         except Exception:
             pass
