@@ -220,6 +220,10 @@ mb_status mb_profile_enable(mb_context* ctx, int on);
 int mb_profile_num_stages(void);
 const char* mb_profile_stage_name(int stage);
 mb_status mb_profile_read(mb_context* ctx, float* total_ms, int* counts);
+/* mb_profile_enable(ctx, 2) keeps the step's side streams concurrent (mode 1 folds them into the caller's stream so that stage
+ * times add up); mb_profile_timeline then returns, for up to `cap` recorded stage launches, the stage id and its start / end in ms
+ * from the earliest recorded start -- the device timeline of the overlapped step -- and resets the recording. */
+mb_status mb_profile_timeline(mb_context* ctx, int cap, int* stages, float* start_ms, float* end_ms, int* n);
 
 /* bytes of device workspace a context currently holds (grows on demand, reused across batches) */
 size_t mb_workspace_bytes(const mb_context* ctx);

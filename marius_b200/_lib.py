@@ -57,6 +57,7 @@ _SIGS = {
     "mb_ipc_export": [_vp, _vp, C.POINTER(C.c_int64)],
     "mb_ipc_import": [_vp, _vp, _i64, C.POINTER(_vp)],
     "mb_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
+    "mb_profile_timeline": [_vp, _i32, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }
 EXPORTS = list(_SIGS) + ["mb_profile_num_stages", "mb_profile_stage_name", "mb_destroy", "mb_last_error", "mb_version", "mb_launch_count", "mb_build_info", "mb_workspace_bytes"]

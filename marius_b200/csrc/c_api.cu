@@ -86,6 +86,7 @@ struct mb_context {
                                           // which cannot be captured); ordered against the caller's stream with ev_in / ev_out
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_slot = nullptr;        // the node-slot plan is ready (the node update waits on this, not on the relation plan)
     // CUDA-graph replay of the fused step (mb_train_step / mb_train_step_host): one captured graph per call signature
     struct StepGraph {
         bool valid = false;
@@ -103,7 +104,7 @@ struct mb_context {
     int64_t* g_sneg = nullptr;
     size_t g_uniq_cap = 0, g_edges_cap = 0, g_dneg_cap = 0, g_sneg_cap = 0;
     // optional per-stage CUDA-event timing (mb_profile_*): events are recorded on the caller's stream
-    bool profiling = false;
+    int profiling = 0;  // 0 off, 1 stage timing with the side streams folded into the caller's stream, 2 timeline (streams stay concurrent)
     struct Span {
         int stage;
         cudaEvent_t a, b;
@@ -320,7 +321,8 @@ enum class UpdateMode { kBatchLocal, kFusedTable };
 
 // The duplicate-accumulation plans (slot list sorted by node id, edges sorted by relation id) only depend on the batch's
 // index tensors, so they run on the context's side stream concurrently with gather / prep / the score GEMM.
-static mb_status run_index_plans(mb_context* ctx, const Plan& p, const mb_batch* b, bool need_rel, uint32_t** svals, uint32_t** rvals, cudaStream_t st) {
+static mb_status run_index_plans(mb_context* ctx, const Plan& p, const mb_batch* b, bool need_rel, uint32_t** svals, uint32_t** rvals, cudaStream_t st,
+                                 cudaEvent_t slot_plan_ready = nullptr) {
     uint32_t* skeys = nullptr;
     {
         StageTimer tm(ctx, ST_SORT, st);
@@ -329,6 +331,7 @@ static mb_status run_index_plans(mb_context* ctx, const Plan& p, const mb_batch*
                                           p.sides == 2 ? bits_for((uint64_t)std::max<int64_t>(p.U, 1)) : 32, p.hist, &skeys, svals, st));
         MB_TRY(segment_offsets_u32(skeys, p.n_slots, p.U, p.offsets, st));
     }
+    if (slot_plan_ready) MB_CUDA_TRY(cudaEventRecord(slot_plan_ready, st));
     if (need_rel) {
         StageTimer tm(ctx, ST_REL_SORT, st);
         uint32_t* rk = nullptr;
@@ -362,12 +365,11 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
 
     // ---- fork: index plans on the side stream (inline when profiling so that stage times stay meaningful)
     uint32_t *svals = nullptr, *rvals = nullptr;
-    const bool overlap = !ctx->profiling && ctx->side != nullptr;
+    const bool overlap = ctx->profiling != 1 && ctx->side != nullptr;
     if (overlap) {
         MB_CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
         MB_CUDA_TRY(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        MB_TRY(run_index_plans(ctx, p, b, need_rel, &svals, &rvals, ctx->side));
-        MB_CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->side));
+        MB_TRY(run_index_plans(ctx, p, b, need_rel, &svals, &rvals, ctx->side, ctx->ev_slot));
     } else {
         MB_TRY(run_index_plans(ctx, p, b, need_rel, &svals, &rvals, st));
     }
@@ -469,7 +471,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
                                p.gpos, p.gcat, p.has_rel ? p.drel : nullptr, st));
     }
     // ---- join: the slot / relation plans and the negative-row gradients are needed from here on
-    if (overlap) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    if (overlap) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_slot, 0));
     if (dneg_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
     // relation gradients (segmented sum of per-edge gradients by relation id) touch nothing the node update touches: they run on the
     // side stream next to it
@@ -536,7 +538,12 @@ mb_status mb_create(int device, mb_context** out) {
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_loss_pinned, sizeof(float));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    // The index plans are chains of small kernels that must finish before the node update.  They share the GPU with grid-filling row
+    // kernels and persistent contractions, so their blocks are given scheduling priority (a low-priority side stream was observed to
+    // finish its 60 us of sorts 400 us late, stalling the update).
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
@@ -545,6 +552,7 @@ mb_status mb_create(int device, mb_context** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_slot, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete c;
         set_error(std::string("context creation failed: ") + cudaGetErrorString(e));
@@ -583,6 +591,7 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_slot) cudaEventDestroy(ctx->ev_slot);
     for (auto& sp : ctx->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -659,7 +668,7 @@ mb_status mb_graph_enable(mb_context* ctx, int on) {
 
 mb_status mb_profile_enable(mb_context* ctx, int on) {
     MB_REQUIRE(ctx != nullptr, "context is null");
-    ctx->profiling = on != 0;
+    ctx->profiling = on == 2 ? 2 : (on != 0 ? 1 : 0);
     return MB_OK;
 }
 
@@ -679,6 +688,34 @@ mb_status mb_profile_read(mb_context* ctx, float* total_ms, int* counts) {
         if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
             total_ms[sp.stage] += ms;
             counts[sp.stage] += 1;
+        }
+        ctx->event_pool.push_back(sp.a);
+        ctx->event_pool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+    return MB_OK;
+}
+
+mb_status mb_profile_timeline(mb_context* ctx, int cap, int* stages, float* start_ms, float* end_ms, int* n) {
+    MB_REQUIRE(ctx != nullptr && stages != nullptr && start_ms != nullptr && end_ms != nullptr && n != nullptr && cap >= 0, "bad arguments");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    MB_CUDA_TRY(cudaDeviceSynchronize());
+    *n = 0;
+    if (ctx->spans.empty()) return MB_OK;
+    // time origin: the earliest start event (elapsed time is signed, so any span's start serves as a provisional origin)
+    cudaEvent_t origin = ctx->spans[0].a;
+    float min_off = 0.f;
+    for (auto& sp : ctx->spans) {
+        float off = 0.f;
+        if (cudaEventElapsedTime(&off, origin, sp.a) == cudaSuccess && off < min_off) min_off = off;
+    }
+    for (auto& sp : ctx->spans) {
+        float a = 0.f, b = 0.f;
+        if (*n < cap && cudaEventElapsedTime(&a, origin, sp.a) == cudaSuccess && cudaEventElapsedTime(&b, origin, sp.b) == cudaSuccess) {
+            stages[*n] = sp.stage;
+            start_ms[*n] = a - min_off;
+            end_ms[*n] = b - min_off;
+            (*n)++;
         }
         ctx->event_pool.push_back(sp.a);
         ctx->event_pool.push_back(sp.b);
@@ -1027,7 +1064,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     MB_CUDA_TRY(cudaGraphLaunch(ctx->sg.exec, ctx->gstream));
     MB_CUDA_TRY(cudaEventRecord(ctx->ev_out, ctx->gstream));
     MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out, 0));
-    count_launch(28);  // kernels inside the replayed graph (mb_launch_count stays an honest kernel count)
+    count_launch(29);  // kernels inside the replayed graph (mb_launch_count stays an honest kernel count)
     return MB_OK;
 }
 

@@ -502,7 +502,7 @@ mb_status launch_segment_reduce(int mode, const float* rows, const uint32_t* slo
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 bool decoder_vec_ok(const float* emb, int64_t emb_ld, int d, bool has_rel, const float* rel, const float* inv_rel, int sides) {
-    return (d % 8 == 0) && (emb_ld % 4 == 0) && al16(emb) && (!has_rel || (al16(rel) && (sides == 1 || al16(inv_rel))));
+    return (d % 8 == 0) && d <= 512 && (emb_ld % 4 == 0) && al16(emb) && (!has_rel || (al16(rel) && (sides == 1 || al16(inv_rel))));
 }
 
 static vec::ShardPtrs make_sp(const mb_shards* sh) {
@@ -554,14 +554,36 @@ mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, con
             a.Neg_hi[s] = (on && Neg_hi) ? (__nv_bfloat16*)Neg_hi + s * CN * d : nullptr;
             a.Neg_lo[s] = (on && Neg_lo) ? (__nv_bfloat16*)Neg_lo + s * CN * d : nullptr;
         }
-        int grid = warp_grid(Bp + sides * CN);
-        if (dec == MB_DECODER_COMPLEX)
-            vec::prep_kernel<MB_DECODER_COMPLEX><<<grid, vec::kThreads, 0, st>>>(a);
-        else if (dec == MB_DECODER_DISTMULT)
-            vec::prep_kernel<MB_DECODER_DISTMULT><<<grid, vec::kThreads, 0, st>>>(a);
-        else
-            vec::prep_kernel<MB_DECODER_DOT><<<grid, vec::kThreads, 0, st>>>(a);
-        MB_LAUNCH_CHECK();
+        // edge rows, then negative rows (two in flight per warp)
+        if (Bp > 0) {
+            const int grid = warp_grid(Bp);
+            const bool small = d <= 128;  // chunks per lane: full row <= 1 (d <= 128) / 4 (d <= 512); complex half <= 1 (d <= 256) / 2
+            if (dec == MB_DECODER_COMPLEX) {
+                if (d <= 256)
+                    vec::edge_rows_kernel<MB_DECODER_COMPLEX, 1><<<grid, vec::kThreads, 0, st>>>(a);
+                else
+                    vec::edge_rows_kernel<MB_DECODER_COMPLEX, 2><<<grid, vec::kThreads, 0, st>>>(a);
+            } else if (dec == MB_DECODER_DISTMULT) {
+                if (small)
+                    vec::edge_rows_kernel<MB_DECODER_DISTMULT, 1><<<grid, vec::kThreads, 0, st>>>(a);
+                else
+                    vec::edge_rows_kernel<MB_DECODER_DISTMULT, 4><<<grid, vec::kThreads, 0, st>>>(a);
+            } else {
+                if (small)
+                    vec::edge_rows_kernel<MB_DECODER_DOT, 1><<<grid, vec::kThreads, 0, st>>>(a);
+                else
+                    vec::edge_rows_kernel<MB_DECODER_DOT, 4><<<grid, vec::kThreads, 0, st>>>(a);
+            }
+            MB_LAUNCH_CHECK();
+        }
+        if (CN > 0) {
+            const int grid = warp_grid((sides * CN + 1) / 2);
+            if (d <= 128)
+                vec::neg_rows_kernel<1><<<grid, vec::kThreads, 0, st>>>(a);
+            else
+                vec::neg_rows_kernel<4><<<grid, vec::kThreads, 0, st>>>(a);
+            MB_LAUNCH_CHECK();
+        }
         return MB_OK;
     }
     // scalar fallback needs the fp32 adjusted rows and a batch-local embedding matrix
@@ -632,13 +654,24 @@ mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld,
             a.drel[s] = (on && drel && has_rel) ? drel + s * B * d : nullptr;
         }
         a.gcat = gcat;
-        int grid = warp_grid(B);
-        if (dec == MB_DECODER_COMPLEX)
-            vec::edge_backward_kernel<MB_DECODER_COMPLEX><<<grid, vec::kThreads, 0, st>>>(a);
-        else if (dec == MB_DECODER_DISTMULT)
-            vec::edge_backward_kernel<MB_DECODER_DISTMULT><<<grid, vec::kThreads, 0, st>>>(a);
-        else
-            vec::edge_backward_kernel<MB_DECODER_DOT><<<grid, vec::kThreads, 0, st>>>(a);
+        const int grid = warp_grid(B);
+        const bool small = d <= 128;
+        if (dec == MB_DECODER_COMPLEX) {
+            if (d <= 256)
+                vec::edge_backward_kernel<MB_DECODER_COMPLEX, 1><<<grid, vec::kThreads, 0, st>>>(a);
+            else
+                vec::edge_backward_kernel<MB_DECODER_COMPLEX, 2><<<grid, vec::kThreads, 0, st>>>(a);
+        } else if (dec == MB_DECODER_DISTMULT) {
+            if (small)
+                vec::edge_backward_kernel<MB_DECODER_DISTMULT, 1><<<grid, vec::kThreads, 0, st>>>(a);
+            else
+                vec::edge_backward_kernel<MB_DECODER_DISTMULT, 4><<<grid, vec::kThreads, 0, st>>>(a);
+        } else {
+            if (small)
+                vec::edge_backward_kernel<MB_DECODER_DOT, 1><<<grid, vec::kThreads, 0, st>>>(a);
+            else
+                vec::edge_backward_kernel<MB_DECODER_DOT, 4><<<grid, vec::kThreads, 0, st>>>(a);
+        }
         MB_LAUNCH_CHECK();
         return MB_OK;
     }

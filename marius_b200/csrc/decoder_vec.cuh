@@ -1,6 +1,11 @@
-// decoder_vec.cuh -- 128-bit vectorised versions of the decoder-side row kernels (used when d % 8 == 0, the production
-// shapes; the scalar kernels in decoder_kernels.cu remain the general-d fallback).  One warp per row, each lane owns
-// float4 column chunks: d=400 -> 100 chunks, <= 4 per lane, all loads of a row issued before first use.
+// decoder_vec.cuh -- 128-bit vectorised versions of the decoder-side row kernels (used when d % 8 == 0 and d <= 512, the
+// production shapes; the scalar kernels in decoder_kernels.cu remain the general-d fallback).  One warp per row, each lane owns
+// float4 column chunks (d=400 -> 100 chunks, <= 4 per lane), all loads of a row issued before first use.
+//
+// Index chasing is lane-parallel: a row kernel's address needs two or three dependent global loads (edge / negative index ->
+// unique-id map -> table row), and a warp that walks that chain once per row spends most of its time with nothing in flight.
+// Instead lane k resolves the row pointers of the k-th of the warp's next 32 work items (items are dealt round-robin to the warps,
+// so the chains of up to 32 items run side by side), and the row loop broadcasts them with shuffles: the chain is paid once per warp.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -35,6 +40,25 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
     return fmaf(a.w, b.w, acc);
 }
 __device__ __forceinline__ float4 neg4(const float4& a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+// Row loads of the lane-parallel kernels.  The pointers come out of shuffles (the compiler no longer knows they are global), and a lane
+// whose chunk index is past the row end must not branch around its load (a branch per chunk keeps the compiler from hoisting the
+// loads of a row above the first use, which serialises them): the chunk index is clamped instead, the lane re-reads the row's last
+// chunk (same cache line as its neighbours) and simply does not store.
+__device__ __forceinline__ float4 ldg_nc4(const float* p, int v) {  // read-only data (table rows during the forward, relation rows)
+    float4 r;
+    asm("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(reinterpret_cast<const float4*>(p) + v));
+    return r;
+}
+__device__ __forceinline__ float4 ldg4(const float* p, int v) {  // data written earlier in the step / rewritten by this kernel
+    float4 r;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(reinterpret_cast<const float4*>(p) + v));
+    return r;
+}
+template <typename T>
+__device__ __forceinline__ T* shfl_ptr(T* p, int src_lane) {
+    return reinterpret_cast<T*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), src_lane));
+}
+__device__ __forceinline__ int64_t shfl_i64(int64_t v, int src_lane) { return (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)v, src_lane); }
 
 // Node-partition-sharded table: rank o owns global rows [o * rows_per_rank, (o+1) * rows_per_rank).  table[o] / state[o]
 // are the owners' base pointers -- local HBM for o == this rank, peer HBM mapped over NVLink (CUDA IPC) otherwise -- so the same fused
@@ -67,7 +91,7 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// prep: edge rows (relation operator + positive scores, both corruption sides) AND negative-row gather/split in one launch.
+// prep: edge rows (relation operator + positive scores, both corruption sides) and negative-row gather/split, one launch each.
 struct PrepArgs {
     const float* emb;
     int64_t emb_ld;
@@ -87,99 +111,177 @@ struct PrepArgs {
     __nv_bfloat16 *Neg_hi[2], *Neg_lo[2];  // or null
 };
 
-template <int DEC>  // MB_DECODER_*: relation operator fixed at compile time (DOT == identity)
-__global__ void __launch_bounds__(kThreads) prep_kernel(PrepArgs a) {
+// negative rows: emb[negs[side][j]] -> fp32 copy and/or bf16 hi/lo.  Items = the rows of dst_negs then src_negs; 8 rows per warp step,
+// two rows in flight per lane.
+template <int CH>  // float4 chunks per lane: d <= 128 * CH
+__global__ void __launch_bounds__(kThreads) neg_rows_kernel(PrepArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int d = a.d, dv = d >> 2;
+    const int64_t total = (int64_t)a.sides * a.CN;
+    // the warp owns items warp0, warp0 + nwarps, ... ; lane k resolves the k-th of the next 32 of them
+    for (int64_t first = warp0; first < total; first += 32 * nwarps) {
+        const float* mine = nullptr;
+        {
+            const int64_t q = first + lane * nwarps;
+            if (q < total) {
+                const int side = q >= a.CN ? 1 : 0;
+                const int64_t nid = __ldg((side ? a.negs[1] : a.negs[0]) + (q - (int64_t)side * a.CN));
+                mine = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + nid)) : a.emb + nid * a.emb_ld;
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < 32; k += 2) {
+            if (first + k * nwarps >= total) break;
+            const float* r0 = shfl_ptr(mine, k);
+            const float* r1 = shfl_ptr(mine, k + 1);
+            const float* q0 = r0 ? r0 : a.emb;  // past-the-end rows of the last step: load something valid, store nothing
+            const float* q1 = r1 ? r1 : a.emb;
+            float4 x0[CH], x1[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int vc = min(lane + 32 * c, dv - 1);
+                x0[c] = ldg_nc4(q0, vc);
+                x1[c] = ldg_nc4(q1, vc);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float* r = h ? r1 : r0;
+                if (r == nullptr) continue;
+                const int64_t q = first + (k + h) * nwarps;
+                const int side = q >= a.CN ? 1 : 0;
+                const int64_t j = q - (int64_t)side * a.CN;
+                float* nf = side ? a.Neg[1] : a.Neg[0];
+                __nv_bfloat16* nh = side ? a.Neg_hi[1] : a.Neg_hi[0];
+                __nv_bfloat16* nl = side ? a.Neg_lo[1] : a.Neg_lo[0];
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int v = lane + 32 * c;
+                    if (v >= dv) continue;
+                    const float4 x = h ? x1[c] : x0[c];
+                    if (nf) st4(nf + j * d, v, x);
+                    if (nh) store_split4(nh, nl, j * d + 4 * v, x);
+                }
+            }
+        }
+    }
+}
+
+// edge rows: relation operator + positive scores for both corruption sides, adjusted rows as fp32 and/or bf16 hi/lo.  Items = the Bp
+// (padded) positives; 4 edges per warp step.  CHV = float4 chunks per lane of a full row (DOT / DistMult) or of a complex half (ComplEx).
+template <int DEC, int CHV>  // MB_DECODER_*: relation operator fixed at compile time (DOT == identity)
+__global__ void __launch_bounds__(kThreads) edge_rows_kernel(PrepArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     const int d = a.d, dv = d >> 2, hv = d >> 3;  // float4 chunks per row / per complex half
-    const int64_t total = a.Bp + (int64_t)a.sides * a.CN;
-    for (int64_t t = warp0; t < total; t += nwarps) {
-        if (t >= a.Bp) {
-            // ---- negative row: emb[negs[side][j]] -> fp32 copy and/or bf16 hi/lo
-            const int64_t q = t - a.Bp;
-            const int side = q >= a.CN ? 1 : 0;
-            const int64_t j = q - (int64_t)side * a.CN;
-            const int64_t nid = a.negs[side][j];
-            const float* src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[nid]) : a.emb + nid * a.emb_ld;
-            for (int v = lane; v < dv; v += 32) {
-                float4 x = ld4(src, v);
-                if (a.Neg[side]) st4(a.Neg[side] + j * d, v, x);
-                if (a.Neg_hi[side]) store_split4(a.Neg_hi[side], a.Neg_lo[side], j * d + 4 * v, x);
+    const bool two = a.sides == 2;
+    for (int64_t first = warp0; first < a.Bp; first += 32 * nwarps) {
+        const float *my_src = nullptr, *my_dst = nullptr;
+        int64_t my_rid = 0;
+        {
+            const int64_t p = first + lane * nwarps;
+            if (p < a.B) {
+                const int64_t si = __ldg(a.edges + p * a.cols), ti = __ldg(a.edges + p * a.cols + a.cols - 1);
+                if (DEC != MB_DECODER_DOT) my_rid = __ldg(a.edges + p * a.cols + 1);
+                my_src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + si)) : a.emb + si * a.emb_ld;
+                my_dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + ti)) : a.emb + ti * a.emb_ld;
             }
-            continue;
         }
-        const int64_t p = t;
-        if (p >= a.B) {  // zero padding rows (comparators.cpp:11-15, decoder_methods.cpp:103-111)
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < a.sides; s++) {
-                for (int v = lane; v < dv; v += 32) {
-                    if (a.A[s]) st4(a.A[s] + p * d, v, z);
-                    if (a.A_hi[s]) store_split4(a.A_hi[s], a.A_lo[s], p * d + 4 * v, z);
-                }
-                if (lane == 0) a.pos[s][p] = 0.f;
-            }
-            continue;
-        }
-        const int64_t si = a.edges[p * a.cols], ti = a.edges[p * a.cols + a.cols - 1];
-        const float* src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[si]) : a.emb + si * a.emb_ld;
-        const float* dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[ti]) : a.emb + ti * a.emb_ld;
-        const int64_t rid = (DEC != MB_DECODER_DOT) ? a.edges[p * a.cols + 1] : 0;
-        const float* r = (DEC != MB_DECODER_DOT) ? a.rel + rid * d : nullptr;
-        const float* ri = (DEC != MB_DECODER_DOT && a.sides == 2) ? a.inv_rel + rid * d : nullptr;
-        float acc0 = 0.f, acc1 = 0.f;
-        if (DEC == MB_DECODER_COMPLEX) {
-            for (int v = lane; v < hv; v += 32) {
-                float4 sr = ld4(src, v), sim = ld4(src, hv + v), dr = ld4(dst, v), dim = ld4(dst, hv + v);
-                float4 rr = ld4(r, v), rim = ld4(r, hv + v);
-                float4 ar = sub4(mul4(sr, rr), mul4(sim, rim));    // relation_operators.cpp:31
-                float4 ai = addrn4(mul4(sr, rim), mul4(sim, rr));  // relation_operators.cpp:32
-                acc0 = dot4(ar, dr, acc0);
-                acc0 = dot4(ai, dim, acc0);
-                if (a.A[0]) {
-                    st4(a.A[0] + p * d, v, ar);
-                    st4(a.A[0] + p * d, hv + v, ai);
-                }
-                if (a.A_hi[0]) {
-                    store_split4(a.A_hi[0], a.A_lo[0], p * d + 4 * v, ar);
-                    store_split4(a.A_hi[0], a.A_lo[0], p * d + 4 * (hv + v), ai);
-                }
-                if (a.sides == 2) {
-                    float4 qr = ld4(ri, v), qi = ld4(ri, hv + v);
-                    float4 br = sub4(mul4(dr, qr), mul4(dim, qi));
-                    float4 bi = addrn4(mul4(dr, qi), mul4(dim, qr));
-                    acc1 = dot4(br, sr, acc1);
-                    acc1 = dot4(bi, sim, acc1);
-                    if (a.A[1]) {
-                        st4(a.A[1] + p * d, v, br);
-                        st4(a.A[1] + p * d, hv + v, bi);
+#pragma unroll 1
+        for (int k = 0; k < 32; k++) {
+            const int64_t p = first + k * nwarps;
+            if (p >= a.Bp) break;
+            const float* src = shfl_ptr(my_src, k);
+            const float* dst = shfl_ptr(my_dst, k);
+            const int64_t rid = shfl_i64(my_rid, k);
+            if (p >= a.B) {  // zero padding rows (comparators.cpp:11-15, decoder_methods.cpp:103-111)
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = 0; s < a.sides; s++) {
+                    for (int v = lane; v < dv; v += 32) {
+                        if (a.A[s]) st4(a.A[s] + p * d, v, z);
+                        if (a.A_hi[s]) store_split4(a.A_hi[s], a.A_lo[s], p * d + 4 * v, z);
                     }
-                    if (a.A_hi[1]) {
-                        store_split4(a.A_hi[1], a.A_lo[1], p * d + 4 * v, br);
-                        store_split4(a.A_hi[1], a.A_lo[1], p * d + 4 * (hv + v), bi);
+                    if (lane == 0) a.pos[s][p] = 0.f;
+                }
+                continue;
+            }
+            const float* r = (DEC != MB_DECODER_DOT) ? a.rel + rid * d : nullptr;
+            const float* ri = (DEC != MB_DECODER_DOT && two) ? a.inv_rel + rid * d : nullptr;
+            float acc0 = 0.f, acc1 = 0.f;
+            if (DEC == MB_DECODER_COMPLEX) {
+                float4 sr[CHV], sim[CHV], dr[CHV], dim[CHV], rr[CHV], rim[CHV], qr[CHV], qi[CHV];
+                const float* riq = two ? ri : r;
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int vc = min(lane + 32 * c, hv - 1);
+                    sr[c] = ldg_nc4(src, vc), sim[c] = ldg_nc4(src, hv + vc), dr[c] = ldg_nc4(dst, vc), dim[c] = ldg_nc4(dst, hv + vc);
+                    rr[c] = ldg_nc4(r, vc), rim[c] = ldg_nc4(r, hv + vc);
+                    qr[c] = ldg_nc4(riq, vc), qi[c] = ldg_nc4(riq, hv + vc);
+                }
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int v = lane + 32 * c;
+                    if (v >= hv) continue;
+                    float4 ar = sub4(mul4(sr[c], rr[c]), mul4(sim[c], rim[c]));    // relation_operators.cpp:31
+                    float4 ai = addrn4(mul4(sr[c], rim[c]), mul4(sim[c], rr[c]));  // relation_operators.cpp:32
+                    acc0 = dot4(ar, dr[c], acc0);
+                    acc0 = dot4(ai, dim[c], acc0);
+                    if (a.A[0]) {
+                        st4(a.A[0] + p * d, v, ar);
+                        st4(a.A[0] + p * d, hv + v, ai);
+                    }
+                    if (a.A_hi[0]) {
+                        store_split4(a.A_hi[0], a.A_lo[0], p * d + 4 * v, ar);
+                        store_split4(a.A_hi[0], a.A_lo[0], p * d + 4 * (hv + v), ai);
+                    }
+                    if (two) {
+                        float4 br = sub4(mul4(dr[c], qr[c]), mul4(dim[c], qi[c]));
+                        float4 bi = addrn4(mul4(dr[c], qi[c]), mul4(dim[c], qr[c]));
+                        acc1 = dot4(br, sr[c], acc1);
+                        acc1 = dot4(bi, sim[c], acc1);
+                        if (a.A[1]) {
+                            st4(a.A[1] + p * d, v, br);
+                            st4(a.A[1] + p * d, hv + v, bi);
+                        }
+                        if (a.A_hi[1]) {
+                            store_split4(a.A_hi[1], a.A_lo[1], p * d + 4 * v, br);
+                            store_split4(a.A_hi[1], a.A_lo[1], p * d + 4 * (hv + v), bi);
+                        }
+                    }
+                }
+            } else {
+                float4 sv[CHV], dvv[CHV], rv[CHV], qv[CHV];
+                const float* riq = two ? ri : r;
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int vc = min(lane + 32 * c, dv - 1);
+                    sv[c] = ldg_nc4(src, vc), dvv[c] = ldg_nc4(dst, vc);
+                    if (DEC == MB_DECODER_DISTMULT) rv[c] = ldg_nc4(r, vc), qv[c] = ldg_nc4(riq, vc);
+                }
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int v = lane + 32 * c;
+                    if (v >= dv) continue;
+                    float4 av = (DEC == MB_DECODER_DISTMULT) ? mul4(sv[c], rv[c]) : sv[c];  // relation_operators.cpp:11
+                    acc0 = dot4(av, dvv[c], acc0);
+                    if (a.A[0]) st4(a.A[0] + p * d, v, av);
+                    if (a.A_hi[0]) store_split4(a.A_hi[0], a.A_lo[0], p * d + 4 * v, av);
+                    if (DEC == MB_DECODER_DISTMULT && two) {
+                        float4 bv = mul4(dvv[c], qv[c]);
+                        acc1 = dot4(bv, sv[c], acc1);
+                        if (a.A[1]) st4(a.A[1] + p * d, v, bv);
+                        if (a.A_hi[1]) store_split4(a.A_hi[1], a.A_lo[1], p * d + 4 * v, bv);
                     }
                 }
             }
-        } else {
-            for (int v = lane; v < dv; v += 32) {
-                float4 sv = ld4(src, v), dvv = ld4(dst, v);
-                float4 av = (DEC == MB_DECODER_DISTMULT) ? mul4(sv, ld4(r, v)) : sv;  // relation_operators.cpp:11
-                acc0 = dot4(av, dvv, acc0);
-                if (a.A[0]) st4(a.A[0] + p * d, v, av);
-                if (a.A_hi[0]) store_split4(a.A_hi[0], a.A_lo[0], p * d + 4 * v, av);
-                if (a.sides == 2) {
-                    float4 bv = mul4(dvv, ld4(ri, v));
-                    acc1 = dot4(bv, sv, acc1);
-                    if (a.A[1]) st4(a.A[1] + p * d, v, bv);
-                    if (a.A_hi[1]) store_split4(a.A_hi[1], a.A_lo[1], p * d + 4 * v, bv);
-                }
+            acc0 = warp_sum(acc0);
+            acc1 = warp_sum(acc1);
+            if (lane == 0) {
+                a.pos[0][p] = acc0;  // comparators.cpp:67-68
+                if (two) a.pos[1][p] = acc1;
             }
-        }
-        acc0 = warp_sum(acc0);
-        acc1 = warp_sum(acc1);
-        if (lane == 0) {
-            a.pos[0][p] = acc0;  // comparators.cpp:67-68
-            if (a.sides == 2) a.pos[1][p] = acc1;
         }
     }
 }
@@ -261,76 +363,113 @@ struct EdgeBwdVArgs {
     float* drel[2];        // [B,d] per side or null
 };
 
-template <int DEC>
+template <int DEC, int CHV>  // CHV: float4 chunks per lane of a full row (DOT / DistMult) or of a complex half (ComplEx)
 __global__ void __launch_bounds__(kThreads) edge_backward_kernel(EdgeBwdVArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     const int d = a.d, dv = d >> 2, hv = d >> 3;
     const bool inverse = a.sides == 2;
-    for (int64_t i = warp0; i < a.B; i += nwarps) {
-        const int64_t si = a.edges[i * a.cols], ti = a.edges[i * a.cols + a.cols - 1];
-        const float* src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[si]) : a.emb + si * a.emb_ld;
-        const float* dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, a.row_map[ti]) : a.emb + ti * a.emb_ld;
-        const int64_t rid = (DEC != MB_DECODER_DOT) ? a.edges[i * a.cols + 1] : 0;
-        const float* r = (DEC != MB_DECODER_DOT) ? a.rel + rid * d : nullptr;
-        const float* ri = (DEC != MB_DECODER_DOT && inverse) ? a.inv_rel + rid * d : nullptr;
-        const float g0 = a.gpos[0][i];
-        const float g1 = inverse ? a.gpos[1][i] : 0.f;
-        const float* da0 = a.dA[0] + i * d;
-        const float* da1 = inverse ? a.dA[1] + i * d : nullptr;
-        float* dsrc = a.gcat + i * d;
-        float* ddst = a.gcat + (a.B + i) * d;
-        if (DEC == MB_DECODER_COMPLEX) {
-            for (int v = lane; v < hv; v += 32) {
-                float4 sr = ld4(src, v), sim = ld4(src, hv + v), dr = ld4(dst, v), dim = ld4(dst, hv + v);
-                float4 rr = ld4(r, v), rim = ld4(r, hv + v);
-                float4 ar = sub4(mul4(sr, rr), mul4(sim, rim)), ai = addrn4(mul4(sr, rim), mul4(sim, rr));
-                float4 gar = fma4(g0, dr, ld4(da0, v)), gai = fma4(g0, dim, ld4(da0, hv + v));  // d/da: bmm backward + pos dot
-                float4 dsr = add4(mul4(gar, rr), mul4(gai, rim));
-                float4 dsi = sub4(mul4(gai, rr), mul4(gar, rim));
-                if (a.drel[0]) {
-                    st4(a.drel[0] + i * d, v, add4(mul4(gar, sr), mul4(gai, sim)));
-                    st4(a.drel[0] + i * d, hv + v, sub4(mul4(gai, sr), mul4(gar, sim)));
-                }
-                float4 ddr = scale4(g0, ar), ddi = scale4(g0, ai);  // pos = <a, dst>
-                if (inverse) {
-                    float4 qr = ld4(ri, v), qi = ld4(ri, hv + v);
-                    float4 br = sub4(mul4(dr, qr), mul4(dim, qi)), bi = addrn4(mul4(dr, qi), mul4(dim, qr));
-                    float4 gbr = fma4(g1, sr, ld4(da1, v)), gbi = fma4(g1, sim, ld4(da1, hv + v));
-                    ddr = add4(ddr, add4(mul4(gbr, qr), mul4(gbi, qi)));
-                    ddi = add4(ddi, sub4(mul4(gbi, qr), mul4(gbr, qi)));
-                    if (a.drel[1]) {
-                        st4(a.drel[1] + i * d, v, add4(mul4(gbr, dr), mul4(gbi, dim)));
-                        st4(a.drel[1] + i * d, hv + v, sub4(mul4(gbi, dr), mul4(gbr, dim)));
-                    }
-                    dsr = fma4(g1, br, dsr);  // inv_pos = <b, src>
-                    dsi = fma4(g1, bi, dsi);
-                }
-                st4(dsrc, v, dsr);
-                st4(dsrc, hv + v, dsi);
-                st4(ddst, v, ddr);
-                st4(ddst, hv + v, ddi);
+    for (int64_t first = warp0; first < a.B; first += 32 * nwarps) {
+        const float *my_src = nullptr, *my_dst = nullptr;
+        int64_t my_rid = 0;
+        float my_g0 = 0.f, my_g1 = 0.f;
+        {
+            const int64_t i = first + lane * nwarps;
+            if (i < a.B) {
+                const int64_t si = __ldg(a.edges + i * a.cols), ti = __ldg(a.edges + i * a.cols + a.cols - 1);
+                if (DEC != MB_DECODER_DOT) my_rid = __ldg(a.edges + i * a.cols + 1);
+                my_src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + si)) : a.emb + si * a.emb_ld;
+                my_dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + ti)) : a.emb + ti * a.emb_ld;
+                my_g0 = a.gpos[0][i];
+                if (inverse) my_g1 = a.gpos[1][i];
             }
-        } else {
-            for (int v = lane; v < dv; v += 32) {
-                float4 sv = ld4(src, v), dvv = ld4(dst, v);
-                float4 rv = (DEC == MB_DECODER_DISTMULT) ? ld4(r, v) : make_float4(1.f, 1.f, 1.f, 1.f);
-                float4 av = (DEC == MB_DECODER_DISTMULT) ? mul4(sv, rv) : sv;
-                float4 ga = fma4(g0, dvv, ld4(da0, v));
-                float4 ds = (DEC == MB_DECODER_DISTMULT) ? mul4(ga, rv) : ga;
-                if (a.drel[0]) st4(a.drel[0] + i * d, v, mul4(ga, sv));
-                float4 dd = scale4(g0, av);
-                if (inverse) {
-                    float4 qv = ld4(ri, v);
-                    float4 bv = mul4(dvv, qv);
-                    float4 gb = fma4(g1, sv, ld4(da1, v));
-                    dd = add4(dd, mul4(gb, qv));
-                    if (a.drel[1]) st4(a.drel[1] + i * d, v, mul4(gb, dvv));
-                    ds = fma4(g1, bv, ds);
+        }
+#pragma unroll 1
+        for (int k = 0; k < 32; k++) {
+            const int64_t i = first + k * nwarps;
+            if (i >= a.B) break;
+            const float* src = shfl_ptr(my_src, k);
+            const float* dst = shfl_ptr(my_dst, k);
+            const int64_t rid = shfl_i64(my_rid, k);
+            const float g0 = __shfl_sync(0xffffffffu, my_g0, k), g1 = __shfl_sync(0xffffffffu, my_g1, k);
+            const float* r = (DEC != MB_DECODER_DOT) ? a.rel + rid * d : nullptr;
+            const float* ri = (DEC != MB_DECODER_DOT && inverse) ? a.inv_rel + rid * d : nullptr;
+            const float* da0 = a.dA[0] + i * d;
+            const float* da1 = inverse ? a.dA[1] + i * d : nullptr;
+            float* dsrc = a.gcat + i * d;
+            float* ddst = a.gcat + (a.B + i) * d;
+            if (DEC == MB_DECODER_COMPLEX) {
+                float4 sr[CHV], sim[CHV], dr[CHV], dim[CHV], rr[CHV], rim[CHV], qr[CHV], qi[CHV], a0r[CHV], a0i[CHV], a1r[CHV], a1i[CHV];
+                const float* riq = inverse ? ri : r;
+                const float* da1q = inverse ? da1 : da0;
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int vc = min(lane + 32 * c, hv - 1);
+                    sr[c] = ldg_nc4(src, vc), sim[c] = ldg_nc4(src, hv + vc), dr[c] = ldg_nc4(dst, vc), dim[c] = ldg_nc4(dst, hv + vc);
+                    rr[c] = ldg_nc4(r, vc), rim[c] = ldg_nc4(r, hv + vc);
+                    a0r[c] = ldg4(da0, vc), a0i[c] = ldg4(da0, hv + vc);
+                    qr[c] = ldg_nc4(riq, vc), qi[c] = ldg_nc4(riq, hv + vc), a1r[c] = ldg4(da1q, vc), a1i[c] = ldg4(da1q, hv + vc);
                 }
-                st4(dsrc, v, ds);
-                st4(ddst, v, dd);
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int v = lane + 32 * c;
+                    if (v >= hv) continue;
+                    float4 ar = sub4(mul4(sr[c], rr[c]), mul4(sim[c], rim[c])), ai = addrn4(mul4(sr[c], rim[c]), mul4(sim[c], rr[c]));
+                    float4 gar = fma4(g0, dr[c], a0r[c]), gai = fma4(g0, dim[c], a0i[c]);  // d/da: bmm backward + pos dot
+                    float4 dsr = add4(mul4(gar, rr[c]), mul4(gai, rim[c]));
+                    float4 dsi = sub4(mul4(gai, rr[c]), mul4(gar, rim[c]));
+                    if (a.drel[0]) {
+                        st4(a.drel[0] + i * d, v, add4(mul4(gar, sr[c]), mul4(gai, sim[c])));
+                        st4(a.drel[0] + i * d, hv + v, sub4(mul4(gai, sr[c]), mul4(gar, sim[c])));
+                    }
+                    float4 ddr = scale4(g0, ar), ddi = scale4(g0, ai);  // pos = <a, dst>
+                    if (inverse) {
+                        float4 br = sub4(mul4(dr[c], qr[c]), mul4(dim[c], qi[c])), bi = addrn4(mul4(dr[c], qi[c]), mul4(dim[c], qr[c]));
+                        float4 gbr = fma4(g1, sr[c], a1r[c]), gbi = fma4(g1, sim[c], a1i[c]);
+                        ddr = add4(ddr, add4(mul4(gbr, qr[c]), mul4(gbi, qi[c])));
+                        ddi = add4(ddi, sub4(mul4(gbi, qr[c]), mul4(gbr, qi[c])));
+                        if (a.drel[1]) {
+                            st4(a.drel[1] + i * d, v, add4(mul4(gbr, dr[c]), mul4(gbi, dim[c])));
+                            st4(a.drel[1] + i * d, hv + v, sub4(mul4(gbi, dr[c]), mul4(gbr, dim[c])));
+                        }
+                        dsr = fma4(g1, br, dsr);  // inv_pos = <b, src>
+                        dsi = fma4(g1, bi, dsi);
+                    }
+                    st4(dsrc, v, dsr);
+                    st4(dsrc, hv + v, dsi);
+                    st4(ddst, v, ddr);
+                    st4(ddst, hv + v, ddi);
+                }
+            } else {
+                float4 sv[CHV], dvv[CHV], rv[CHV], qv[CHV], a0[CHV], a1[CHV];
+                const float* da1q = inverse ? da1 : da0;
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int vc = min(lane + 32 * c, dv - 1);
+                    sv[c] = ldg_nc4(src, vc), dvv[c] = ldg_nc4(dst, vc), a0[c] = ldg4(da0, vc), a1[c] = ldg4(da1q, vc);
+                    rv[c] = (DEC == MB_DECODER_DISTMULT) ? ldg_nc4(r, vc) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    qv[c] = (DEC == MB_DECODER_DISTMULT && inverse) ? ldg_nc4(ri, vc) : make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+#pragma unroll
+                for (int c = 0; c < CHV; c++) {
+                    const int v = lane + 32 * c;
+                    if (v >= dv) continue;
+                    float4 av = (DEC == MB_DECODER_DISTMULT) ? mul4(sv[c], rv[c]) : sv[c];
+                    float4 ga = fma4(g0, dvv[c], a0[c]);
+                    float4 ds = (DEC == MB_DECODER_DISTMULT) ? mul4(ga, rv[c]) : ga;
+                    if (a.drel[0]) st4(a.drel[0] + i * d, v, mul4(ga, sv[c]));
+                    float4 dd = scale4(g0, av);
+                    if (inverse) {
+                        float4 bv = mul4(dvv[c], qv[c]);
+                        float4 gb = fma4(g1, sv[c], a1[c]);
+                        dd = add4(dd, mul4(gb, qv[c]));
+                        if (a.drel[1]) st4(a.drel[1] + i * d, v, mul4(gb, dvv[c]));
+                        ds = fma4(g1, bv, ds);
+                    }
+                    st4(dsrc, v, ds);
+                    st4(ddst, v, dd);
+                }
             }
         }
     }
@@ -369,64 +508,80 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
     const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
     const int d = a.d, dv = d >> 2;
-    for (int64_t u = warp0; u < a.n_seg; u += nwarps) {
-        const uint32_t beg = a.offsets[u], end = a.offsets[u + 1];
-        float4 e[CH], s[CH];
-        float *erow = nullptr, *srow = nullptr;
-        if (MODE == 2 && beg == end) continue;  // padding segment (graph replay runs with n_seg = capacity): no row, nothing to update
-        if (MODE == 2) {  // issue the table reads first: they do not depend on the slot list
-            const int64_t r = a.ids[u];
-            if (a.sp.world <= 1) {
-                erow = a.table + r * a.ld;
-                srow = a.state_table + r * a.ld;
-            } else {  // the owner's HBM (peer-mapped when remote): Adagrad read-modify-write straight over NVLink
-                const int64_t o = r / a.sp.rows_per_rank, lr_ = r - o * a.sp.rows_per_rank;
-                erow = a.sp.table[o] + lr_ * a.ld;
-                srow = a.sp.state[o] + lr_ * a.ld;
+    // the warp owns segments warp0, warp0 + nwarps, ... ; lane k resolves bounds, table rows and first gradient row of the k-th of the next 32
+    for (int64_t first = warp0; first < a.n_seg; first += 32 * nwarps) {
+        uint32_t my_beg = 0, my_end = 0;
+        float *my_e = nullptr, *my_s = nullptr;
+        const float* my_row = nullptr;
+        {
+            const int64_t u = first + lane * nwarps;
+            if (u < a.n_seg) {
+                my_beg = __ldg(a.offsets + u);
+                my_end = __ldg(a.offsets + u + 1);
+                if (MODE == 2 && my_end > my_beg) {  // (empty = padding segment: graph replay runs with n_seg = capacity; no row, nothing to update)
+                    const int64_t r = __ldg(a.ids + u);
+                    if (a.sp.world <= 1) {
+                        my_e = a.table + r * a.ld;
+                        my_s = a.state_table + r * a.ld;
+                    } else {  // the owner's HBM (peer-mapped when remote): Adagrad read-modify-write straight over NVLink
+                        const int64_t o = r / a.sp.rows_per_rank, lr_ = r - o * a.sp.rows_per_rank;
+                        my_e = a.sp.table[o] + lr_ * a.ld;
+                        my_s = a.sp.state[o] + lr_ * a.ld;
+                    }
+                }
+                if (my_end > my_beg) my_row = a.rows + (int64_t)__ldg(a.slots + my_beg) * d;
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < 32; k++) {
+            const int64_t u = first + k * nwarps;
+            if (u >= a.n_seg) break;
+            const uint32_t beg = __shfl_sync(0xffffffffu, my_beg, k), end = __shfl_sync(0xffffffffu, my_end, k);
+            float* erow = shfl_ptr(my_e, k);
+            float* srow = shfl_ptr(my_s, k);
+            const float* row0 = shfl_ptr(my_row, k);
+            if (MODE == 2 && beg == end) continue;
+            float4 e[CH], s[CH], acc[CH];
+            const float* g0 = row0 ? row0 : a.rows;  // empty segment (modes 0 / 1): load something valid, add nothing
+#pragma unroll
+            for (int c = 0; c < CH; c++) {  // table row, state row and first gradient row: 3 * CH independent loads in flight per lane
+                const int vc = min(lane + 32 * c, dv - 1);
+                if (MODE == 2) {
+                    e[c] = ldg4(erow, vc);
+                    s[c] = ldg4(srow, vc);
+                } else if (MODE == 1) {
+                    s[c] = ldg_nc4(a.state + u * a.state_ld, vc);
+                }
+                acc[c] = ldg4(g0, vc);
             }
 #pragma unroll
-            for (int c = 0; c < CH; c++) {
-                int v = lane + 32 * c;
-                if (v < dv) {
-                    e[c] = reinterpret_cast<const float4*>(erow)[v];
-                    s[c] = reinterpret_cast<const float4*>(srow)[v];
+            for (int c = 0; c < CH; c++) acc[c] = row0 ? addrn4(make_float4(0.f, 0.f, 0.f, 0.f), acc[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t q = beg + 1; q < end; q++) {  // duplicates: remaining gradient rows in slot order
+                const float* row = a.rows + (int64_t)a.slots[q] * d;
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int v = lane + 32 * c;
+                    if (v < dv) acc[c] = addrn4(acc[c], ld_f4(reinterpret_cast<const float4*>(row) + v));
                 }
             }
-        } else if (MODE == 1) {
 #pragma unroll
             for (int c = 0; c < CH; c++) {
-                int v = lane + 32 * c;
-                if (v < dv) s[c] = ld4(a.state + u * a.state_ld, v);
-            }
-        }
-        float4 acc[CH];
-#pragma unroll
-        for (int c = 0; c < CH; c++) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (uint32_t q = beg; q < end; q++) {
-            const float* row = a.rows + (int64_t)a.slots[q] * d;
-#pragma unroll
-            for (int c = 0; c < CH; c++) {
-                int v = lane + 32 * c;
-                if (v < dv) acc[c] = addrn4(acc[c], ld_f4(reinterpret_cast<const float4*>(row) + v));
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < CH; c++) {
-            int v = lane + 32 * c;
-            if (v >= dv) continue;
-            if (MODE == 0) {
-                st4(a.out + u * a.out_ld, v, acc[c]);
-            } else if (MODE == 1) {
-                if (a.out) st4(a.out + u * a.out_ld, v, acc[c]);
-                float4 de, ds, sn;
-                adagrad4(acc[c], s[c], a.neg_lr, de, ds, sn);
-                st4(a.delta_e + u * d, v, de);
-                st4(a.delta_s + u * d, v, ds);
-            } else {
-                float4 de, ds, sn;
-                adagrad4(acc[c], s[c], a.neg_lr, de, ds, sn);
-                st_stream(reinterpret_cast<float4*>(erow) + v, addrn4(e[c], de));
-                st_stream(reinterpret_cast<float4*>(srow) + v, sn);
+                const int v = lane + 32 * c;
+                if (v >= dv) continue;
+                if (MODE == 0) {
+                    st4(a.out + u * a.out_ld, v, acc[c]);
+                } else if (MODE == 1) {
+                    if (a.out) st4(a.out + u * a.out_ld, v, acc[c]);
+                    float4 de, ds, sn;
+                    adagrad4(acc[c], s[c], a.neg_lr, de, ds, sn);
+                    st4(a.delta_e + u * d, v, de);
+                    st4(a.delta_s + u * d, v, ds);
+                } else {
+                    float4 de, ds, sn;
+                    adagrad4(acc[c], s[c], a.neg_lr, de, ds, sn);
+                    st_stream(reinterpret_cast<float4*>(erow) + v, addrn4(e[c], de));
+                    st_stream(reinterpret_cast<float4*>(srow) + v, sn);
+                }
             }
         }
     }

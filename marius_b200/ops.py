@@ -77,8 +77,18 @@ class Context:
         """enable / disable CUDA-graph replay of the fused step for this context"""
         check(lib.mb_graph_enable(self._h, int(bool(on))))
 
-    def profile(self, on: bool) -> None:
-        check(lib.mb_profile_enable(self._h, int(bool(on))))
+    def profile(self, on) -> None:
+        """False/0 off, True/1 stage timing (side streams folded into the caller's stream), 2 timeline (streams stay concurrent)"""
+        check(lib.mb_profile_enable(self._h, int(on)))
+
+    def profile_timeline(self, cap: int = 4096) -> list:
+        """[(stage name, start ms, end ms)] of the stage launches recorded since the last read (profile(2)); synchronises the device."""
+        st = (C.c_int * cap)()
+        a = (C.c_float * cap)()
+        b = (C.c_float * cap)()
+        n = C.c_int(0)
+        check(lib.mb_profile_timeline(self._h, cap, st, a, b, C.byref(n)))
+        return [(lib.mb_profile_stage_name(st[i]).decode(), float(a[i]), float(b[i])) for i in range(n.value)]
 
     def profile_read(self) -> dict:
         """{stage name: (total ms, launches)} accumulated since the last read (synchronises the device)."""
