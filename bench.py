@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # our sm_100a path (one rank per GPU under torchrun for N > 1)
     python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref) on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic edges: ComplEx, d=400, 1000 negatives per chunk of
-1000 positives, both-side corruption, SoftmaxCE-SUM, sparse Adagrad lr 0.1 (BASELINE.json configs[1] shape; the
+A "step" is one pass of the hot path over one batch of synthetic edges (default 50 000 positives): ComplEx, d=400, 1000 negatives
+per chunk of 1000 positives, both-side corruption, SoftmaxCE-SUM, sparse Adagrad lr 0.1 (BASELINE.json configs[1] shape; the
 table is sized to fit one B200 WITH its Adagrad state).  Negative sampling and unique-id mapping are
 inputs: batches are pre-built and excluded from every timed region, for both arms.
 
@@ -420,7 +420,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference_run(args.cpu_steps, 1, B, args.ref_nodes, seed=7)
+            r = cpu_reference_run(args.cpu_steps, 1, args.ref_batch, args.ref_nodes, seed=7)
             cpu = dict(value=r["value"], unit=UNIT, cores=r["cores"], kind=r["kind"], sample=r["sample"])
         except Exception as ex:  # the baseline is reported, never required
             cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="unavailable", sample=str(ex)[:200])
@@ -455,17 +455,21 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=10000, help="positives per step (chunks of 1000)")
+    ap.add_argument("--batch", type=int, default=50000,
+                    help="positives per step, in chunks of 1000 (50 000 = the batch the Marius paper trains Freebase86m with; 10 000 runs ~25 %% slower "
+                         "per edge because the contractions have too few tiles per SM, see DESIGN.md 6)")
     ap.add_argument("--nodes", type=int, default=40_000_000, help="table rows per GPU (with Adagrad state: 2 x rows x 1600 B)")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32", "bf16"])
     ap.add_argument("--ref-nodes", type=int, default=2_000_000, help="host table rows for the CPU reference arm")
-    ap.add_argument("--ref-batch", type=int, default=10000)
+    ap.add_argument("--ref-batch", type=int, default=0, help="batch of the CPU reference arm (0 = --batch)")
     ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = remote rows read / updated over NVLink-mapped peer memory inside the fused step; "
                          "'nccl' = rows and gradient rows exchanged with grouped NCCL send/recv (marius_b200/dist.py ShardedTable)")
     args = ap.parse_args()
+    if args.ref_batch <= 0:
+        args.ref_batch = args.batch
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
