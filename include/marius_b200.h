@@ -139,6 +139,24 @@ typedef struct mb_batch {
 mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, float* pos, float* neg,
                              float* inv_pos, float* inv_neg, void* stream);
 
+/* ---- evaluation ----------------------------------------------------------------------------------------
+ * apply_score_filter (data/samplers/negative.cpp:306-311, called by Model::forward_lp, nn/model.cpp:279-285):
+ * scores[filter[i,0], filter[i,1]] = -1e9 for the F (row, column) pairs of `filter` ([F,2] int64, device).  Like index_put_, a
+ * negative index wraps once and an out-of-range pair is an error (MB_ERR_INVALID; reported after a stream synchronisation). */
+mb_status mb_apply_score_filter(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, void* stream);
+
+/* LinkPredictionReporter::computeRanks (reporting/reporting.cpp:56-58): ranks[i] = 1 + #{ j : neg[i,j] >= pos[i] }, int64. */
+mb_status mb_compute_ranks(const float* pos, const float* neg, int64_t rows, int64_t N, int64_t ld, int64_t* ranks, void* stream);
+
+/* Model::evaluate_batch for link prediction (nn/model.cpp:335-349): forward_lp with the batch's score filters
+ * (dst_filter on the dst-corruption scores, src_filter on the src-corruption scores; NULL / 0 = none), then one computeRanks per
+ * side.  ranks [Bp] and inv_ranks [Bp] (inverse side; may be NULL when the batch has none) are int64 device arrays in the order
+ * LinkPredictionReporter::addResult receives them; padding rows (B <= i < Bp) rank N + 1 exactly as in the reference.  The score
+ * matrices stay in the context's workspace; pos / inv_pos [Bp] are optional outputs (NULL to skip). */
+mb_status mb_evaluate_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, const int64_t* dst_filter,
+                            int64_t Fd, const int64_t* src_filter, int64_t Fs, int64_t* ranks, int64_t* inv_ranks, float* pos, float* inv_pos,
+                            void* stream);
+
 /* Backward of node_corrupt_forward for ARBITRARY upstream gradients (what libtorch autograd computes under loss.backward(),
  * model.cpp:324, for any of the reference's loss functions, nn/loss.cpp:50-175): gpos [Bp], gneg [Bp,N] (+ inverse side) ->
  * grad [U,d] = d/d node_embeddings_, rel_grad / inv_rel_grad [R,d].  Used by the autograd::Function of the C++ adapter. */

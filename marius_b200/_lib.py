@@ -44,6 +44,9 @@ _SIGS = {
     "mb_map_tensors": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "mb_reduce_rows_by_key": [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     "mb_decoder_forward": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
+    "mb_apply_score_filter": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],
+    "mb_compute_ranks": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
+    "mb_evaluate_batch": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "mb_decoder_backward": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mb_train_batch": [_vp, C.POINTER(mb_batch), _vp, _i64, _vp, _i64, _f, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mb_train_step": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, _vp, _vp],

@@ -872,6 +872,72 @@ mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float
     return MB_OK;
 }
 
+static mb_status filter_checked(mb_context* ctx, float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, cudaStream_t st) {
+    if (F == 0) return MB_OK;
+    MB_REQUIRE(filter != nullptr && scores != nullptr, "null filter / scores");
+    int* flag = nullptr;
+    MB_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&flag), sizeof(int), st));
+    MB_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    mb_status rs = launch_score_filter(scores, rows, N, ld, filter, F, flag, st);
+    int host_flag = 0;
+    cudaError_t e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(flag, st);
+    (void)ctx;
+    MB_TRY(rs);
+    MB_CUDA_TRY(e);
+    MB_REQUIRE(host_flag == 0, "score filter index out of range");
+    return MB_OK;
+}
+
+mb_status mb_apply_score_filter(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, void* stream) {
+    MB_REQUIRE(rows >= 0 && N >= 0 && F >= 0 && ld >= N, "bad dimensions");
+    return filter_checked(nullptr, scores, rows, N, ld, filter, F, (cudaStream_t)stream);
+}
+
+mb_status mb_compute_ranks(const float* pos, const float* neg, int64_t rows, int64_t N, int64_t ld, int64_t* ranks, void* stream) {
+    MB_REQUIRE(rows >= 0 && N >= 0 && ld >= N, "bad dimensions");
+    MB_REQUIRE(rows == 0 || (pos != nullptr && neg != nullptr && ranks != nullptr), "UndefinedTensor");
+    return launch_ranks(pos, neg, rows, N, ld, ranks, (cudaStream_t)stream);
+}
+
+mb_status mb_evaluate_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, int precision, const int64_t* dst_filter,
+                            int64_t Fd, const int64_t* src_filter, int64_t Fs, int64_t* ranks, int64_t* inv_ranks, float* pos, float* inv_pos,
+                            void* stream) {
+    MB_REQUIRE(ctx != nullptr, "context is null");
+    MB_TRY(validate_batch(batch));
+    MB_REQUIRE(emb != nullptr && ranks != nullptr, "UndefinedTensor");
+    MB_REQUIRE(emb_ld >= batch->d, "emb_ld < d");
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    MB_REQUIRE(Fd >= 0 && Fs >= 0, "negative filter size");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    Plan p;
+    fill_plan_dims(p, batch, precision);
+    if (p.sides == 2) MB_REQUIRE(inv_ranks != nullptr, "inverse outputs required when inverse relations are used");
+    {
+        Arena sizing(nullptr);
+        p.layout(sizing, false, false, true);
+        MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+        Arena place(ctx->ws);
+        p.layout(place, false, false, true);
+    }
+    float* S1 = p.S + p.Bp * p.N;
+    MB_TRY(run_forward(ctx, p, batch, emb, emb_ld, nullptr, precision, p.pos, p.S, S1, true, st));
+    if (p.Bc == 0) {  // no positives: nothing to rank
+        return MB_OK;
+    }
+    MB_TRY(filter_checked(ctx, p.S, p.Bp, p.N, p.N, dst_filter, Fd, st));
+    MB_TRY(launch_ranks(p.pos, p.S, p.Bp, p.N, p.N, ranks, st));
+    if (p.sides == 2) {
+        MB_TRY(filter_checked(ctx, S1, p.Bp, p.N, p.N, src_filter, Fs, st));
+        MB_TRY(launch_ranks(p.pos + p.Bp, S1, p.Bp, p.N, p.N, inv_ranks, st));
+    }
+    if (pos) MB_CUDA_TRY(cudaMemcpyAsync(pos, p.pos, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
+    if (inv_pos && p.sides == 2) MB_CUDA_TRY(cudaMemcpyAsync(inv_pos, p.pos + p.Bp, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
+    return MB_OK;
+}
+
 mb_status mb_train_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, const float* state, int64_t state_ld, float lr,
                          int reduction, int precision, float* loss, float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad,
                          void* stream) {

@@ -58,6 +58,10 @@ mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, co
 mb_status launch_rel_reduce(const float* drel0, const float* drel1, float* out0, float* out1, const uint32_t* slots, const uint32_t* offsets, int64_t R,
                             int d, cudaStream_t st);
 
+// eval_kernels.cu
+mb_status launch_score_filter(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, int* bad_flag, cudaStream_t st);
+mb_status launch_ranks(const float* pos, const float* neg, int64_t rows, int64_t N, int64_t ld, int64_t* ranks, cudaStream_t st);
+
 // gemm_simt.cu
 mb_status gemm_simt(const float* A, int64_t sAm, int64_t sAk, int64_t sAb, const float* B, int64_t sBk, int64_t sBn, int64_t sBb, float* C, int64_t ldc,
                     int64_t sCb, int M, int N, int K, int batches, cudaStream_t st);

@@ -271,6 +271,64 @@ def decoder_forward(ctx: Context, kind: int, emb: torch.Tensor, edges, rel, inv_
     return pos, neg, inv_pos, inv_neg
 
 
+def _check_filter(f: Optional[torch.Tensor]):
+    if f is None:
+        return None, 0
+    if f.dim() != 2 or f.size(1) != 2 or f.dtype != torch.int64:
+        raise MariusB200Error(_INVALID, "score filter must be an int64 [F, 2] tensor of (row, column) pairs")
+    f = f.contiguous()
+    return f, int(f.size(0))
+
+
+def apply_score_filter(scores: torch.Tensor, filt: Optional[torch.Tensor]) -> torch.Tensor:
+    """apply_score_filter (negative.cpp:306-311): scores[filter[:,0], filter[:,1]] = -1e9, in place."""
+    _need_cuda(scores, filt)
+    f, F = _check_filter(filt)
+    if F:
+        check(lib.mb_apply_score_filter(_ptr(scores), scores.size(0), scores.size(1), _rowmajor(scores, "scores"), _ptr(f), F, _stream()))
+    return scores
+
+
+def compute_ranks(pos: torch.Tensor, neg: torch.Tensor) -> torch.Tensor:
+    """LinkPredictionReporter::computeRanks (reporting.cpp:56-58): (neg >= pos.unsqueeze(1)).sum(1) + 1, int64."""
+    _need_cuda(pos, neg)
+    if pos.dim() != 1 or neg.dim() != 2 or pos.size(0) != neg.size(0):
+        raise MariusB200Error(_INVALID, "computeRanks: pos [rows], neg [rows, N]")
+    ranks = torch.empty(pos.size(0), dtype=torch.int64, device=pos.device)
+    check(lib.mb_compute_ranks(_ptr(pos.contiguous()), _ptr(neg), neg.size(0), neg.size(1), _rowmajor(neg, "neg_scores"), _ptr(ranks), _stream()))
+    return ranks
+
+
+def evaluate_batch(ctx: Context, kind: int, emb: torch.Tensor, edges, rel, inv_rel, dst_negs, src_negs, dst_filter=None, src_filter=None,
+                   precision: int = PREC_BF16X3):
+    """Model::evaluate_batch (model.cpp:335-349): scores, score filters and ranks of both corruption sides in one call.
+    Returns (ranks [Bp], inv_ranks [Bp] or None, pos [Bp], inv_pos [Bp] or None)."""
+    _need_cuda(emb, edges, rel, inv_rel, dst_negs, src_negs, dst_filter, src_filter)
+    if emb is None:
+        raise MariusB200Error(_INVALID, "UndefinedTensor")
+    b, keep = _make_batch(kind, emb.size(0), emb.size(1), edges, rel, inv_rel, dst_negs, src_negs)
+    Bp = padded_rows(b.B, b.C)
+    inverse = b.inv_rel is not None and b.src_negs is not None and kind != DOT and b.edge_cols == 3
+    dev = emb.device
+    df, Fd = _check_filter(dst_filter)
+    sf, Fs = _check_filter(src_filter)
+    ranks = torch.empty(Bp, dtype=torch.int64, device=dev)
+    pos = torch.empty(Bp, dtype=torch.float32, device=dev)
+    inv_ranks = torch.empty(Bp, dtype=torch.int64, device=dev) if inverse else None
+    inv_pos = torch.empty(Bp, dtype=torch.float32, device=dev) if inverse else None
+    check(lib.mb_evaluate_batch(ctx.handle, C.byref(b), _ptr(emb), _rowmajor(emb, "node_embeddings"), int(precision), _ptr(df), Fd, _ptr(sf), Fs,
+                                _ptr(ranks), _ptr(inv_ranks), _ptr(pos), _ptr(inv_pos), _stream()))
+    return ranks, inv_ranks, pos, inv_pos
+
+
+def ranking_metrics(ranks: torch.Tensor, ks=(1, 3, 10)) -> dict:
+    """MeanRankMetric / MeanReciprocalRankMetric / HitskMetric (reporting.cpp:17-31) on a rank vector."""
+    out = {"mean_rank": float(ranks.to(torch.float64).mean().item()), "mrr": float(ranks.to(torch.float32).reciprocal().mean().item())}
+    for k in ks:
+        out[f"hits@{k}"] = float((ranks <= k).sum().item()) / ranks.size(0)
+    return out
+
+
 def train_batch(ctx: Context, kind: int, emb, state, edges, rel, inv_rel, dst_negs, src_negs, lr: float, reduction: int = REDUCTION_SUM,
                 precision: int = PREC_BF16X3, want_grad: bool = True):
     """Model::train_batch (model.cpp:290-333) on batch-local tensors.  Returns a dict: loss, grad, delta_e, delta_s, rel_grad, inv_rel_grad."""

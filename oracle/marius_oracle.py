@@ -172,6 +172,45 @@ def node_corrupt_forward(kind, emb, edges, rel, inv_rel, dst_negs, src_negs, acc
 
 
 # ----------------------------------------------------------------------------------------------
+# evaluation: score filter, ranks, ranking metrics                         
+# ----------------------------------------------------------------------------------------------
+def apply_score_filter(scores: np.ndarray, filt: Optional[np.ndarray]) -> np.ndarray:
+    """apply_score_filter (data/samplers/negative.cpp:306-311): ``scores[filter[:,0], filter[:,1]] = -1e9`` in place
+    (called on the negative scores of each side by Model::forward_lp, nn/model.cpp:279-285)."""
+    if filt is not None and filt.shape[0] > 0:
+        scores[filt[:, 0], filt[:, 1]] = F32(-1e9)
+    return scores
+
+
+def compute_ranks(pos: np.ndarray, neg: np.ndarray) -> np.ndarray:
+    """LinkPredictionReporter::computeRanks (reporting/reporting.cpp:56-58): ``(neg >= pos.unsqueeze(1)).sum(1) + 1`` as int64.
+    Padding rows (pos = 0, all-zero scores) get rank N + 1, exactly as in the reference."""
+    return (neg >= pos[:, None]).sum(axis=1).astype(np.int64) + 1
+
+
+def ranking_metrics(ranks: np.ndarray, ks=(1, 3, 10)) -> dict:
+    """MeanRankMetric / MeanReciprocalRankMetric / HitskMetric (reporting/reporting.cpp:17-31): mean rank in float64, MRR as the
+    float32 mean of float32 reciprocals, Hits@k = #(rank <= k) / n in float64."""
+    out = {"mean_rank": float(ranks.astype(np.float64).mean()), "mrr": float((F32(1.0) / ranks.astype(F32)).mean(dtype=F32))}
+    for k in ks:
+        out[f"hits@{k}"] = float((ranks <= k).sum()) / ranks.shape[0]
+    return out
+
+
+def evaluate_batch(kind, emb, edges, rel, inv_rel, dst_negs, src_negs, dst_filter=None, src_filter=None, acc=F32):
+    """Model::evaluate_batch (nn/model.cpp:335-349): forward_lp with the batch's filters applied, then one computeRanks per side
+    (the reporter receives the dst-corruption ranks first, then the src-corruption ranks).  Returns (ranks, inv_ranks or None, Scores)."""
+    sc = node_corrupt_forward(kind, emb, edges, rel, inv_rel, dst_negs, src_negs, acc)
+    apply_score_filter(sc.neg, dst_filter)
+    ranks = compute_ranks(sc.pos, sc.neg)
+    inv_ranks = None
+    if sc.inv_neg is not None:
+        apply_score_filter(sc.inv_neg, src_filter)
+        inv_ranks = compute_ranks(sc.inv_pos, sc.inv_neg)
+    return ranks, inv_ranks, sc
+
+
+# ----------------------------------------------------------------------------------------------
 # loss                                                                     (a11)
 # ----------------------------------------------------------------------------------------------
 def softmax_ce(pos: np.ndarray, neg: np.ndarray, reduction: int, acc=F32):

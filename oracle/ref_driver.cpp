@@ -32,6 +32,7 @@
 #include "nn/layers/embedding/embedding.h"
 #include "nn/loss.h"
 #include "nn/model.h"
+#include "reporting/reporting.h"
 #include "storage/buffer.h"
 #include "storage/storage.h"
 
@@ -225,6 +226,64 @@ int ref_train_batch(int decoder_type, int d, int num_rel, const float *rel, cons
         copy_out(delta_s, batch->node_state_update_);
         copy_out(rel_grad, decoder->relations_.grad());
         if (inverse) copy_out(inv_rel_grad, decoder->inverse_relations_.grad());
+        return 0;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return 1;
+    }
+}
+
+// Model::evaluate_batch (model.cpp:335-349) on batch-local tensors: forward_lp with the batch's score filters
+// (model.cpp:279-285 -> negative.cpp:306-311) and LinkPredictionReporter::addResult -> computeRanks
+// (reporting.cpp:56-72) once per corruption side.  dst_filter / src_filter: [F,2] int64 (row, column) pairs or NULL.
+// Outputs: ranks / inv_ranks [Bp] int64 in the order the reporter collects them; neg / inv_neg [Bp,N] the filtered scores (may be NULL).
+int ref_evaluate_batch(int decoder_type, int d, int num_rel, const float *rel, const float *inv_rel, const float *emb, int64_t U, const int64_t *edges,
+                       int64_t B, const int64_t *dst_negs, const int64_t *src_negs, int C, int N, const int64_t *dst_filter, int64_t Fd,
+                       const int64_t *src_filter, int64_t Fs, int64_t *ranks, int64_t *inv_ranks, float *pos, float *neg, float *inv_pos, float *inv_neg) {
+    try {
+        bool inverse = (inv_rel != nullptr) && (src_negs != nullptr);
+        auto model = make_model(decoder_type, d, num_rel, inverse, 1, rel, inv_rel);
+        auto reporter = std::make_shared<LinkPredictionReporter>();
+        model->reporter_ = reporter;
+        auto batch = std::make_shared<Batch>(false);
+        batch->node_embeddings_ = f32(emb, {U, (int64_t)d}).clone();
+        batch->edges_ = i64(edges, {B, 3}).clone();
+        batch->dst_neg_indices_mapping_ = i64(dst_negs, {C, N}).clone();
+        if (inverse) batch->src_neg_indices_mapping_ = i64(src_negs, {C, N}).clone();
+        if (dst_filter && Fd > 0) batch->dst_neg_filter_ = i64(dst_filter, {Fd, 2}).clone();
+        if (inverse && src_filter && Fs > 0) batch->src_neg_filter_ = i64(src_filter, {Fs, 2}).clone();
+        torch::NoGradGuard ng;
+        model->evaluate_batch(batch);
+        if (reporter->per_batch_ranks_.size() != (inverse ? 2u : 1u)) throw std::runtime_error("unexpected number of rank tensors");
+        torch::Tensor r0 = reporter->per_batch_ranks_[0].to(torch::kInt64).contiguous();
+        std::memcpy(ranks, r0.data_ptr<int64_t>(), sizeof(int64_t) * r0.numel());
+        if (inverse) {
+            torch::Tensor r1 = reporter->per_batch_ranks_[1].to(torch::kInt64).contiguous();
+            std::memcpy(inv_ranks, r1.data_ptr<int64_t>(), sizeof(int64_t) * r1.numel());
+        }
+        if (pos || neg || inv_pos || inv_neg) {
+            auto scores = model->forward_lp(batch, false);
+            copy_out(pos, std::get<0>(scores));
+            copy_out(neg, std::get<1>(scores));
+            copy_out(inv_pos, std::get<2>(scores));
+            copy_out(inv_neg, std::get<3>(scores));
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return 1;
+    }
+}
+
+// RankingMetric::computeMetric (reporting.cpp:17-31) on a rank vector: out = {mean rank, MRR, Hits@1, Hits@3, Hits@10}
+int ref_ranking_metrics(const int64_t *ranks, int64_t n, double *out) {
+    try {
+        torch::Tensor r = i64(ranks, {n}).clone();
+        out[0] = MeanRankMetric().computeMetric(r).item<double>();
+        out[1] = MeanReciprocalRankMetric().computeMetric(r).item<double>();
+        out[2] = HitskMetric(1).computeMetric(r).item<double>();
+        out[3] = HitskMetric(3).computeMetric(r).item<double>();
+        out[4] = HitskMetric(10).computeMetric(r).item<double>();
         return 0;
     } catch (const std::exception &e) {
         g_last_error = e.what();

@@ -60,6 +60,9 @@ def lib():
         _lib.ref_train_loop.argtypes = [C.c_int, C.c_int, C.c_int, _F, _F, C.c_int64, C.c_int, _I, _I, _I, C.c_int64, _I, _I, C.c_int, C.c_int,
                                         C.c_float, C.c_int, C.c_int]
         _lib.ref_train_loop.restype = C.c_double
+        _lib.ref_evaluate_batch.argtypes = [C.c_int, C.c_int, C.c_int, _F, _F, _F, C.c_int64, _I, C.c_int64, _I, _I, C.c_int, C.c_int, _I, C.c_int64, _I,
+                                            C.c_int64, _I, _I, _F, _F, _F, _F]
+        _lib.ref_ranking_metrics.argtypes = [_I, C.c_int64, C.POINTER(C.c_double)]
     return _lib
 
 
@@ -150,3 +153,32 @@ def train_loop(kind, d, num_rel, table, state_table, uniq, uniq_off, edges, dst_
     if t < 0:
         raise RuntimeError(lib().ref_last_error().decode())
     return t
+
+
+def evaluate_batch(kind, emb, edges, rel, inv_rel, dst_negs, src_negs, dst_filter=None, src_filter=None):
+    """Runs the reference Model::evaluate_batch (forward_lp + score filters + LinkPredictionReporter::computeRanks)."""
+    U, d = emb.shape
+    B = edges.shape[0]
+    Cc, N = dst_negs.shape
+    Bp = Cc * int(np.ceil(B / Cc))
+    inverse = inv_rel is not None and src_negs is not None
+    out = dict(ranks=np.zeros(Bp, np.int64), pos=np.zeros(Bp, np.float32), neg=np.zeros((Bp, N), np.float32))
+    if inverse:
+        out.update(inv_ranks=np.zeros(Bp, np.int64), inv_pos=np.zeros(Bp, np.float32), inv_neg=np.zeros((Bp, N), np.float32))
+    df = np.ascontiguousarray(dst_filter, dtype=np.int64) if dst_filter is not None else None
+    sf = np.ascontiguousarray(src_filter, dtype=np.int64) if src_filter is not None else None
+    rc = lib().ref_evaluate_batch(_KIND_TO_DRIVER[kind], d, rel.shape[0], _fp(rel), _fp(inv_rel) if inverse else None, _fp(emb), U, _ip(edges), B,
+                                  _ip(dst_negs), _ip(src_negs) if inverse else None, Cc, N, _ip(df), 0 if df is None else df.shape[0], _ip(sf),
+                                  0 if sf is None else sf.shape[0], _ip(out["ranks"]), _ip(out.get("inv_ranks")), _fp(out["pos"]), _fp(out["neg"]),
+                                  _fp(out.get("inv_pos")), _fp(out.get("inv_neg")))
+    if rc:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return out
+
+
+def ranking_metrics(ranks: np.ndarray) -> dict:
+    out = (C.c_double * 5)()
+    r = np.ascontiguousarray(ranks, dtype=np.int64)
+    if lib().ref_ranking_metrics(_ip(r), r.shape[0], out):
+        raise RuntimeError(lib().ref_last_error().decode())
+    return {"mean_rank": out[0], "mrr": out[1], "hits@1": out[2], "hits@3": out[3], "hits@10": out[4]}

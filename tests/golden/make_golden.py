@@ -4,7 +4,7 @@ Run in the build container (needs /root/reference):   make -C oracle && python t
 Every array in tests/golden/*.npz is an input to, or an output of, the reference C++ itself
 (oracle/_ref/libmarius_ref.so = the reference's TUs compiled in place + oracle/ref_driver.cpp):
   InMemory::indexRead/indexAdd, PartitionBuffer::{indexRead,indexAdd,getGlobalToLocalMap,getNextAdmit,getNextEvict},
-  map_tensors, Model::forward_lp, Model::train_batch.
+  map_tensors, Model::forward_lp, Model::train_batch, Model::evaluate_batch (+ LinkPredictionReporter::computeRanks, ranking metrics).
 The fixtures travel to the GPU box; /root/reference does not.
 """
 import os
@@ -33,6 +33,37 @@ def train_case(name, kind, B, C, N, d, num_nodes, num_rel, reduction, seed, lr=0
     np.savez_compressed(os.path.join(OUT, name + ".npz"), kind=kind, B=B, C=C, N=N, d=d, lr=np.float32(lr), reduction=reduction, uniq=uniq, edges=edges,
                         dst_negs=dn, src_negs=sn, emb=emb, state=state, rel=rel, inv_rel=inv_rel, **{"ref_" + k: v for k, v in ref.items()})
     print(name, "U", U)
+
+
+def eval_case(name, kind, B, C, N, d, num_nodes, num_rel, seed, n_filter, all_nodes=False, emb_scale=0.5):
+    """Model::evaluate_batch: scores -> score filters -> ranks.  all_nodes: the filtered-evaluation shape (negative.cpp:321-325,355:
+    one chunk whose negatives are every node, arange(num_nodes))."""
+    rng = np.random.default_rng(seed)
+    if all_nodes:
+        U, C, N = num_nodes, 1, num_nodes
+        edges = np.stack([rng.integers(0, U, B), rng.integers(0, num_rel, B), rng.integers(0, U, B)], axis=1).astype(np.int64)
+        dn = np.arange(U, dtype=np.int64).reshape(1, U)
+        sn = dn.copy()
+    else:
+        uniq, edges, dn, sn = O.make_batch(rng, num_nodes, num_rel, B, C, N)
+        U = len(uniq)
+    emb = rng.uniform(-emb_scale, emb_scale, (U, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (num_rel, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (num_rel, d)).astype(np.float32)
+    Bp = C * int(np.ceil(B / C))
+    mk = lambda: np.unique(np.stack([rng.integers(0, Bp, n_filter), rng.integers(0, N, n_filter)], axis=1).astype(np.int64), axis=0)
+    dst_filter, src_filter = (mk(), mk()) if n_filter > 0 else (None, None)
+    if all_nodes:  # the true destination / source of every edge is always filtered (it is among the negatives)
+        dst_filter = np.unique(np.concatenate([dst_filter, np.stack([np.arange(B), edges[:, 2]], axis=1)]), axis=0)
+        src_filter = np.unique(np.concatenate([src_filter, np.stack([np.arange(B), edges[:, 0]], axis=1)]), axis=0)
+    ref = R.evaluate_batch(kind, emb, edges, rel, inv_rel, dn, sn, dst_filter, src_filter)
+    metrics = R.ranking_metrics(np.concatenate([ref["ranks"], ref["inv_ranks"]]))
+    empty = np.zeros((0, 2), np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind=kind, B=B, C=C, N=N, d=d, edges=edges, dst_negs=dn, src_negs=sn, emb=emb, rel=rel,
+                        inv_rel=inv_rel, dst_filter=empty if dst_filter is None else dst_filter, src_filter=empty if src_filter is None else src_filter,
+                        metrics=np.array([metrics[k] for k in ("mean_rank", "mrr", "hits@1", "hits@3", "hits@10")]),
+                        **{"ref_" + k: v for k, v in ref.items()})
+    print(name, "U", U, metrics)
 
 
 def storage_case():
@@ -80,4 +111,7 @@ if __name__ == "__main__":
     train_case("train_distmult_mean", O.DISTMULT, 64, 2, 32, 16, 300, 5, O.REDUCTION_MEAN, 3)
     train_case("train_complex_mid", O.COMPLEX, 96, 3, 64, 48, 2000, 7, O.REDUCTION_SUM, 4)
     train_case("train_distmult_dup", O.DISTMULT, 128, 4, 64, 32, 60, 4, O.REDUCTION_SUM, 5)   # heavy id collisions
+    eval_case("eval_distmult_pad", O.DISTMULT, 7, 3, 5, 8, 40, 3, 21, 0)                      # padded rows get rank N + 1
+    eval_case("eval_complex_filter", O.COMPLEX, 96, 2, 64, 32, 500, 7, 22, 200)               # sampled negatives + score filters
+    eval_case("eval_distmult_all", O.DISTMULT, 50, 1, 0, 16, 120, 5, 23, 60, all_nodes=True)  # filtered evaluation against all nodes
     train_case("train_complex_d100", O.COMPLEX, 200, 2, 100, 100, 14541, 237, O.REDUCTION_SUM, 6, emb_scale=0.1)  # FB15k-237-sized

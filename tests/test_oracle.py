@@ -150,3 +150,45 @@ def test_against_reference_library(kind):
     table = rng.standard_normal((300, 12)).astype(np.float32)
     idx = rng.integers(0, 300, 64, dtype=np.int64)
     assert np.array_equal(O.index_read(table, idx), R.index_read(table, idx))
+
+
+# ---- (4) evaluation path: score filter, ranks, ranking metrics -----------------
+EVAL_CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "eval_*.npz")))
+
+
+def ranks_match_up_to_ties(ranks, ref_ranks, pos, neg, tol=1e-5):
+    """Ranks are integers: two implementations whose scores differ in the last bits may only disagree on a row by the number of
+    negatives that tie with the positive within `tol` (relative to the largest score)."""
+    scale = max(float(np.abs(neg[neg > -1e8]).max()), 1e-12)
+    near = (np.abs(neg - pos[:, None]) <= tol * scale).sum(axis=1)
+    return bool(np.all(np.abs(ranks - ref_ranks) <= near))
+
+
+def test_eval_known_answers():
+    # reporting.cpp:56-58 on a hand-checked case: ties count against the positive (>=), rank is 1-based
+    pos = np.array([1.0, 0.5, -2.0], np.float32)
+    neg = np.array([[0.9, 1.0, 1.1, -5.0], [0.4, 0.3, 0.2, 0.1], [0.0, 0.0, 0.0, 0.0]], np.float32)
+    assert O.compute_ranks(pos, neg).tolist() == [3, 1, 5]
+    # negative.cpp:306-311: filtered entries become -1e9 and so never outrank the positive
+    f = np.array([[0, 2], [0, 1], [2, 0]], np.int64)
+    assert O.compute_ranks(pos, O.apply_score_filter(neg.copy(), f)).tolist() == [1, 1, 4]
+    m = O.ranking_metrics(np.array([1, 2, 4, 10, 11], np.int64))
+    assert m["mean_rank"] == pytest.approx(5.6) and m["hits@1"] == 0.2 and m["hits@3"] == 0.4 and m["hits@10"] == 0.8
+    assert m["mrr"] == pytest.approx((1 + 0.5 + 0.25 + 0.1 + 1 / 11) / 5, rel=1e-6)
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_golden_evaluate_batch(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name))
+    ranks, inv_ranks, sc = O.evaluate_batch(int(g["kind"]), g["emb"], g["edges"], g["rel"], g["inv_rel"], g["dst_negs"], g["src_negs"], g["dst_filter"],
+                                            g["src_filter"])
+    assert rel_err(sc.neg, g["ref_neg"]) < 2e-5 and rel_err(sc.inv_neg, g["ref_inv_neg"]) < 2e-5
+    # the rank rule itself is exact on the reference's own scores
+    assert np.array_equal(O.compute_ranks(g["ref_pos"], g["ref_neg"]), g["ref_ranks"])
+    assert np.array_equal(O.compute_ranks(g["ref_inv_pos"], g["ref_inv_neg"]), g["ref_inv_ranks"])
+    assert ranks_match_up_to_ties(ranks, g["ref_ranks"], g["ref_pos"], g["ref_neg"])
+    assert ranks_match_up_to_ties(inv_ranks, g["ref_inv_ranks"], g["ref_inv_pos"], g["ref_inv_neg"])
+    m = O.ranking_metrics(np.concatenate([g["ref_ranks"], g["ref_inv_ranks"]]))
+    ref_m = g["metrics"]
+    assert m["mean_rank"] == pytest.approx(ref_m[0], rel=1e-12) and m["mrr"] == pytest.approx(ref_m[1], rel=1e-6)
+    assert (m["hits@1"], m["hits@3"], m["hits@10"]) == (ref_m[2], ref_m[3], ref_m[4])
