@@ -214,3 +214,95 @@ float Model::train_batch_fused(shared_ptr<Batch> batch, InMemory& embeddings, In
     if (call_step) step();
     return loss.item<float>();
 }
+
+// ---- reporting (reporting/reporting.cpp) -----------------------------------------------------------------------------------------
+HitskMetric::HitskMetric(int k) : k_(k) {
+    name_ = "Hits@" + std::to_string(k);
+    unit_ = "";
+}
+torch::Tensor HitskMetric::computeMetric(torch::Tensor ranks) {  // reporting.cpp:17
+    return torch::tensor((double)ranks.le(k_).nonzero().size(0) / ranks.size(0), torch::kFloat64);
+}
+MeanRankMetric::MeanRankMetric() {
+    name_ = "Mean Rank";
+    unit_ = "";
+}
+torch::Tensor MeanRankMetric::computeMetric(torch::Tensor ranks) { return ranks.to(torch::kFloat64).mean(); }  // reporting.cpp:24
+MeanReciprocalRankMetric::MeanReciprocalRankMetric() {
+    name_ = "MRR";
+    unit_ = "";
+}
+torch::Tensor MeanReciprocalRankMetric::computeMetric(torch::Tensor ranks) { return ranks.to(torch::kFloat32).reciprocal().mean(); }  // reporting.cpp:31
+
+void LinkPredictionReporter::clear() {
+    all_ranks_ = torch::Tensor();
+    all_scores_ = torch::Tensor();
+    per_batch_ranks_ = {};
+    per_batch_scores_ = {};
+    per_batch_edges_ = {};
+}
+
+torch::Tensor LinkPredictionReporter::computeRanks(torch::Tensor pos_scores, torch::Tensor neg_scores) {
+    // reporting.cpp:56-58  (neg_scores >= pos_scores.unsqueeze(1)).sum(1) + 1
+    if (!pos_scores.defined() || !neg_scores.defined()) throw UndefinedTensorException();
+    if (pos_scores.dim() != 1 || neg_scores.dim() != 2 || pos_scores.size(0) != neg_scores.size(0)) throw TensorSizeMismatchException(neg_scores, "computeRanks");
+    torch::Tensor pos = pos_scores.to(torch::kFloat32).contiguous();
+    torch::Tensor neg = neg_scores.to(torch::kFloat32);
+    if (neg.stride(1) != 1) neg = neg.contiguous();
+    torch::Tensor ranks = torch::empty({pos.size(0)}, torch::TensorOptions().dtype(torch::kInt64).device(pos.device()));
+    mb_throw_on_error(mb_compute_ranks(pos.data_ptr<float>(), neg.data_ptr<float>(), neg.size(0), neg.size(1), neg.size(0) > 1 ? neg.stride(0) : neg.size(1),
+                                       ranks.data_ptr<int64_t>(), mb_current_stream(pos.device())));
+    return ranks;
+}
+
+void LinkPredictionReporter::addResult(torch::Tensor pos_scores, torch::Tensor neg_scores, torch::Tensor edges) {
+    std::lock_guard<std::mutex> guard(lock_);
+    if (neg_scores.defined()) per_batch_ranks_.emplace_back(computeRanks(pos_scores, neg_scores));
+    if (edges.defined()) {
+        per_batch_scores_.emplace_back(pos_scores.to(torch::kCPU));
+        per_batch_edges_.emplace_back(edges.to(torch::kCPU));
+    }
+}
+
+void LinkPredictionReporter::addRanks(torch::Tensor ranks) {
+    std::lock_guard<std::mutex> guard(lock_);
+    per_batch_ranks_.emplace_back(ranks);
+}
+
+string LinkPredictionReporter::report() {  // reporting.cpp:74-95 (returns the text instead of logging it through spdlog)
+    all_ranks_ = torch::cat(per_batch_ranks_).to(torch::kCPU);
+    if (!per_batch_scores_.empty()) all_scores_ = torch::cat(per_batch_scores_);
+    per_batch_ranks_ = {};
+    per_batch_scores_ = {};
+    string out = "\n=================================\nLink Prediction: " + std::to_string(all_ranks_.size(0)) + " edges evaluated\n";
+    for (auto& m : metrics_) out += m->name_ + ": " + std::to_string(m->computeMetric(all_ranks_).item<double>()) + m->unit_ + "\n";
+    return out + "=================================";
+}
+
+void Model::evaluate_batch(shared_ptr<Batch> batch) {  // model.cpp:335-349
+    if (reporter_ == nullptr) throw UnexpectedNullPtrException("reporter_");
+    if (decoder_->decoder_method_ != EdgeDecoderMethod::CORRUPT_NODE || !batch->dst_neg_indices_mapping_.defined()) {
+        // the reference's generic route: forward_lp, then addResult per side that has negative scores
+        auto scores = forward_lp(batch, true);
+        if (std::get<1>(scores).defined()) reporter_->addResult(std::get<0>(scores), std::get<1>(scores));
+        if (std::get<3>(scores).defined()) reporter_->addResult(std::get<2>(scores), std::get<3>(scores));
+        return;
+    }
+    torch::NoGradGuard ng;
+    if (!batch->node_embeddings_.defined()) throw UndefinedTensorException();
+    torch::Tensor emb = batch->node_embeddings_.detach().contiguous();
+    torch::Tensor edges, dn, sn;
+    mb_batch mbb = describe(*this, *batch, emb.size(0), emb.size(1), edges, dn, sn);
+    const int64_t Bc = (mbb.B + mbb.C - 1) / mbb.C, Bp = Bc * mbb.C;
+    const bool inverse = mbb.src_negs != nullptr;
+    auto iopt = torch::TensorOptions().dtype(torch::kInt64).device(emb.device());
+    torch::Tensor ranks = torch::empty({Bp}, iopt), inv_ranks = inverse ? torch::empty({Bp}, iopt) : torch::Tensor();
+    torch::Tensor df = batch->dst_neg_filter_.defined() ? batch->dst_neg_filter_.to(torch::kInt64).contiguous() : torch::Tensor();
+    torch::Tensor sf = (inverse && batch->src_neg_filter_.defined()) ? batch->src_neg_filter_.to(torch::kInt64).contiguous() : torch::Tensor();
+    mb_throw_on_error(mb_evaluate_batch(mb_context_for(emb.device()), &mbb, emb.data_ptr<float>(), emb.stride(0), mb_default_precision(),
+                                        df.defined() ? df.data_ptr<int64_t>() : nullptr, df.defined() ? df.size(0) : 0,
+                                        sf.defined() ? sf.data_ptr<int64_t>() : nullptr, sf.defined() ? sf.size(0) : 0, ranks.data_ptr<int64_t>(),
+                                        inverse ? inv_ranks.data_ptr<int64_t>() : nullptr, nullptr, nullptr, mb_current_stream(emb.device())));
+    reporter_->addRanks(ranks);
+    if (inverse) reporter_->addRanks(inv_ranks);
+}

@@ -135,6 +135,23 @@ PYBIND11_MODULE(_host, m) {
         .def("embeddingsToHost", &Batch::embeddingsToHost)
         .def("clear", &Batch::clear);
 
+    // reporting_wrap.cpp
+    py::class_<RankingMetric, shared_ptr<RankingMetric>>(m, "RankingMetric")
+        .def_readwrite("name", &RankingMetric::name_)
+        .def("compute_metric", &RankingMetric::computeMetric, py::arg("ranks"));
+    py::class_<HitskMetric, RankingMetric, shared_ptr<HitskMetric>>(m, "Hitsk").def(py::init<int>(), py::arg("k"));
+    py::class_<MeanRankMetric, RankingMetric, shared_ptr<MeanRankMetric>>(m, "MeanRank").def(py::init<>());
+    py::class_<MeanReciprocalRankMetric, RankingMetric, shared_ptr<MeanReciprocalRankMetric>>(m, "MeanReciprocalRank").def(py::init<>());
+    py::class_<LinkPredictionReporter, shared_ptr<LinkPredictionReporter>>(m, "LinkPredictionReporter")
+        .def(py::init<>())
+        .def_readwrite("per_batch_ranks", &LinkPredictionReporter::per_batch_ranks_)
+        .def_readwrite("all_ranks", &LinkPredictionReporter::all_ranks_)
+        .def("add_metric", &LinkPredictionReporter::addMetric, py::arg("metric"))
+        .def("clear", &LinkPredictionReporter::clear)
+        .def("compute_ranks", &LinkPredictionReporter::computeRanks, py::arg("pos_scores"), py::arg("neg_scores"))
+        .def("add_result", &LinkPredictionReporter::addResult, py::arg("pos_scores"), py::arg("neg_scores"), py::arg("edges") = torch::Tensor())
+        .def("report", &LinkPredictionReporter::report);
+
     // model_wrap.cpp
     py::class_<Model, shared_ptr<Model>>(m, "Model")
         .def(py::init([](shared_ptr<EdgeDecoder> decoder, shared_ptr<LossFunction> loss, torch::Device device) {
@@ -148,6 +165,8 @@ PYBIND11_MODULE(_host, m) {
         .def("forward_lp", &Model::forward_lp, py::arg("batch"), py::arg("train"))
         .def("train_batch", &Model::train_batch, py::arg("batch"), py::arg("call_step") = true)
         .def("train_batch_fused", &Model::train_batch_fused, py::arg("batch"), py::arg("embeddings"), py::arg("state"), py::arg("call_step") = true)
+        .def_readwrite("reporter", &Model::reporter_)
+        .def("evaluate_batch", &Model::evaluate_batch, py::arg("batch"))
         .def("clear_grad", &Model::clear_grad)
         .def("step", &Model::step)
         .def("parameters", [](Model& mdl) { return mdl.parameters(); });

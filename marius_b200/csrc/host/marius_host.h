@@ -13,6 +13,7 @@
 //   nn/model.h          Model                        Model (forward_lp / train_batch / evaluate-side scores)
 // Error conventions follow common/exception.h:12-42 (all derive std::runtime_error).
 #pragma once
+#include <mutex>
 
 #include <torch/extension.h>
 
@@ -255,6 +256,53 @@ class Batch {
     void clear();
 };
 
+// ---- reporting -------------------------------------------------------------------------------------------------
+/** reporting/reporting.h:20-58: ranking metrics over the collected rank vector */
+class RankingMetric {
+   public:
+    string name_;
+    string unit_;
+    virtual ~RankingMetric() {}
+    virtual torch::Tensor computeMetric(torch::Tensor ranks) = 0;
+};
+class HitskMetric : public RankingMetric {
+   public:
+    int k_;
+    explicit HitskMetric(int k);
+    torch::Tensor computeMetric(torch::Tensor ranks) override;
+};
+class MeanRankMetric : public RankingMetric {
+   public:
+    MeanRankMetric();
+    torch::Tensor computeMetric(torch::Tensor ranks) override;
+};
+class MeanReciprocalRankMetric : public RankingMetric {
+   public:
+    MeanReciprocalRankMetric();
+    torch::Tensor computeMetric(torch::Tensor ranks) override;
+};
+
+/** reporting/reporting.h:76-100 / reporting.cpp:44-95: ranks are computed on the device by mb_compute_ranks and stay there until report() */
+class LinkPredictionReporter {
+   public:
+    std::vector<shared_ptr<RankingMetric>> metrics_;
+    std::vector<torch::Tensor> per_batch_ranks_;
+    std::vector<torch::Tensor> per_batch_scores_;
+    std::vector<torch::Tensor> per_batch_edges_;
+    torch::Tensor all_ranks_;
+    torch::Tensor all_scores_;
+    std::mutex lock_;
+
+    void addMetric(shared_ptr<RankingMetric> metric) { metrics_.emplace_back(metric); }
+    void clear();
+    torch::Tensor computeRanks(torch::Tensor pos_scores, torch::Tensor neg_scores);
+    void addResult(torch::Tensor pos_scores, torch::Tensor neg_scores, torch::Tensor edges = torch::Tensor());
+    /** adds rank vectors computed elsewhere (Model::evaluate_batch's fused scores -> filter -> ranks call) */
+    void addRanks(torch::Tensor ranks);
+    /** concatenates the collected ranks into all_ranks_ (CPU) and returns "name: value" lines in the reference's format */
+    string report();
+};
+
 // ---- model -----------------------------------------------------------------------------------------------------
 /** nn/model.h:16-63, link-prediction path with a pure-embedding encoder (EmbeddingLayer::forward is a view, embedding.cpp:17) */
 class Model : public torch::nn::Module {
@@ -272,6 +320,9 @@ class Model : public torch::nn::Module {
     void train_batch(shared_ptr<Batch> batch, bool call_step = true);
     /** train_batch + DataLoader::updateEmbeddings(batch, gpu=true) fused on device-resident tables (pipeline_gpu.cpp:49-91) */
     float train_batch_fused(shared_ptr<Batch> batch, InMemory& embeddings, InMemory& state, bool call_step = true);
+    /** nn/model.cpp:335-349: scores (+ the batch's score filters) -> ranks of both corruption sides, handed to reporter_ */
+    shared_ptr<LinkPredictionReporter> reporter_;
+    void evaluate_batch(shared_ptr<Batch> batch);
     void clear_grad();
     void step();
 };

@@ -29,11 +29,13 @@ Storage, InMemory, PartitionBuffer = _host.Storage, _host.InMemory, _host.Partit
 EdgeDecoder, DistMult, ComplEx = _host.EdgeDecoder, _host.DistMult, _host.ComplEx
 Batch, Model, LossFunction, SoftmaxCrossEntropy = _host.Batch, _host.Model, _host.LossFunction, _host.SoftmaxCrossEntropy
 node_corrupt_forward, only_pos_forward = _host.node_corrupt_forward, _host.only_pos_forward
+LinkPredictionReporter, Hitsk, MeanRank, MeanReciprocalRank = _host.LinkPredictionReporter, _host.Hitsk, _host.MeanRank, _host.MeanReciprocalRank
 MariusRuntimeException = _host.MariusRuntimeException
 set_default_precision, default_precision = _host.set_default_precision, _host.default_precision
 
 storage = SimpleNamespace(Storage=Storage, InMemory=InMemory, PartitionBuffer=PartitionBuffer)
 data = SimpleNamespace(Batch=Batch)
+report = SimpleNamespace(LinkPredictionReporter=LinkPredictionReporter, Hitsk=Hitsk, MeanRank=MeanRank, MeanReciprocalRank=MeanReciprocalRank)
 nn = SimpleNamespace(Model=Model, SoftmaxCrossEntropy=SoftmaxCrossEntropy, LossFunction=LossFunction,
                      decoders=SimpleNamespace(edge=SimpleNamespace(DistMult=DistMult, ComplEx=ComplEx, EdgeDecoder=EdgeDecoder,
                                                                    node_corrupt_forward=node_corrupt_forward, only_pos_forward=only_pos_forward)))

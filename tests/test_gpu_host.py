@@ -262,3 +262,56 @@ def test_train_batch_fused_on_device_tables(host):
     got = emb_st.data.cpu().numpy()
     assert np.abs(got - table).max() / np.abs(table).max() < 1e-4
     assert np.abs(state_st.data.cpu().numpy() - state).max() / max(np.abs(state).max(), 1e-6) < 1e-4
+
+
+# ---- evaluation: Model::evaluate_batch + LinkPredictionReporter (model.cpp:335-349, reporting.cpp:44-95) --------------------------
+@pytest.mark.parametrize("name", ["eval_distmult_pad.npz", "eval_complex_filter.npz", "eval_distmult_all.npz"])
+def test_evaluate_batch_reporter(host, name):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    kind, d, R = int(g["kind"]), int(g["d"]), g["rel"].shape[0]
+    cls = host.nn.decoders.edge.DistMult if kind == O.DISTMULT else host.nn.decoders.edge.ComplEx
+    dec = cls(num_relations=R, embedding_dim=d, use_inverse_relations=True, device=CUDA, mode="train")
+    with torch.no_grad():
+        dec.relations.copy_(torch.from_numpy(g["rel"]))
+        dec.inverse_relations.copy_(torch.from_numpy(g["inv_rel"]))
+    model = host.nn.Model(dec, host.nn.SoftmaxCrossEntropy(reduction="sum"), CUDA)
+    rep = host.report.LinkPredictionReporter()
+    for m in (host.report.MeanRank(), host.report.MeanReciprocalRank(), host.report.Hitsk(1), host.report.Hitsk(3), host.report.Hitsk(10)):
+        rep.add_metric(m)
+    model.reporter = rep
+    batch = host.data.Batch(False)
+    batch.node_embeddings = torch.from_numpy(g["emb"]).to(CUDA)
+    batch.edges = torch.from_numpy(g["edges"]).to(CUDA)
+    batch.dst_neg_indices_mapping = torch.from_numpy(g["dst_negs"]).to(CUDA)
+    batch.src_neg_indices_mapping = torch.from_numpy(g["src_negs"]).to(CUDA)
+    if g["dst_filter"].shape[0]:
+        batch.dst_neg_filter = torch.from_numpy(g["dst_filter"]).to(CUDA)
+        batch.src_neg_filter = torch.from_numpy(g["src_filter"]).to(CUDA)
+    model.evaluate_batch(batch)
+    assert len(rep.per_batch_ranks) == 2  # dst-corruption ranks first, then src-corruption ranks (model.cpp:343-348)
+    ranks, inv_ranks = rep.per_batch_ranks[0].cpu().numpy(), rep.per_batch_ranks[1].cpu().numpy()
+    # the generic route of the adapter (forward_lp -> add_result -> compute_ranks) gives the same integers
+    pos, neg, inv_pos, inv_neg = model.forward_lp(batch, True)
+    assert np.array_equal(rep.compute_ranks(pos, neg).cpu().numpy(), ranks) and np.array_equal(rep.compute_ranks(inv_pos, inv_neg).cpu().numpy(), inv_ranks)
+    assert np.array_equal(ranks, O.compute_ranks(pos.detach().cpu().numpy(), neg.detach().cpu().numpy()))
+
+    def close(r, ref, p, n):  # equal to the reference's ranks up to near-ties
+        scale = np.abs(n[n > -1e8]).max()
+        return bool(np.all(np.abs(r - ref) <= (np.abs(n - p[:, None]) <= 2e-4 * scale).sum(axis=1)))
+
+    assert close(ranks, g["ref_ranks"], g["ref_pos"], g["ref_neg"]) and close(inv_ranks, g["ref_inv_ranks"], g["ref_inv_pos"], g["ref_inv_neg"])
+    text = rep.report()
+    assert f"Link Prediction: {2 * len(ranks)} edges evaluated" in text and "MRR: " in text and "Hits@10: " in text
+    assert rep.all_ranks.device.type == "cpu" and rep.all_ranks.numel() == 2 * len(ranks) and len(rep.per_batch_ranks) == 0
+    mrr = float(text.split("MRR: ")[1].split("\n")[0])
+    assert mrr == pytest.approx(float(g["metrics"][1]), rel=0.02)
+
+
+def test_evaluate_batch_needs_reporter(host):
+    model = get_test_model_lp(host, mode="train")
+    batch = host.data.Batch(False)
+    batch.node_embeddings = node_embeddings.to(CUDA)
+    batch.edges = batch_edges.to(CUDA)
+    batch.dst_neg_indices_mapping = torch.tensor([[2, 0], [0, 1], [1, 0]]).to(CUDA)
+    with pytest.raises(RuntimeError):
+        model.evaluate_batch(batch)
