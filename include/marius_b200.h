@@ -106,6 +106,22 @@ mb_status mb_adagrad_update_rows(float* table, float* state_table, int64_t num_r
 mb_status mb_map_tensors(mb_context* ctx, const int64_t* all_ids, int64_t n, int64_t max_id, int64_t* unique_out, int64_t* mapped_out,
                          int64_t* num_unique_dev, void* stream);
 
+/* ---- batch assembly ----------------------------------------------------------------------------------------
+ * mb_sample_negatives  CorruptNodeNegativeSampler::getNegatives (data/samplers/negative.cpp:328-366): out [C,N] int64 (device).  Per
+ *   chunk the first (int)(N * degree_fraction) ids are an endpoint of a random edge of the batch (batch_sample, negative.cpp:7-19:
+ *   the source column when inverse != 0, else the destination column), the rest are uniform in [0, num_nodes).  The ids are a pure
+ *   function of (seed, batch_index, inverse, position): Philox4x32-10, restated by oracle/marius_oracle.py::sample_negatives -- the
+ *   reference's own stream (libtorch's global generator) is not reproducible on a device, see DESIGN.md.
+ * mb_edge_sample  DataLoader::edgeSample without a neighbour sampler (data/dataloader.cpp:389-471): all_ids = cat(src, dst,
+ *   src_negs, dst_negs) -> map_tensors -> unique_out (sorted unique global ids, entries past *num_unique_dev are -1; capacity
+ *   2B + CN (+ CN)), edges_local [B,cols] = (mapped src, rel, mapped dst), src_negs_local / dst_negs_local [C,N].  src_negs may be NULL
+ *   (no inverse side).  Bit-identical to the reference for the same global ids. */
+mb_status mb_sample_negatives(int64_t num_nodes, int C, int N, float degree_fraction, const int64_t* edges, int64_t B, int edge_cols, int inverse,
+                              uint64_t seed, uint32_t batch_index, int64_t* out, void* stream);
+mb_status mb_edge_sample(mb_context* ctx, const int64_t* edges, int64_t B, int edge_cols, const int64_t* src_negs, const int64_t* dst_negs, int C, int N,
+                         int64_t max_id, int64_t* unique_out, int64_t* edges_local, int64_t* src_negs_local, int64_t* dst_negs_local,
+                         int64_t* num_unique_dev, void* stream);
+
 /* mb_reduce_rows_by_key: rows_out[u,:] = sum of rows[i,:] over all i with ids[i] == unique_out[u]; unique_out sorted ascending,
  * *num_unique (device).  The owner-side merge of the multi-GPU row exchange: gradient rows for the same table
  * row arriving from different ranks are summed (fixed order, no atomics) before the Adagrad update.  unique_out and rows_out hold n

@@ -42,6 +42,8 @@ _SIGS = {
     "mb_adagrad_deltas": [_vp, _vp, _i64, _i64, _i64, _f, _vp, _vp, _vp],
     "mb_adagrad_update_rows": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _f, _vp],
     "mb_map_tensors": [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
+    "mb_sample_negatives": [_i64, _i32, _i32, _f, _vp, _i64, _i32, _i32, C.c_uint64, C.c_uint32, _vp, _vp],
+    "mb_edge_sample": [_vp, _vp, _i64, _i32, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp],
     "mb_reduce_rows_by_key": [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     "mb_decoder_forward": [_vp, C.POINTER(mb_batch), _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp],
     "mb_apply_score_filter": [_vp, _i64, _i64, _i64, _vp, _i64, _vp],

@@ -800,6 +800,57 @@ mb_status mb_map_tensors(mb_context* ctx, const int64_t* all_ids, int64_t n, int
     return map_tensors_device(all_ids, n, bits_for((uint64_t)max_id), ka, kb, va, vb, flags, hist, total, unique_out, mapped_out, num_unique_dev, st);
 }
 
+mb_status mb_sample_negatives(int64_t num_nodes, int C, int N, float degree_fraction, const int64_t* edges, int64_t B, int edge_cols, int inverse,
+                              uint64_t seed, uint32_t batch_index, int64_t* out, void* stream) {
+    MB_REQUIRE(num_nodes > 0 && C >= 0 && N >= 0, "bad dimensions");
+    MB_REQUIRE(degree_fraction >= 0.f && degree_fraction <= 1.f, "degree_fraction must be in [0, 1]");
+    MB_REQUIRE((int64_t)C * N == 0 || out != nullptr, "out is null");
+    const int num_batch = (int)(N * degree_fraction);  // negative.cpp:334
+    if (num_batch > 0) {
+        MB_REQUIRE(edges != nullptr && B > 0, "degree-based negatives need the batch's edges");
+        MB_REQUIRE(edge_cols == 2 || edge_cols == 3, "Edge list must be a 3 or 2 column tensor");
+    }
+    return launch_sample_negatives(num_nodes, C, N, num_batch, edges, B, edge_cols, inverse != 0, seed, batch_index, out, (cudaStream_t)stream);
+}
+
+mb_status mb_edge_sample(mb_context* ctx, const int64_t* edges, int64_t B, int edge_cols, const int64_t* src_negs, const int64_t* dst_negs, int C, int N,
+                         int64_t max_id, int64_t* unique_out, int64_t* edges_local, int64_t* src_negs_local, int64_t* dst_negs_local,
+                         int64_t* num_unique_dev, void* stream) {
+    MB_REQUIRE(ctx != nullptr && B >= 0 && C >= 0 && N >= 0 && max_id >= 0, "bad arguments");
+    MB_REQUIRE(edge_cols == 2 || edge_cols == 3, "Edge list must be a 3 or 2 column tensor");  // dataloader.cpp:463-469
+    const int64_t CN = (int64_t)C * N, n_s = src_negs ? CN : 0, n = 2 * B + n_s + CN;
+    MB_REQUIRE(num_unique_dev != nullptr, "num_unique_dev is null");
+    MB_REQUIRE(B == 0 || (edges && edges_local), "null edges");
+    MB_REQUIRE(CN == 0 || (dst_negs && dst_negs_local), "null dst_negs");
+    MB_REQUIRE(n_s == 0 || src_negs_local != nullptr, "null src_negs_local");
+    MB_REQUIRE(n == 0 || unique_out != nullptr, "null unique_out");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t *ka, *kb;
+    uint32_t *va, *vb, *flags, *hist, *total;
+    int64_t *all_ids, *mapped;
+    auto lay = [&](Arena& ar) {
+        all_ids = ar.take<int64_t>(n);
+        mapped = ar.take<int64_t>(n);
+        ka = ar.take<uint64_t>(n);
+        kb = ar.take<uint64_t>(n);
+        va = ar.take<uint32_t>(n);
+        vb = ar.take<uint32_t>(n);
+        flags = ar.take<uint32_t>(n + 1);
+        hist = reinterpret_cast<uint32_t*>(ar.take<char>(sort_scratch_bytes(n)));
+        total = ar.take<uint32_t>(1);
+    };
+    Arena sizing(nullptr);
+    lay(sizing);
+    MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+    Arena place(ctx->ws);
+    lay(place);
+    MB_TRY(launch_concat_ids(edges, B, edge_cols, src_negs, dst_negs, CN, all_ids, st));
+    MB_TRY(map_tensors_device(all_ids, n, bits_for((uint64_t)max_id), ka, kb, va, vb, flags, hist, total, unique_out, mapped, num_unique_dev, st));
+    MB_TRY(launch_split_mapped(mapped, edges, B, edge_cols, src_negs != nullptr, CN, edges_local, src_negs_local, dst_negs_local, st));
+    return MB_OK;
+}
+
 mb_status mb_reduce_rows_by_key(mb_context* ctx, const int64_t* ids, const float* rows, int64_t n, int64_t d, int64_t max_id, int64_t* unique_out,
                                 float* rows_out, int64_t* num_unique_dev, void* stream) {
     MB_REQUIRE(ctx != nullptr && n >= 0 && d > 0 && max_id >= 0, "bad arguments");

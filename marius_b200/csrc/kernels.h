@@ -58,6 +58,14 @@ mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, co
 mb_status launch_rel_reduce(const float* drel0, const float* drel1, float* out0, float* out1, const uint32_t* slots, const uint32_t* offsets, int64_t R,
                             int d, cudaStream_t st);
 
+// sample_kernels.cu
+mb_status launch_sample_negatives(int64_t num_nodes, int C, int N, int num_batch, const int64_t* edges, int64_t B, int cols, bool inverse, uint64_t seed,
+                                  uint32_t batch, int64_t* out, cudaStream_t st);
+mb_status launch_concat_ids(const int64_t* edges, int64_t B, int cols, const int64_t* src_negs, const int64_t* dst_negs, int64_t CN, int64_t* all_ids,
+                            cudaStream_t st);
+mb_status launch_split_mapped(const int64_t* mapped, const int64_t* edges, int64_t B, int cols, bool has_src_negs, int64_t CN, int64_t* edges_local,
+                              int64_t* src_negs_local, int64_t* dst_negs_local, cudaStream_t st);
+
 // eval_kernels.cu
 mb_status launch_score_filter(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, int* bad_flag, cudaStream_t st);
 mb_status launch_ranks(const float* pos, const float* neg, int64_t rows, int64_t N, int64_t ld, int64_t* ranks, cudaStream_t st);

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kThreads) gather_rows_kernel(const float* __re
             ocol[u] = it.col;
             if (ok[u]) {
                 int64_t src = __ldg(idx + it.row);
-                val[u] = vload(reinterpret_cast<const V*>(table + src * ld) + it.col);
+                // a negative id is padding (mb_edge_sample / mb_reduce_rows_by_key fill unused capacity with -1): reads as a zero row
+                val[u] = src >= 0 ? vload(reinterpret_cast<const V*>(table + src * ld) + it.col) : V{};
             }
             it.next();
         }

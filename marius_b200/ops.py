@@ -206,6 +206,42 @@ def map_tensors(ctx: Context, all_ids: torch.Tensor, max_id: Optional[int] = Non
     return uniq[: int(cnt.item())], mapped
 
 
+def sample_negatives(num_nodes: int, C_: int, N: int, seed: int, batch_index: int, inverse: bool, device, degree_fraction: float = 0.0,
+                     edges: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """CorruptNodeNegativeSampler::getNegatives (negative.cpp:328-366) on the device: [C, N] int64 ids, a pure function of
+    (seed, batch_index, inverse, position)."""
+    _need_cuda(edges)
+    out = torch.empty((C_, N), dtype=torch.int64, device=device)
+    B, cols = (edges.size(0), edges.size(1)) if edges is not None else (0, 3)
+    if edges is not None:
+        edges = edges.contiguous()
+    check(lib.mb_sample_negatives(int(num_nodes), int(C_), int(N), float(degree_fraction), _ptr(edges), B, cols, int(bool(inverse)), int(seed),
+                                  int(batch_index), _ptr(out), _stream()))
+    return out
+
+
+def edge_sample(ctx: Context, edges: torch.Tensor, src_negs: Optional[torch.Tensor], dst_negs: torch.Tensor, max_id: int):
+    """DataLoader::edgeSample (dataloader.cpp:389-471) on the device: global edges / negatives -> (unique ids padded with -1 to
+    capacity, num_unique [1] int64 device, local edges, local src_negs or None, local dst_negs)."""
+    _need_cuda(edges, src_negs, dst_negs)
+    if edges.dim() != 2 or edges.size(1) not in (2, 3):
+        raise MariusB200Error(_INVALID, "Edge list must be a 3 or 2 column tensor")
+    edges, dst_negs = edges.contiguous(), dst_negs.contiguous()
+    src_negs = src_negs.contiguous() if src_negs is not None else None
+    B, cols = edges.shape
+    Cc, N = dst_negs.shape
+    n = 2 * B + Cc * N * (2 if src_negs is not None else 1)
+    dev = edges.device
+    uniq = torch.empty(n, dtype=torch.int64, device=dev)
+    num = torch.zeros(1, dtype=torch.int64, device=dev)
+    e_loc = torch.empty_like(edges)
+    s_loc = torch.empty_like(src_negs) if src_negs is not None else None
+    d_loc = torch.empty_like(dst_negs)
+    check(lib.mb_edge_sample(ctx.handle, _ptr(edges), B, cols, _ptr(src_negs), _ptr(dst_negs), Cc, N, int(max_id), _ptr(uniq), _ptr(e_loc), _ptr(s_loc),
+                             _ptr(d_loc), _ptr(num), _stream()))
+    return uniq, num, e_loc, s_loc, d_loc
+
+
 def reduce_rows_by_key(ctx: Context, ids: torch.Tensor, rows: torch.Tensor, max_id: Optional[int] = None, padded: bool = False):
     """(sorted unique ids, per-id sum of rows): the owner-side merge of gradient rows received from several ranks.
     padded=True returns the full-length buffers (unique ids padded with -1, zero rows) without any host synchronisation."""

@@ -172,6 +172,59 @@ def node_corrupt_forward(kind, emb, edges, rel, inv_rel, dst_negs, src_negs, acc
 
 
 # ----------------------------------------------------------------------------------------------
+# batch assembly: negative sampling + edgeSample                           
+# ----------------------------------------------------------------------------------------------
+def philox4x32_10_u64(seed: int, index: np.ndarray, stream: int, batch: int) -> np.ndarray:
+    """Philox4x32-10 (Salmon et al., SC'11; the generator cuRAND / libtorch CUDA use): key = seed, counter = (index lo, index hi,
+    stream, batch); returns the first two output words as one uint64 per index.  This is the definition of the device sampler's
+    stream (marius_b200/csrc/sample_kernels.cu), restated with numpy integer arithmetic."""
+    M0, M1, W0, W1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    idx = index.astype(np.uint64)
+    c0, c1 = idx & MASK, idx >> np.uint64(32)
+    c2 = np.full_like(c0, np.uint64(stream))
+    c3 = np.full_like(c0, np.uint64(batch))
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2  # 32x32 -> 64-bit products
+        c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ k0, p1 & MASK, (p0 >> np.uint64(32)) ^ c3 ^ k1, p0 & MASK
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c0 | (c1 << np.uint64(32))
+
+
+def sample_negatives(num_nodes: int, C: int, N: int, seed: int, batch_index: int, inverse: bool, degree_fraction: float = 0.0,
+                     edges: Optional[np.ndarray] = None) -> np.ndarray:
+    """CorruptNodeNegativeSampler::getNegatives (data/samplers/negative.cpp:328-366): per chunk, ``(int)(N * degree_fraction)``
+    endpoints of random batch edges (batch_sample, negative.cpp:7-19: source column when ``inverse``, else destination) followed by
+    uniform ids in [0, num_nodes) -- ``random % range`` like libtorch's randint, with Philox instead of libtorch's generator."""
+    num_batch = int(np.float32(N) * np.float32(degree_fraction))
+    r = philox4x32_10_u64(seed, np.arange(C * N, dtype=np.uint64), 1 if inverse else 0, batch_index)
+    j = np.arange(C * N) % max(N, 1)
+    out = (r % np.uint64(num_nodes)).astype(np.int64)
+    if num_batch > 0:
+        col = 0 if inverse else edges.shape[1] - 1
+        deg = edges[(r % np.uint64(edges.shape[0])).astype(np.int64), col]
+        out = np.where(j < num_batch, deg, out)
+    return out.reshape(C, N)
+
+
+def edge_sample(edges: np.ndarray, src_negs: Optional[np.ndarray], dst_negs: np.ndarray):
+    """DataLoader::edgeSample without a neighbour sampler (data/dataloader.cpp:389-471): map_tensors over
+    cat(src, dst, src_negs, dst_negs), edges rewritten to (mapped src, rel, mapped dst), negatives keep their [C,N] shape.
+    Returns (unique ids, local edges, local src_negs or None, local dst_negs)."""
+    B = edges.shape[0]
+    parts = [edges[:, 0], edges[:, -1]] + ([src_negs.reshape(-1)] if src_negs is not None else []) + [dst_negs.reshape(-1)]
+    uniq, mapped = map_tensors(np.concatenate(parts))
+    local = edges.copy()
+    local[:, 0], local[:, -1] = mapped[:B], mapped[B:2 * B]
+    off = 2 * B
+    s_loc = None
+    if src_negs is not None:
+        s_loc = mapped[off:off + src_negs.size].reshape(src_negs.shape)
+        off += src_negs.size
+    return uniq, local, s_loc, mapped[off:].reshape(dst_negs.shape)
+
+
+# ----------------------------------------------------------------------------------------------
 # evaluation: score filter, ranks, ranking metrics                         (SURVEY 8f row 3)
 # ----------------------------------------------------------------------------------------------
 def apply_score_filter(scores: np.ndarray, filt: Optional[np.ndarray]) -> np.ndarray:

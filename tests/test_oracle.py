@@ -192,3 +192,49 @@ def test_golden_evaluate_batch(golden_dir, name):
     ref_m = g["metrics"]
     assert m["mean_rank"] == pytest.approx(ref_m[0], rel=1e-12) and m["mrr"] == pytest.approx(ref_m[1], rel=1e-6)
     assert (m["hits@1"], m["hits@3"], m["hits@10"]) == (ref_m[2], ref_m[3], ref_m[4])
+
+
+# ---- (5) batch assembly: negative sampling + edgeSample ---------------------------
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10 (first two output words); counter = (index lo, index hi, stream, batch), key = seed
+    kat = [((0, 0, 0, 0), 0xE169C58D6627E8D5), ((0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF), 0x41C83B0E408F276D),
+           ((0x299F31D0A4093822, 0x85A308D3243F6A88, 0x13198A2E, 0x03707344), 0x94FDCCEBD16CFE09)]
+    for (seed, index, stream, batch), want in kat:
+        assert int(O.philox4x32_10_u64(seed, np.array([index], dtype=np.uint64), stream, batch)[0]) == want
+
+
+def test_sample_negatives_contract():
+    # shapes / ranges of negative.cpp:328-366 and test/python/bindings/integration/test_data.py:108-162
+    neg = O.sample_negatives(1000, 4, 250, seed=3, batch_index=0, inverse=False)
+    assert neg.shape == (4, 250) and neg.dtype == np.int64 and neg.min() >= 0 and neg.max() < 1000
+    assert not np.array_equal(neg, O.sample_negatives(1000, 4, 250, seed=3, batch_index=1, inverse=False))      # a new batch draws new ids
+    assert not np.array_equal(neg, O.sample_negatives(1000, 4, 250, seed=3, batch_index=0, inverse=True))       # the two sides are independent
+    assert np.array_equal(neg, O.sample_negatives(1000, 4, 250, seed=3, batch_index=0, inverse=False))          # stateless
+    big = O.sample_negatives(50, 1, 200000, seed=9, batch_index=0, inverse=False).reshape(-1)
+    counts = np.bincount(big, minlength=50)
+    chi2 = float(((counts - 4000.0) ** 2 / 4000.0).sum())
+    assert chi2 < 100  # 49 degrees of freedom: p(chi2 > 100) ~ 2e-5
+    # degree-based fraction: the first (int)(N * f) ids of every chunk are endpoints of batch edges (negative.cpp:7-19,334,347)
+    rng = np.random.default_rng(0)
+    edges = np.stack([rng.integers(5000, 5010, 64), rng.integers(0, 3, 64), rng.integers(7000, 7010, 64)], axis=1).astype(np.int64)
+    d = O.sample_negatives(1000, 3, 100, seed=1, batch_index=2, inverse=False, degree_fraction=0.5, edges=edges)
+    assert np.all((d[:, :50] >= 7000) & (d[:, :50] < 7010)) and np.all(d[:, 50:] < 1000)
+    s = O.sample_negatives(1000, 3, 100, seed=1, batch_index=2, inverse=True, degree_fraction=0.25, edges=edges)
+    assert np.all((s[:, :25] >= 5000) & (s[:, :25] < 5010)) and np.all(s[:, 25:] < 1000)
+
+
+def test_edge_sample_matches_map_tensors_golden(golden_dir):
+    # edgeSample = map_tensors over cat(src, dst, src_negs, dst_negs) (dataloader.cpp:398-461); map_tensors is pinned by the golden
+    rng = np.random.default_rng(4)
+    edges = np.stack([rng.integers(0, 300, 40), rng.integers(0, 5, 40), rng.integers(0, 300, 40)], axis=1).astype(np.int64)
+    sn, dn = rng.integers(0, 300, (2, 30)).astype(np.int64), rng.integers(0, 300, (2, 30)).astype(np.int64)
+    uniq, local, s_loc, d_loc = O.edge_sample(edges, sn, dn)
+    assert np.array_equal(uniq, np.unique(np.concatenate([edges[:, 0], edges[:, 2], sn.reshape(-1), dn.reshape(-1)])))
+    assert np.array_equal(uniq[local[:, 0]], edges[:, 0]) and np.array_equal(uniq[local[:, 2]], edges[:, 2]) and np.array_equal(local[:, 1], edges[:, 1])
+    assert np.array_equal(uniq[s_loc], sn) and np.array_equal(uniq[d_loc], dn)
+    if R.available():
+        all_ids = np.concatenate([edges[:, 0], edges[:, 2], sn.reshape(-1), dn.reshape(-1)])
+        ru, rm = R.map_tensors(all_ids)
+        assert np.array_equal(ru, uniq) and np.array_equal(rm[:40], local[:, 0]) and np.array_equal(rm[80:140].reshape(2, 30), s_loc)
+    u2, l2, s2, d2 = O.edge_sample(edges[:, [0, 2]], None, dn)  # 2-column edges, no inverse side
+    assert s2 is None and l2.shape == (40, 2) and np.array_equal(u2[d2], dn)
