@@ -301,9 +301,14 @@ def run_ours(args):
         torch.cuda.synchronize()
     loss = torch.zeros(1, device=dev)
 
+    dense_calls = [0]
+
     def dense_step():
-        # Model::step(): the reference's dense Adagrad on the relation tables (optim.cpp:114-145), all-reduced across ranks
-        if world > 1:
+        # Model::step(): the reference's dense Adagrad on the relation tables (optim.cpp:114-145), every batch on every rank.  The relation
+        # gradients are all-reduced across ranks every `gpu_sync_interval` batches, the reference's own cadence (pipeline_gpu.cpp:52-78,
+        # default 16: marius_config.py:674); between syncs the replicas of the (small, dense) relation tables drift exactly as they do there.
+        dense_calls[0] += 1
+        if world > 1 and dense_calls[0] % args.gpu_sync_interval == 0:
             dist.all_reduce(rel_grads)
         ops.dense_adagrad_step(rels, rel_states, rel_grads, LR)
 
@@ -434,10 +439,10 @@ def run_ours(args):
                                 precision=args.precision,
                                 parallelism=(f"table sharded by node partition over {world} GPUs; per batch: src + negatives local, dst uniform over all "
                                              f"partitions (~{(world - 1) / world * 25:.0f}% of a batch's rows are remote); "
-                                             + ("remote rows read and Adagrad-updated over NVLink-mapped peer memory (CUDA IPC) inside the fused step"
+                                             + ("remote rows fetched once per step over NVLink-mapped peer memory (CUDA IPC), their Adagrad deltas added at the owner with red.global.sys.add.v4.f32"
                                                 if peer is not None else
                                                 f"rows / gradient rows exchanged by grouped NCCL send/recv, remote rows/step/rank {np.mean(remote_rows) if remote_rows else 0:.0f}")
-                                             + "; relation grads all-reduced (NCCL)") if world > 1 else "single GPU, fused gather+score+update step",
+                                             + f"; relation grads all-reduced (NCCL) every {args.gpu_sync_interval} batches (reference gpu_sync_interval)") if world > 1 else "single GPU, fused gather+score+update step",
                                 l2="inputs larger than L2: every step gathers/updates a fresh uniform-random row set of a table >> 126 MB",
                                 unique_rows_per_step=U_mean, step_hbm_gbs_algorithmic=step_hbm, step_hbm_frac=step_hbm / pk["hbm_gbs"],
                                 stage_ms={k: round(v, 4) for k, v in per_stage.items()}, stage_sum_ms=step_stage_ms, last_loss=last_loss),
@@ -464,6 +469,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0, help="batch of the CPU reference arm (0 = --batch)")
     ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-sync-interval", type=int, default=16,
+                    help="N > 1: all-reduce the dense relation gradients every this many batches (the reference's gpu_sync_interval, default 16)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = remote rows read / updated over NVLink-mapped peer memory inside the fused step; "
                          "'nccl' = rows and gradient rows exchanged with grouped NCCL send/recv (marius_b200/dist.py ShardedTable)")

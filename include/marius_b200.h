@@ -204,15 +204,18 @@ mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, fl
  * replicas-plus-shared-host-table scheme, nn/model.cpp:136-159, pipeline/pipeline_gpu.cpp:23).  Rank o owns global rows
  * [o * rows_per_rank, (o+1) * rows_per_rank); tables[o] / states[o] are the owners' base pointers as seen from THIS process: its
  * own allocation for o == rank, CUDA-IPC mappings of the peers' allocations otherwise (peer access over NVLink enabled).
- * `unique_ids` are GLOBAL row ids.  The kernels of mb_train_step read remote rows with plain loads and apply the Adagrad
- * read-modify-write to remote rows with plain stores: the only cross-GPU traffic is the rows a batch needs, and there is no
- * staging buffer or collective on the row path.  Rows touched concurrently by two ranks follow the reference's unlocked
+ * `unique_ids` are GLOBAL row ids.  Remote rows are fetched once per step into a batch-local cache by a copy kernel that keeps many
+ * rows per SM in flight (NVLink latency is ~5x HBM latency), the decoder kernels then read local memory only; the update reads the
+ * owner's Adagrad state row and applies delta_e / delta_s with fire-and-forget vector reductions (red.global.sys.add.v4.f32) at the
+ * owner's HBM -- exactly the reference's indexAdd of both deltas.  The only cross-GPU traffic is the rows a batch needs: one row
+ * in (embedding) + one row in (state) + two rows out per remote row, and there is no collective on the row path.  Rows touched concurrently by two ranks follow the reference's unlocked
  * (bounded-staleness) update semantics (storage/buffer.cpp:459).  Up to 8 shards. */
 typedef struct mb_shards {
     float* tables[8];
     float* states[8];
     int world;
     int64_t rows_per_rank;
+    int rank; /* which shard is this process's own HBM (tables[rank] is local memory, the others are peer mappings) */
 } mb_shards;
 /* CUDA IPC plumbing for one-process-per-GPU deployments: mb_ipc_export returns the 64-byte handle of the allocation containing
  * `dev_ptr` and the offset of `dev_ptr` inside it; mb_ipc_import opens a peer's handle with the context's device current (lazy peer

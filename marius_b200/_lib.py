@@ -29,7 +29,7 @@ class mb_batch(C.Structure):
 
 
 class mb_shards(C.Structure):
-    _fields_ = [("tables", C.c_void_p * 8), ("states", C.c_void_p * 8), ("world", C.c_int), ("rows_per_rank", C.c_int64)]
+    _fields_ = [("tables", C.c_void_p * 8), ("states", C.c_void_p * 8), ("world", C.c_int), ("rows_per_rank", C.c_int64), ("rank", C.c_int)]
 
 
 _vp, _i64, _i32, _f = C.c_void_p, C.c_int64, C.c_int, C.c_float

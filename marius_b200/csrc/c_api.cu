@@ -86,6 +86,7 @@ struct mb_context {
                                           // which cannot be captured); ordered against the caller's stream with ev_in / ev_out
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_sfetch_fork = nullptr, ev_sfetch_join = nullptr, ev_efetch_join = nullptr;  // sharded step: remote state rows are fetched on side2 during the contractions
     cudaEvent_t ev_slot = nullptr;        // the node-slot plan is ready (the node update waits on this, not on the relation plan)
     // CUDA-graph replay of the fused step (mb_train_step / mb_train_step_host): one captured graph per call signature
     struct StepGraph {
@@ -201,12 +202,17 @@ struct Plan {
     bool has_rel, use_tc;
     // buffers
     float *emb_u, *A, *pos, *gpos, *row_loss, *NegE, *S, *dA, *gcat, *drel;
+    float* state_u = nullptr;          // sharded table: local copies of the remote rows' Adagrad state
+    const float** row_ptrs = nullptr;  // sharded table: address of every unique row (own HBM or the fetched copy in emb_u)
+    bool sharded = false;
     __nv_bfloat16 *A_hl, *Neg_hl, *G_hl;
     uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *offsets, *hist;
     uint32_t *rkeys_a, *rkeys_b, *rvals_a, *rvals_b, *roffsets, *rhist;
 
     void layout(Arena& ar, bool need_emb_u, bool training, bool own_scores) {
         emb_u = need_emb_u ? ar.take<float>(U * d) : nullptr;
+        row_ptrs = sharded ? ar.take<const float*>(U) : nullptr;
+        state_u = sharded ? ar.take<float>(U * d) : nullptr;
         A = ar.take<float>(sides * Bp * d);
         pos = ar.take<float>(sides * Bp);
         NegE = use_tc ? nullptr : ar.take<float>(sides * CN * d);
@@ -285,7 +291,8 @@ static mb_status tc_contract(int cfg, const void* A_hi, const void* A_lo, int64_
 
 // forward: adjusted rows A, positive scores, negative rows, score GEMM.  S0/S1 are the score outputs per side ([Bp,N] each).
 static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, const int64_t* row_map, int precision,
-                             float* pos, float* S0, float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false, const mb_shards* sh = nullptr) {
+                             float* pos, float* S0, float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false, const float* const* row_ptrs = nullptr,
+                             const mb_shards* sh = nullptr, cudaEvent_t rows_fetched = nullptr) {
     const int d = (int)p.d;
     const int64_t a_half = p.sides * p.Bp * d;  // hi block then lo block, each [sides][Bp][d]
     const int64_t n_half = p.sides * p.CN * d;
@@ -293,7 +300,7 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
         StageTimer tm(ctx, ST_PREP, st);
         // the fp32 adjusted rows are only read by the SIMT GEMM and by the scalar (general-d) backward kernel
         const bool need_A = !p.use_tc || !decoder_vec_ok(emb, emb_ld, d, p.has_rel, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.sides);
-        MB_TRY(launch_prep(sh, emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, p.CN, d, b->decoder, p.sides,
+        MB_TRY(launch_prep(sh, rows_fetched, row_ptrs, emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, p.CN, d, b->decoder, p.sides,
                            b->dst_negs, p.sides == 2 ? b->src_negs : nullptr, need_A ? p.A : nullptr, pos, p.use_tc ? (void*)p.A_hl : nullptr,
                            p.use_tc ? (void*)(p.A_hl + a_half) : nullptr, p.NegE, p.use_tc ? (void*)p.Neg_hl : nullptr,
                            p.use_tc ? (void*)(p.Neg_hl + n_half) : nullptr, st));
@@ -353,6 +360,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     Plan p;
     fill_plan_dims(p, b, precision);
     const bool fused = mode == UpdateMode::kFusedTable;
+    p.sharded = fused && sh != nullptr && sh->world > 1;
     {
         Arena sizing(nullptr);
         p.layout(sizing, fused, true, true);
@@ -376,6 +384,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
 
     const float* emb = emb_in;
     const int64_t* row_map = nullptr;
+    bool state_fetch_forked = false, emb_fetch_forked = false;
     if (fused) {
         // DataLoader::loadGPUParameters (dataloader.cpp:529-548).  With the vector kernels the gather is fused away: prep / backward read
         // table[unique_ids[local id]] directly (the table is not modified until the update at the end of the step, so this is the same
@@ -384,6 +393,32 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
             emb = table;
             emb_ld = ld;
             row_map = unique_ids;
+            if (p.sharded) {
+                // remote rows are copied once into the batch cache; prep / backward then address every row through row_ptrs
+                // Both fetches run on the second side stream: the embedding rows while the (local) negative rows are prepared, the state
+                // rows -- only needed by the update at the end of the step -- while the contractions keep the SMs busy.
+                cudaStream_t fs = (overlap && ctx->side2 != nullptr) ? ctx->side2 : st;
+                if (fs != st) {
+                    MB_CUDA_TRY(cudaEventRecord(ctx->ev_sfetch_fork, st));
+                    MB_CUDA_TRY(cudaStreamWaitEvent(fs, ctx->ev_sfetch_fork, 0));
+                }
+                {
+                    StageTimer tm(ctx, ST_GATHER, fs);
+                    MB_TRY(launch_fetch_remote_rows(sh, unique_ids, p.U, ld, d, p.emb_u, p.row_ptrs, false, fs));
+                }
+                if (fs != st) {
+                    MB_CUDA_TRY(cudaEventRecord(ctx->ev_efetch_join, fs));
+                    emb_fetch_forked = true;
+                }
+                {
+                    StageTimer tm(ctx, ST_GATHER, fs);
+                    MB_TRY(launch_fetch_remote_rows(sh, unique_ids, p.U, ld, d, p.state_u, nullptr, true, fs));
+                }
+                if (fs != st) {
+                    MB_CUDA_TRY(cudaEventRecord(ctx->ev_sfetch_join, fs));
+                    state_fetch_forked = true;
+                }
+            }
         } else if (sh != nullptr && sh->world > 1) {
             set_error("the sharded step needs the vector kernels (d % 8 == 0, 16-byte aligned tables)");
             return MB_ERR_UNSUPPORTED;
@@ -395,7 +430,8 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         }
     }
 
-    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, row_map, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr, sh));
+    MB_TRY(run_forward(ctx, p, b, emb, emb_ld, row_map, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr, p.row_ptrs, p.sharded ? sh : nullptr,
+                       emb_fetch_forked ? ctx->ev_efetch_join : nullptr));
 
     // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
     const int64_t rows = p.sides * p.Bp;
@@ -467,12 +503,13 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     }
     {
         StageTimer tm(ctx, ST_EDGE_BWD, st);
-        MB_TRY(launch_edge_bwd(sh, emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, p.sides, p.A, p.dA,
+        MB_TRY(launch_edge_bwd(p.row_ptrs, emb, emb_ld, row_map, b->edges, p.cols, b->rel, p.sides == 2 ? b->inv_rel : nullptr, p.B, p.Bp, d, b->decoder, p.sides, p.A, p.dA,
                                p.gpos, p.gcat, p.has_rel ? p.drel : nullptr, st));
     }
     // ---- join: the slot / relation plans and the negative-row gradients are needed from here on
     if (overlap) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_slot, 0));
     if (dneg_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+    if (state_fetch_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_sfetch_join, 0));
     // relation gradients (segmented sum of per-edge gradients by relation id) touch nothing the node update touches: they run on the
     // side stream next to it
     const bool rel_forked = need_rel && overlap;
@@ -491,7 +528,8 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         // node gradients: segmented sum over sorted slots (+ Adagrad)
         StageTimer tm(ctx, ST_UPDATE, st);
         if (fused) {
-            MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st));
+            MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st,
+                                     p.sharded ? p.state_u : nullptr));
         } else if (delta_e != nullptr || delta_s != nullptr) {
             MB_REQUIRE(state != nullptr && delta_e != nullptr && delta_s != nullptr, "delta_e/delta_s need state and both outputs");
             MB_TRY(launch_seg_reduce(nullptr, 1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
@@ -553,6 +591,9 @@ mb_status mb_create(int device, mb_context** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_slot, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sfetch_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sfetch_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_efetch_join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete c;
         set_error(std::string("context creation failed: ") + cudaGetErrorString(e));
@@ -592,6 +633,9 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_slot) cudaEventDestroy(ctx->ev_slot);
+    if (ctx->ev_sfetch_fork) cudaEventDestroy(ctx->ev_sfetch_fork);
+    if (ctx->ev_sfetch_join) cudaEventDestroy(ctx->ev_sfetch_join);
+    if (ctx->ev_efetch_join) cudaEventDestroy(ctx->ev_efetch_join);
     for (auto& sp : ctx->spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -1082,6 +1126,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     std::memcpy(&key.back(), &lr, sizeof(float));
     if (sh != nullptr) {
         key.push_back((uint64_t)sh->world);
+        key.push_back((uint64_t)sh->rank);
         key.push_back((uint64_t)sh->rows_per_rank);
         for (int i = 0; i < sh->world && i < 8; i++) {
             key.push_back((uint64_t)(uintptr_t)sh->tables[i]);
@@ -1181,7 +1226,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     MB_CUDA_TRY(cudaGraphLaunch(ctx->sg.exec, ctx->gstream));
     MB_CUDA_TRY(cudaEventRecord(ctx->ev_out, ctx->gstream));
     MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out, 0));
-    count_launch(29);  // kernels inside the replayed graph (mb_launch_count stays an honest kernel count)
+    count_launch(sh != nullptr && sh->world > 1 ? 31 : 29);  // kernels inside the replayed graph (mb_launch_count stays an honest kernel count)
     return MB_OK;
 }
 
@@ -1201,6 +1246,7 @@ mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, fl
 
 static mb_status check_shards(const mb_shards* sh) {
     MB_REQUIRE(sh != nullptr && sh->world >= 1 && sh->world <= 8 && sh->rows_per_rank > 0, "bad shard description");
+    MB_REQUIRE(sh->rank >= 0 && sh->rank < sh->world, "shard rank out of range");
     for (int i = 0; i < sh->world; i++) MB_REQUIRE(sh->tables[i] != nullptr && sh->states[i] != nullptr, "null shard pointer");
     return MB_OK;
 }
@@ -1213,7 +1259,7 @@ mb_status mb_train_step_sharded(mb_context* ctx, const mb_batch* batch, const mb
     MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
     MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
-    return train_step_any(ctx, batch, false, shards->tables[0], shards->states[0], ld, unique_ids, lr, reduction, precision, loss, nullptr, rel_grad,
+    return train_step_any(ctx, batch, false, shards->tables[shards->rank], shards->states[shards->rank], ld, unique_ids, lr, reduction, precision, loss, nullptr, rel_grad,
                           inv_rel_grad, (cudaStream_t)stream, shards);
 }
 
@@ -1225,7 +1271,7 @@ mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* hb, const 
     MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
     cudaStream_t st = (cudaStream_t)stream;
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
-    MB_TRY(train_step_any(ctx, hb, true, shards->tables[0], shards->states[0], ld, unique_ids_host, lr, reduction, precision, nullptr, loss_host, rel_grad,
+    MB_TRY(train_step_any(ctx, hb, true, shards->tables[shards->rank], shards->states[shards->rank], ld, unique_ids_host, lr, reduction, precision, nullptr, loss_host, rel_grad,
                           inv_rel_grad, st, shards));
     MB_CUDA_TRY(cudaStreamSynchronize(st));
     if (loss_host) *loss_host = *ctx->h_loss_pinned;

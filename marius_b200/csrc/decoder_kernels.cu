@@ -511,6 +511,7 @@ static vec::ShardPtrs make_sp(const mb_shards* sh) {
     if (sh != nullptr && sh->world > 1) {
         sp.world = sh->world;
         sp.rows_per_rank = sh->rows_per_rank;
+        sp.rank = sh->rank;
         for (int i = 0; i < sh->world && i < 8; i++) {
             sp.table[i] = sh->tables[i];
             sp.state[i] = sh->states[i];
@@ -519,7 +520,7 @@ static vec::ShardPtrs make_sp(const mb_shards* sh) {
     return sp;
 }
 
-mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float* const* row_ptrs, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                       int64_t CN, int d, int decoder, int sides, const int64_t* dst_negs, const int64_t* src_negs, float* A /*[sides][Bp][d] or null*/,
                       float* pos /*[sides][Bp]*/, void* A_hi, void* A_lo /*[sides][Bp][d] or null*/, float* Neg /*[sides][CN][d] or null*/,
                       void* Neg_hi, void* Neg_lo, cudaStream_t st) {
@@ -531,6 +532,7 @@ mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, con
         a.emb = emb;
         a.emb_ld = emb_ld;
         a.row_map = row_map;
+        a.row_ptrs = row_ptrs;
         a.sp = make_sp(sh);
         a.edges = edges;
         a.cols = cols;
@@ -554,7 +556,16 @@ mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, con
             a.Neg_hi[s] = (on && Neg_hi) ? (__nv_bfloat16*)Neg_hi + s * CN * d : nullptr;
             a.Neg_lo[s] = (on && Neg_lo) ? (__nv_bfloat16*)Neg_lo + s * CN * d : nullptr;
         }
-        // edge rows, then negative rows (two in flight per warp)
+        // negative rows first (two in flight per warp): with a sharded table they run while the remote rows are still being fetched
+        if (CN > 0) {
+            const int grid = warp_grid((sides * CN + 1) / 2);
+            if (d <= 128)
+                vec::neg_rows_kernel<1><<<grid, vec::kThreads, 0, st>>>(a);
+            else
+                vec::neg_rows_kernel<4><<<grid, vec::kThreads, 0, st>>>(a);
+            MB_LAUNCH_CHECK();
+        }
+        if (rows_fetched != nullptr) MB_CUDA_TRY(cudaStreamWaitEvent(st, rows_fetched, 0));
         if (Bp > 0) {
             const int grid = warp_grid(Bp);
             const bool small = d <= 128;  // chunks per lane: full row <= 1 (d <= 128) / 4 (d <= 512); complex half <= 1 (d <= 256) / 2
@@ -576,18 +587,10 @@ mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, con
             }
             MB_LAUNCH_CHECK();
         }
-        if (CN > 0) {
-            const int grid = warp_grid((sides * CN + 1) / 2);
-            if (d <= 128)
-                vec::neg_rows_kernel<1><<<grid, vec::kThreads, 0, st>>>(a);
-            else
-                vec::neg_rows_kernel<4><<<grid, vec::kThreads, 0, st>>>(a);
-            MB_LAUNCH_CHECK();
-        }
         return MB_OK;
     }
     // scalar fallback needs the fp32 adjusted rows and a batch-local embedding matrix
-    if (row_map != nullptr) {
+    if (row_map != nullptr || row_ptrs != nullptr) {
         set_error("launch_prep: row_map requires the vector path");
         return MB_ERR_INVALID;
     }
@@ -626,7 +629,7 @@ mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, f
     return launch_loss_grad(G, pos, gpos, row_loss, G_hi, G_lo, rows, N, w, st, ldg);
 }
 
-mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+mb_status launch_edge_bwd(const float* const* row_ptrs, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                           int d, int decoder, int sides, const float* A /*[sides][Bp][d], scalar path only*/, const float* dA, const float* gpos,
                           float* gcat, float* drel /*[sides][B][d] or null*/, cudaStream_t st) {
     if (B == 0) return MB_OK;
@@ -638,7 +641,7 @@ mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld,
         a.emb = emb;
         a.emb_ld = emb_ld;
         a.row_map = row_map;
-        a.sp = make_sp(sh);
+        a.row_ptrs = row_ptrs;
         a.edges = edges;
         a.cols = cols;
         a.rel = rel;
@@ -675,7 +678,7 @@ mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld,
         MB_LAUNCH_CHECK();
         return MB_OK;
     }
-    if (row_map != nullptr) {
+    if (row_map != nullptr || row_ptrs != nullptr) {
         set_error("launch_edge_bwd: row_map requires the vector path");
         return MB_ERR_INVALID;
     }
@@ -684,9 +687,34 @@ mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld,
                                 (drel && has_rel && sides == 2) ? drel + B * d : nullptr, st);
 }
 
+// sharded table: row_ptrs[u] for every unique row + the remote rows copied into `cache` [U,d] (see fetch_remote_rows_kernel)
+mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int64_t U, int64_t ld, int d, float* cache, const float** row_ptrs,
+                                   bool state_rows, cudaStream_t st) {
+    if (U == 0) return MB_OK;
+    if (sh == nullptr || sh->world < 1 || sh->rank < 0 || sh->rank >= sh->world || (d % 4) != 0 || d > 512 || (ld % 4) != 0 || !al16(cache)) {
+        set_error("launch_fetch_remote_rows: bad shard description / unsupported row shape");
+        return MB_ERR_INVALID;
+    }
+    vec::FetchArgs a{ids, U, make_sp(sh), ld, d, cache, row_ptrs};
+    const int grid = warp_grid(U);
+    if (state_rows) {
+        if (d <= 128)
+            vec::fetch_remote_rows_kernel<1, true><<<grid, vec::kThreads, 0, st>>>(a);
+        else
+            vec::fetch_remote_rows_kernel<4, true><<<grid, vec::kThreads, 0, st>>>(a);
+    } else {
+        if (d <= 128)
+            vec::fetch_remote_rows_kernel<1, false><<<grid, vec::kThreads, 0, st>>>(a);
+        else
+            vec::fetch_remote_rows_kernel<4, false><<<grid, vec::kThreads, 0, st>>>(a);
+    }
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
 mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                             const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                            const int64_t* ids, float lr, cudaStream_t st) {
+                            const int64_t* ids, float lr, cudaStream_t st, const float* state_cache) {
     if (n_seg == 0) return MB_OK;
     const bool vec_ok = (d % 4 == 0) && d <= 512 && al16(rows) && (!out || (al16(out) && out_ld % 4 == 0)) && (!state || (al16(state) && state_ld % 4 == 0)) &&
                         (!delta_e || (al16(delta_e) && al16(delta_s))) && (!table || (al16(table) && al16(state_table) && ld % 4 == 0));
@@ -696,7 +724,7 @@ mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, co
     }
     if (!vec_ok)
         return launch_segment_reduce(mode, rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, lr, st);
-    vec::SegVArgs a{rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, -lr, make_sp(sh)};
+    vec::SegVArgs a{rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, -lr, make_sp(sh), state_cache};
     int grid = warp_grid(n_seg);
 #define MB_SEG(MODE)                                                                      \
     if (d <= 128)                                                                         \

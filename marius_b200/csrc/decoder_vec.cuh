@@ -54,6 +54,10 @@ __device__ __forceinline__ float4 ldg4(const float* p, int v) {  // data written
     asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(reinterpret_cast<const float4*>(p) + v));
     return r;
 }
+// fire-and-forget 128-bit add at system scope (the target may be a peer GPU's HBM): one NVLink write, no read, no reply
+__device__ __forceinline__ void red_add4_sys(float4* p, const float4& v) {
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 template <typename T>
 __device__ __forceinline__ T* shfl_ptr(T* p, int src_lane) {
     return reinterpret_cast<T*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(p), src_lane));
@@ -68,12 +72,85 @@ struct ShardPtrs {
     float* state[8];
     int64_t rows_per_rank;
     int world;  // <= 1: unsharded, `emb` / `table` arguments are used directly
+    int rank;   // the shard that is this GPU's own HBM
 };
 
-__device__ __forceinline__ const float* shard_row(const ShardPtrs& sp, const float* emb, int64_t emb_ld, int64_t g) {
-    if (sp.world <= 1) return emb + g * emb_ld;
-    const int64_t o = g / sp.rows_per_rank;
-    return sp.table[o] + (g - o * sp.rows_per_rank) * emb_ld;
+// where batch-local row `id` lives: the sharded step's per-batch pointer table, the table through the unique-id map, or the batch matrix
+template <typename Args>
+__device__ __forceinline__ const float* batch_row(const Args& a, int64_t id) {
+    if (a.row_ptrs != nullptr) return reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(a.row_ptrs) + id));
+    return a.emb + (a.row_map != nullptr ? __ldg(a.row_map + id) : id) * a.emb_ld;
+}
+
+// Sharded table, start of the step: resolve every unique row of the batch to an address and fetch the remote ones.
+//   row_ptrs[u] = own HBM row                      when this rank owns global row ids[u]
+//               = cache + u * d (filled here)      otherwise: the row is copied once from the owner's HBM over NVLink
+// One copy kernel with two rows per warp in flight and nothing else in its registers keeps far more remote rows in flight per SM
+// than the decoder kernels can (NVLink round trips are several microseconds), and they then read local memory only.
+struct FetchArgs {
+    const int64_t* ids;  // [U] global row ids (negative = padding)
+    int64_t U;
+    ShardPtrs sp;
+    int64_t ld;
+    int d;
+    float* cache;            // [U, d]
+    const float** row_ptrs;  // [U]  (embedding fetch only)
+};
+
+// STATE = false: embedding rows (+ row_ptrs).  STATE = true: the Adagrad state rows of the same remote rows, fetched on a side stream
+// while the contractions run, so that the update at the end of the step reads them from local memory.
+template <int CH, bool STATE>
+__global__ void __launch_bounds__(kThreads) fetch_remote_rows_kernel(FetchArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int dv = a.d >> 2;
+    for (int64_t first = warp0; first < a.U; first += 32 * nwarps) {
+        const float* my_src = nullptr;
+        float* my_dst = nullptr;
+        {
+            const int64_t u = first + lane * nwarps;
+            if (u < a.U) {
+                const int64_t g = __ldg(a.ids + u);
+                const float* where = a.sp.table[a.sp.rank];  // padding entries point at something valid
+                if (g >= 0) {
+                    const int64_t o = g / a.sp.rows_per_rank, l = g - o * a.sp.rows_per_rank;
+                    if (o == a.sp.rank) {
+                        where = a.sp.table[o] + l * a.ld;
+                    } else {
+                        my_src = (STATE ? a.sp.state[o] : a.sp.table[o]) + l * a.ld;
+                        my_dst = a.cache + u * a.d;
+                        where = my_dst;
+                    }
+                }
+                if (!STATE) a.row_ptrs[u] = where;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, my_src != nullptr);
+        while (todo != 0) {  // remote rows of this round, two at a time
+            const int k0 = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int k1 = todo != 0 ? __ffs(todo) - 1 : k0;
+            todo &= todo - 1;  // (no-op when todo is already 0)
+            const float *r0 = shfl_ptr(my_src, k0), *r1 = shfl_ptr(my_src, k1);
+            float *w0 = shfl_ptr(my_dst, k0), *w1 = shfl_ptr(my_dst, k1);
+            float4 x0[CH], x1[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int vc = min(lane + 32 * c, dv - 1);
+                x0[c] = ldg_nc4(r0, vc);
+                x1[c] = ldg_nc4(r1, vc);
+            }
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int v = lane + 32 * c;
+                if (v < dv) {
+                    st4(w0, v, x0[c]);
+                    if (k1 != k0) st4(w1, v, x1[c]);
+                }
+            }
+        }
+    }
 }
 
 // x -> (hi, lo) bf16 with x ~= hi + lo ; 4 elements packed into two 8-byte stores
@@ -96,7 +173,9 @@ struct PrepArgs {
     const float* emb;
     int64_t emb_ld;
     const int64_t* row_map;  // null: emb is the batch-local matrix; else emb is the table and row_map = unique ids (gather fused away)
-    ShardPtrs sp;            // with row_map: where global row g lives
+    const float* const* row_ptrs;  // sharded table: address of every unique row (own HBM, or the batch's cache of fetched remote rows)
+    ShardPtrs sp;                  // sharded table: the negative-row kernel runs BESIDE the remote-row fetch, so it resolves rows through the
+                                   // owners' tables directly (negatives are drawn from the resident partitions, i.e. almost always local)
     const int64_t* edges;
     int cols;
     const float* rel;      // null: no relation operator
@@ -128,7 +207,12 @@ __global__ void __launch_bounds__(kThreads) neg_rows_kernel(PrepArgs a) {
             if (q < total) {
                 const int side = q >= a.CN ? 1 : 0;
                 const int64_t nid = __ldg((side ? a.negs[1] : a.negs[0]) + (q - (int64_t)side * a.CN));
-                mine = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + nid)) : a.emb + nid * a.emb_ld;
+                if (a.sp.world > 1) {
+                    const int64_t g = __ldg(a.row_map + nid), o = g / a.sp.rows_per_rank;
+                    mine = a.sp.table[o] + (g - o * a.sp.rows_per_rank) * a.emb_ld;
+                } else {
+                    mine = batch_row(a, nid);
+                }
             }
         }
 #pragma unroll 1
@@ -185,8 +269,8 @@ __global__ void __launch_bounds__(kThreads) edge_rows_kernel(PrepArgs a) {
             if (p < a.B) {
                 const int64_t si = __ldg(a.edges + p * a.cols), ti = __ldg(a.edges + p * a.cols + a.cols - 1);
                 if (DEC != MB_DECODER_DOT) my_rid = __ldg(a.edges + p * a.cols + 1);
-                my_src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + si)) : a.emb + si * a.emb_ld;
-                my_dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + ti)) : a.emb + ti * a.emb_ld;
+                my_src = batch_row(a, si);
+                my_dst = batch_row(a, ti);
             }
         }
 #pragma unroll 1
@@ -350,7 +434,7 @@ struct EdgeBwdVArgs {
     const float* emb;
     int64_t emb_ld;
     const int64_t* row_map;
-    ShardPtrs sp;
+    const float* const* row_ptrs;
     const int64_t* edges;
     int cols;
     const float* rel;
@@ -379,8 +463,8 @@ __global__ void __launch_bounds__(kThreads) edge_backward_kernel(EdgeBwdVArgs a)
             if (i < a.B) {
                 const int64_t si = __ldg(a.edges + i * a.cols), ti = __ldg(a.edges + i * a.cols + a.cols - 1);
                 if (DEC != MB_DECODER_DOT) my_rid = __ldg(a.edges + i * a.cols + 1);
-                my_src = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + si)) : a.emb + si * a.emb_ld;
-                my_dst = a.row_map ? shard_row(a.sp, a.emb, a.emb_ld, __ldg(a.row_map + ti)) : a.emb + ti * a.emb_ld;
+                my_src = batch_row(a, si);
+                my_dst = batch_row(a, ti);
                 my_g0 = a.gpos[0][i];
                 if (inverse) my_g1 = a.gpos[1][i];
             }
@@ -493,6 +577,7 @@ struct SegVArgs {
     const int64_t* ids;
     float neg_lr;
     ShardPtrs sp;
+    const float* state_cache;  // sharded: [n_seg, d] copies of the remote rows' Adagrad state (fetch_remote_rows_kernel<.., true>) or null
 };
 
 __device__ __forceinline__ void adagrad4(const float4& g, const float4& s, float neg_lr, float4& de, float4& ds, float4& sn) {
@@ -513,6 +598,7 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
         uint32_t my_beg = 0, my_end = 0;
         float *my_e = nullptr, *my_s = nullptr;
         const float* my_row = nullptr;
+        int my_remote = 0;
         {
             const int64_t u = first + lane * nwarps;
             if (u < a.n_seg) {
@@ -523,10 +609,11 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
                     if (a.sp.world <= 1) {
                         my_e = a.table + r * a.ld;
                         my_s = a.state_table + r * a.ld;
-                    } else {  // the owner's HBM (peer-mapped when remote): Adagrad read-modify-write straight over NVLink
+                    } else {  // the owner's HBM: peer-mapped over NVLink when the owner is another rank
                         const int64_t o = r / a.sp.rows_per_rank, lr_ = r - o * a.sp.rows_per_rank;
                         my_e = a.sp.table[o] + lr_ * a.ld;
                         my_s = a.sp.state[o] + lr_ * a.ld;
+                        my_remote = o != a.sp.rank;
                     }
                 }
                 if (my_end > my_beg) my_row = a.rows + (int64_t)__ldg(a.slots + my_beg) * d;
@@ -540,15 +627,19 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
             float* erow = shfl_ptr(my_e, k);
             float* srow = shfl_ptr(my_s, k);
             const float* row0 = shfl_ptr(my_row, k);
+            // remote row: delta_e and delta_s are ADDED at the owner with fire-and-forget reductions -- the reference's indexAdd of both
+            // deltas (dataloader.cpp:550-564) -- so only the state row crosses NVLink inbound and the embedding row is not read at all
+            const bool remote = MODE == 2 && __shfl_sync(0xffffffffu, my_remote, k) != 0;
             if (MODE == 2 && beg == end) continue;
+            const float* sread = (remote && a.state_cache != nullptr) ? a.state_cache + u * d : srow;  // remote state: the step's local copy
             float4 e[CH], s[CH], acc[CH];
             const float* g0 = row0 ? row0 : a.rows;  // empty segment (modes 0 / 1): load something valid, add nothing
 #pragma unroll
             for (int c = 0; c < CH; c++) {  // table row, state row and first gradient row: 3 * CH independent loads in flight per lane
                 const int vc = min(lane + 32 * c, dv - 1);
                 if (MODE == 2) {
-                    e[c] = ldg4(erow, vc);
-                    s[c] = ldg4(srow, vc);
+                    if (!remote) e[c] = ldg4(erow, vc);  // warp-uniform predicate, not a branch: the loads below still issue back to back
+                    s[c] = ldg4(sread, vc);
                 } else if (MODE == 1) {
                     s[c] = ldg_nc4(a.state + u * a.state_ld, vc);
                 }
@@ -579,8 +670,13 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
                 } else {
                     float4 de, ds, sn;
                     adagrad4(acc[c], s[c], a.neg_lr, de, ds, sn);
-                    st_stream(reinterpret_cast<float4*>(erow) + v, addrn4(e[c], de));
-                    st_stream(reinterpret_cast<float4*>(srow) + v, sn);
+                    if (remote) {
+                        red_add4_sys(reinterpret_cast<float4*>(erow) + v, de);
+                        red_add4_sys(reinterpret_cast<float4*>(srow) + v, ds);
+                    } else {
+                        st_stream(reinterpret_cast<float4*>(erow) + v, addrn4(e[c], de));
+                        st_stream(reinterpret_cast<float4*>(srow) + v, sn);
+                    }
                 }
             }
         }

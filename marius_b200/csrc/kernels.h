@@ -41,19 +41,21 @@ mb_status launch_slot_keys(const int64_t* edges, int cols, int64_t B, const int6
 mb_status launch_rel_keys(const int64_t* edges, int cols, int64_t B, uint32_t* keys, cudaStream_t st);
 mb_status launch_segment_reduce(int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                                 const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                                const int64_t* ids, float lr, cudaStream_t st);
+                                const int64_t* ids, float lr, cudaStream_t st, const float* state_cache = nullptr);
 
 bool decoder_vec_ok(const float* emb, int64_t emb_ld, int d, bool has_rel, const float* rel, const float* inv_rel, int sides);
-mb_status launch_prep(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float* const* row_ptrs, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                       int64_t CN, int d, int decoder, int sides, const int64_t* dst_negs, const int64_t* src_negs, float* A, float* pos, void* A_hi,
                       void* A_lo, float* Neg, void* Neg_hi, void* Neg_lo, cudaStream_t st);
 mb_status launch_loss(const float* S, float* G, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w,
                       cudaStream_t st, int64_t ldg = 0);
-mb_status launch_edge_bwd(const mb_shards* sh, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
+mb_status launch_edge_bwd(const float* const* row_ptrs, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                           int d, int decoder, int sides, const float* A, const float* dA, const float* gpos, float* gcat, float* drel, cudaStream_t st);
+mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int64_t U, int64_t ld, int d, float* cache, const float** row_ptrs,
+                                   bool state_rows, cudaStream_t st);
 mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                             const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                            const int64_t* ids, float lr, cudaStream_t st);
+                            const int64_t* ids, float lr, cudaStream_t st, const float* state_cache = nullptr);
 
 mb_status launch_rel_reduce(const float* drel0, const float* drel1, float* out0, float* out1, const uint32_t* slots, const uint32_t* offsets, int64_t R,
                             int d, cudaStream_t st);

@@ -204,7 +204,7 @@ class PeerShardedTable:
                 tptr[r] = ops.ipc_import(ctx, *ht)
                 sptr[r] = ops.ipc_import(ctx, *hs)
             dist.barrier(group=group)
-        self.shards = ops.make_shards_raw(tptr, sptr, self.rows_per_rank)
+        self.shards = ops.make_shards_raw(tptr, sptr, self.rows_per_rank, self.rank)
 
     def train_step(self, kind, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr, reduction=1, precision=None, loss=None, rel_grad=None,
                    inv_rel_grad=None):

@@ -433,8 +433,9 @@ def ipc_import(ctx: Context, handle: bytes, offset: int) -> int:
     return int(out.value)
 
 
-def make_shards_raw(table_ptrs, state_ptrs, rows_per_rank: int):
+def make_shards_raw(table_ptrs, state_ptrs, rows_per_rank: int, rank: int = 0):
     sh = mb_shards()
+    sh.rank = int(rank)
     for i, (t, s_) in enumerate(zip(table_ptrs, state_ptrs)):
         sh.tables[i] = int(t)
         sh.states[i] = int(s_)
@@ -443,7 +444,7 @@ def make_shards_raw(table_ptrs, state_ptrs, rows_per_rank: int):
     return sh
 
 
-def make_shards(tables, states, rows_per_rank: int):
+def make_shards(tables, states, rows_per_rank: int, rank: int = 0):
     """mb_shards from per-owner table / state tensors (this rank's own allocation + CUDA-IPC views of the peers')."""
     if len(tables) != len(states) or not (1 <= len(tables) <= 8):
         raise MariusB200Error(_INVALID, "1..8 shards")
@@ -456,6 +457,7 @@ def make_shards(tables, states, rows_per_rank: int):
         sh.states[i] = s_.data_ptr()
     sh.world = len(tables)
     sh.rows_per_rank = int(rows_per_rank)
+    sh.rank = int(rank)
     return sh
 
 
