@@ -236,6 +236,19 @@ mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* host_batch
 mb_status mb_train_step_host(mb_context* ctx, const mb_batch* host_batch, float* table, float* state_table, int64_t num_rows, int64_t ld,
                              const int64_t* unique_ids_host, float lr, int reduction, int precision, float* loss_host, float* rel_grad,
                              float* inv_rel_grad, void* stream);
+/* The same step without the final wait: returns once it is enqueued on `stream`; *ticket names the pinned slot the loss will land in.
+ * mb_train_step_host_wait(ticket) blocks until that step has finished and returns its loss.  The host index buffers must stay valid
+ * until then, and at most two steps may be in flight (two slots).  This is the reference's pipeline shape -- the transfer / compute
+ * stages run ahead of the consumer of the result (pipeline/pipeline_gpu.cpp:10-145) -- and lets a caller enqueue batch i+1 while the
+ * GPU still runs batch i. */
+mb_status mb_train_step_host_async(mb_context* ctx, const mb_batch* host_batch, float* table, float* state_table, int64_t num_rows, int64_t ld,
+                                   const int64_t* unique_ids_host, float lr, int reduction, int precision, float* rel_grad, float* inv_rel_grad,
+                                   int* ticket, void* stream);
+mb_status mb_train_step_sharded_host_async(mb_context* ctx, const mb_batch* host_batch, const mb_shards* shards, int64_t ld,
+                                           const int64_t* unique_ids_host, float lr, int reduction, int precision, float* rel_grad,
+                                           float* inv_rel_grad, int* ticket, void* stream);
+mb_status mb_train_step_host_wait(mb_context* ctx, int ticket, float* loss_host);
+
 
 /* AdagradOptimizer::step on a dense parameter (nn/optim.cpp:114-145): state += g*g ; p -= lr * g / (sqrt(state) + eps) */
 mb_status mb_dense_adagrad_step(float* param, float* state_sum, const float* grad, int64_t n, float lr, float eps, void* stream);

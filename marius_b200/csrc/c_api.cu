@@ -77,7 +77,10 @@ struct mb_context {
     int64_t* h_dneg = nullptr;
     int64_t* h_sneg = nullptr;
     float* h_loss = nullptr;
-    float* h_loss_pinned = nullptr;  // pinned host landing slot of the step's loss (fixed address: captured by the graph)
+    float* h_loss_pinned = nullptr;  // two pinned host landing slots of the step's loss, used alternately (mb_train_step_host_async keeps
+                                     // one step in flight while the caller reads the previous step's loss)
+    int loss_slot = 0;
+    cudaEvent_t ev_loss[2] = {nullptr, nullptr};
     size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
     std::vector<void*> ipc_mappings;      // peer shards opened with mb_ipc_import (closed in mb_destroy)
     cudaStream_t side = nullptr;          // index plans (slot / relation sorts) overlap the forward pass here
@@ -575,7 +578,9 @@ mb_status mb_create(int device, mb_context** out) {
     mb_context* c = new mb_context();
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
-    if (e == cudaSuccess) e = cudaMallocHost(&c->h_loss_pinned, sizeof(float));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_loss_pinned, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_loss[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_loss[1], cudaEventDisableTiming);
     // The index plans are chains of small kernels that must finish before the node update.  They share the GPU with grid-filling row
     // kernels and persistent contractions, so their blocks are given scheduling priority (a low-priority side stream was observed to
     // finish its 60 us of sorts 400 us late, stalling the update).
@@ -617,6 +622,8 @@ void mb_destroy(mb_context* ctx) {
     if (ctx->h_sneg) cudaFree(ctx->h_sneg);
     if (ctx->h_loss) cudaFree(ctx->h_loss);
     if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
+    for (auto& ev : ctx->ev_loss)
+        if (ev) cudaEventDestroy(ev);
     drop_graph(ctx);
     for (void* m : ctx->ipc_mappings) cudaIpcCloseMemHandle(m);
     if (ctx->g_uniq) cudaFree(ctx->g_uniq);
@@ -1114,7 +1121,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
         MB_TRY(stage_inputs());
         MB_TRY(run_train(ctx, &db, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
                          nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh));
-        if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(loss_host, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
         return MB_OK;
     }
 
@@ -1151,7 +1158,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             MB_TRY(stage_inputs());
             MB_TRY(run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr,
                              nullptr, nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh));
-            if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (loss_host) MB_CUDA_TRY(cudaMemcpyAsync(loss_host, loss_target, sizeof(float), cudaMemcpyDeviceToHost, st));
             return MB_OK;
         }
         // capture (on the context's own stream)
@@ -1168,7 +1175,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
         if (rs == MB_OK)
             rs = run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
                            nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, gs, nullptr, sh);
-        if (rs == MB_OK && loss_host && cudaMemcpyAsync(ctx->h_loss_pinned, loss_target, sizeof(float), cudaMemcpyDeviceToHost, gs) != cudaSuccess)
+        if (rs == MB_OK && loss_host && cudaMemcpyAsync(loss_host, loss_target, sizeof(float), cudaMemcpyDeviceToHost, gs) != cudaSuccess)
             rs = MB_ERR_CUDA;
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(gs, &graph);
@@ -1203,7 +1210,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             else if (dst == ctx->g_edges) ctx->sg.n_edges = nd;
             else if (dst == ctx->g_dneg) ctx->sg.n_dneg = nd;
             else if (dst == ctx->g_sneg) ctx->sg.n_sneg = nd;
-            else if (loss_host && dst == ctx->h_loss_pinned) ctx->sg.n_loss = nd;
+            else if (loss_host && dst == loss_host) ctx->sg.n_loss = nd;
         }
         if (!ctx->sg.n_uniq || !ctx->sg.n_edges || !ctx->sg.n_dneg || (has_sneg && !ctx->sg.n_sneg)) {
             cudaGraphExecDestroy(exec);
@@ -1221,6 +1228,8 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_edges, ctx->g_edges, ub->edges, sizeof(int64_t) * n_e, kind));
     MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_dneg, ctx->g_dneg, ub->dst_negs, sizeof(int64_t) * n_n, kind));
     if (has_sneg) MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_sneg, ctx->g_sneg, ub->src_negs, sizeof(int64_t) * n_n, kind));
+    if (loss_host && ctx->sg.n_loss)  // the loss lands in this call's slot
+        MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_loss, loss_host, loss_target, sizeof(float), cudaMemcpyDeviceToHost));
     MB_CUDA_TRY(cudaEventRecord(ctx->ev_in, st));
     MB_CUDA_TRY(cudaStreamWaitEvent(ctx->gstream, ctx->ev_in, 0));
     MB_CUDA_TRY(cudaGraphLaunch(ctx->sg.exec, ctx->gstream));
@@ -1263,19 +1272,46 @@ mb_status mb_train_step_sharded(mb_context* ctx, const mb_batch* batch, const mb
                           inv_rel_grad, (cudaStream_t)stream, shards);
 }
 
-mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* hb, const mb_shards* shards, int64_t ld, const int64_t* unique_ids_host, float lr,
-                                     int reduction, int precision, float* loss_host, float* rel_grad, float* inv_rel_grad, void* stream) {
+// Host-buffer steps.  Batch::to (batch.cpp:21-60): the index tensors go host -> device on the compute stream and the loss comes back into
+// one of the context's two pinned slots.  The asynchronous form returns once the step is enqueued (ticket = the slot); the caller keeps
+// the host buffers alive until mb_train_step_host_wait(ticket) has returned, and has at most two steps in flight.
+static mb_status host_step_enqueue(mb_context* ctx, const mb_batch* hb, const mb_shards* shards, float* table, float* state_table, int64_t ld,
+                                   const int64_t* unique_ids_host, float lr, int reduction, int precision, float* rel_grad, float* inv_rel_grad,
+                                   cudaStream_t st, int* ticket) {
     MB_REQUIRE(ctx != nullptr && unique_ids_host != nullptr, "null context / ids");
-    MB_TRY(check_shards(shards));
     MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
     MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
-    cudaStream_t st = (cudaStream_t)stream;
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
-    MB_TRY(train_step_any(ctx, hb, true, shards->tables[shards->rank], shards->states[shards->rank], ld, unique_ids_host, lr, reduction, precision, nullptr, loss_host, rel_grad,
+    const int slot = ctx->loss_slot;
+    MB_TRY(train_step_any(ctx, hb, true, table, state_table, ld, unique_ids_host, lr, reduction, precision, nullptr, ctx->h_loss_pinned + slot, rel_grad,
                           inv_rel_grad, st, shards));
-    MB_CUDA_TRY(cudaStreamSynchronize(st));
-    if (loss_host) *loss_host = *ctx->h_loss_pinned;
+    MB_CUDA_TRY(cudaEventRecord(ctx->ev_loss[slot], st));
+    ctx->loss_slot = slot ^ 1;
+    *ticket = slot;
     return MB_OK;
+}
+
+mb_status mb_train_step_host_wait(mb_context* ctx, int ticket, float* loss_host) {
+    MB_REQUIRE(ctx != nullptr && (ticket == 0 || ticket == 1), "bad ticket");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    MB_CUDA_TRY(cudaEventSynchronize(ctx->ev_loss[ticket]));
+    if (loss_host) *loss_host = ctx->h_loss_pinned[ticket];
+    return MB_OK;
+}
+
+mb_status mb_train_step_sharded_host_async(mb_context* ctx, const mb_batch* hb, const mb_shards* shards, int64_t ld, const int64_t* unique_ids_host,
+                                           float lr, int reduction, int precision, float* rel_grad, float* inv_rel_grad, int* ticket, void* stream) {
+    MB_REQUIRE(ticket != nullptr, "ticket is null");
+    MB_TRY(check_shards(shards));
+    return host_step_enqueue(ctx, hb, shards, shards->tables[shards->rank], shards->states[shards->rank], ld, unique_ids_host, lr, reduction, precision,
+                             rel_grad, inv_rel_grad, (cudaStream_t)stream, ticket);
+}
+
+mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* hb, const mb_shards* shards, int64_t ld, const int64_t* unique_ids_host, float lr,
+                                     int reduction, int precision, float* loss_host, float* rel_grad, float* inv_rel_grad, void* stream) {
+    int ticket = 0;
+    MB_TRY(mb_train_step_sharded_host_async(ctx, hb, shards, ld, unique_ids_host, lr, reduction, precision, rel_grad, inv_rel_grad, &ticket, stream));
+    return mb_train_step_host_wait(ctx, ticket, loss_host);
 }
 
 // Diagnostic: D[b] = A[b] . B[b] over K through the contraction kernels, fp32 in / fp32 out.
@@ -1316,23 +1352,23 @@ static mb_status grow_i64(int64_t** p, size_t* cap, size_t need) {
     return MB_OK;
 }
 
+mb_status mb_train_step_host_async(mb_context* ctx, const mb_batch* hb, float* table, float* state_table, int64_t num_rows, int64_t ld,
+                                   const int64_t* unique_ids_host, float lr, int reduction, int precision, float* rel_grad, float* inv_rel_grad,
+                                   int* ticket, void* stream) {
+    MB_REQUIRE(table != nullptr && state_table != nullptr, "null table");
+    MB_REQUIRE(ticket != nullptr, "ticket is null");
+    (void)num_rows;
+    return host_step_enqueue(ctx, hb, nullptr, table, state_table, ld, unique_ids_host, lr, reduction, precision, rel_grad, inv_rel_grad,
+                             (cudaStream_t)stream, ticket);
+}
+
 mb_status mb_train_step_host(mb_context* ctx, const mb_batch* hb, float* table, float* state_table, int64_t num_rows, int64_t ld,
                              const int64_t* unique_ids_host, float lr, int reduction, int precision, float* loss_host, float* rel_grad,
                              float* inv_rel_grad, void* stream) {
-    MB_REQUIRE(ctx != nullptr, "context is null");
-    MB_REQUIRE(table != nullptr && state_table != nullptr, "null table");
-    MB_REQUIRE(unique_ids_host != nullptr, "unique ids are null");
-    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
-    MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
-    cudaStream_t st = (cudaStream_t)stream;
-    MB_CUDA_TRY(cudaSetDevice(ctx->device));
-    // Batch::to (batch.cpp:21-60): the index tensors go host -> device on the compute stream; the loss comes back; the call returns
-    // when the step has finished (the staging buffers are then free for the next call)
-    MB_TRY(train_step_any(ctx, hb, true, table, state_table, ld, unique_ids_host, lr, reduction, precision, nullptr, loss_host, rel_grad, inv_rel_grad, st));
-    MB_CUDA_TRY(cudaStreamSynchronize(st));
-    if (loss_host) *loss_host = *ctx->h_loss_pinned;
-    (void)num_rows;
-    return MB_OK;
+    int ticket = 0;
+    MB_TRY(mb_train_step_host_async(ctx, hb, table, state_table, num_rows, ld, unique_ids_host, lr, reduction, precision, rel_grad, inv_rel_grad, &ticket,
+                                    stream));
+    return mb_train_step_host_wait(ctx, ticket, loss_host);
 }
 
 }  // extern "C"

@@ -212,6 +212,13 @@ class PeerShardedTable:
         return self.ops.train_step_sharded(self.ctx, kind, self.shards, self.ld, self.d, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr,
                                            reduction, p, loss=loss, rel_grad=rel_grad, inv_rel_grad=inv_rel_grad)
 
+    def train_step_host_async(self, kind, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, lr, reduction=1, precision=None, rel_grad=None,
+                              inv_rel_grad=None):
+        """enqueue only: returns (ticket, keep-alive); ops.train_step_host_wait(ctx, ticket) returns the loss"""
+        p = self.ops.PREC_BF16X3 if precision is None else precision
+        return self.ops.train_step_sharded_host_async(self.ctx, kind, self.shards, self.ld, self.d, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h,
+                                                      src_negs_h, lr, reduction, p, rel_grad=rel_grad, inv_rel_grad=inv_rel_grad)
+
     def train_step_host(self, kind, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, lr, reduction=1, precision=None, rel_grad=None,
                         inv_rel_grad=None) -> float:
         p = self.ops.PREC_BF16X3 if precision is None else precision

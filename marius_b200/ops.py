@@ -417,6 +417,41 @@ def train_step_host(ctx: Context, kind: int, table, state_table, unique_ids_h, e
     return float(loss.value)
 
 
+def train_step_host_async(ctx: Context, kind: int, table, state_table, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, lr: float,
+                          reduction: int = REDUCTION_SUM, precision: int = PREC_BF16X3, rel_grad=None, inv_rel_grad=None):
+    """train_step_host without the final wait: returns (ticket, keep-alive) once the step is enqueued.  Pass the ticket to
+    train_step_host_wait to get the loss; hold on to the second value (the host tensors the copies read from) until then.  At most
+    two steps may be in flight."""
+    _need_cuda(table, state_table, rel, inv_rel)
+    for t in (unique_ids_h, edges_h, dst_negs_h, src_negs_h):
+        if t is not None and t.is_cuda:
+            raise MariusB200Error(_INVALID, "train_step_host takes host index tensors")
+    b, keep = _make_batch(kind, unique_ids_h.numel(), table.size(1), edges_h, rel, inv_rel, dst_negs_h, src_negs_h, host=True)
+    uid = unique_ids_h.contiguous()
+    ticket = C.c_int(0)
+    check(lib.mb_train_step_host_async(ctx.handle, C.byref(b), _ptr(table), _ptr(state_table), table.size(0), _rowmajor(table, "table"),
+                                       C.c_void_p(uid.data_ptr()), float(lr), int(reduction), int(precision), _ptr(rel_grad), _ptr(inv_rel_grad),
+                                       C.byref(ticket), _stream()))
+    return int(ticket.value), (keep, uid)
+
+
+def train_step_host_wait(ctx: Context, ticket: int) -> float:
+    loss = C.c_float(0.0)
+    check(lib.mb_train_step_host_wait(ctx.handle, int(ticket), C.byref(loss)))
+    return float(loss.value)
+
+
+def train_step_sharded_host_async(ctx: Context, kind: int, shards, ld: int, d: int, unique_ids_h, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, lr: float,
+                                  reduction: int = REDUCTION_SUM, precision: int = PREC_BF16X3, rel_grad=None, inv_rel_grad=None):
+    _need_cuda(rel, inv_rel)
+    b, keep = _make_batch(kind, unique_ids_h.numel(), d, edges_h, rel, inv_rel, dst_negs_h, src_negs_h, host=True)
+    uid = unique_ids_h.contiguous()
+    ticket = C.c_int(0)
+    check(lib.mb_train_step_sharded_host_async(ctx.handle, C.byref(b), C.byref(shards), int(ld), C.c_void_p(uid.data_ptr()), float(lr), int(reduction),
+                                               int(precision), _ptr(rel_grad), _ptr(inv_rel_grad), C.byref(ticket), _stream()))
+    return int(ticket.value), (keep, uid)
+
+
 def ipc_export(t: torch.Tensor):
     """(64-byte CUDA IPC handle, byte offset) of a device tensor's storage -- picklable, for torch.distributed.all_gather_object."""
     _need_cuda(t)

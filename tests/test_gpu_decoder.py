@@ -323,3 +323,29 @@ def test_sharded_step_with_local_shards_vs_oracle(ops, ctx, world):
     got_s = np.concatenate([s.cpu().numpy() for s in states])
     assert rel_err(got_t, exp_t) < 3e-4 and rel_err(got_s, exp_s) < 3e-4
     assert abs(float(loss.item()) - float(res.loss)) < 3e-4 * abs(float(res.loss))
+
+
+def test_async_host_steps_match_sync_host_steps(ops):
+    """mb_train_step_host_async / _wait with one step in flight (batch i+1 enqueued before the loss of batch i is read) gives exactly
+    the tables and losses of the synchronous host entry point: same kernels, same stream order, two loss slots."""
+    rng = np.random.default_rng(21)
+    num_nodes, R, B, C, N, d = 6000, 5, 512, 2, 256, 64
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    rel, inv_rel = dev(rng.uniform(-1, 1, (R, d)).astype(np.float32)), dev(rng.uniform(-1, 1, (R, d)).astype(np.float32))
+    batches = [tuple(torch.from_numpy(x).pin_memory() for x in O.make_batch(rng, num_nodes, R, B, C, N)) for _ in range(6)]
+    ctx_a, ctx_b = ops.Context(0), ops.Context(0)
+    t1, s1 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    t2, s2 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    sync_losses = [ops.train_step_host(ctx_a, ops.COMPLEX, t1, s1, u, e, rel, inv_rel, dn, sn, 0.1) for (u, e, dn, sn) in batches]
+    async_losses, prev, keep = [], None, []
+    for (u, e, dn, sn) in batches:
+        cur = ops.train_step_host_async(ctx_b, ops.COMPLEX, t2, s2, u, e, rel, inv_rel, dn, sn, 0.1)
+        keep.append(cur[1])
+        if prev is not None:
+            async_losses.append(ops.train_step_host_wait(ctx_b, prev[0]))
+        prev = cur
+    async_losses.append(ops.train_step_host_wait(ctx_b, prev[0]))
+    assert async_losses == sync_losses
+    assert torch.equal(t1, t2) and torch.equal(s1, s2)
+    assert {ops.train_step_host_async(ctx_b, ops.COMPLEX, t2, s2, *batches[0][:2], rel, inv_rel, *batches[0][2:], 0.1)[0] for _ in range(1)} <= {0, 1}
+    torch.cuda.synchronize()

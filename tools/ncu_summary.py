@@ -49,8 +49,10 @@ def raw(rep):
 
 def main():
     tag, lcsv, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
-    out = [f"# ncu summary {tag}", "", "Source: `gpurun` on one B200 (`ncu --clock-control none`), command `python bench.py --steps 2 --warmup 3 --nodes 2000000 "
-           "--no-cpu-baseline` (ComplEx d=400, 1000 negatives, batch 10000; small table so that ncu's replay save/restore stays cheap).",
+    out = [f"# ncu summary {tag}", "", "Source: `gpurun` on one B200 (`ncu --clock-control none`).  Launch list: `python bench.py --steps 2 --warmup 3 --nodes 2000000 "
+           "--no-cpu-baseline` (the bench workload: ComplEx d=400, 1000 negatives, default batch; 2e6-row table so that ncu's replay save/restore stays "
+           "cheap).  `--set full` captures: `*_rows*` = `MB_GRAPH=0 python tools/ncu_workload.py 3` (same shape at batch 10 000), `*50k*` = the bench command "
+           "with `MB_GRAPH=0 --steps 1` at the default batch of 50 000.",
            "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes (the bench line has the real timings).", ""]
     if lcsv and os.path.exists(lcsv):
         agg = launches(lcsv)
