@@ -222,8 +222,11 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     B = args.ref_batch
-    res = cpu_reference_run(args.steps, args.warmup, B, args.ref_nodes)
-    line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=res["ms_per_step"],
+    # bounded sample: the CPU path needs ~0.7 s (16 cores) to ~2.5 s (8 cores) per 50 000-edge batch, so at most --ref-max-steps batches are
+    # timed (after at most 2 warm-up batches) whatever K / W ask for; throughput per batch is steady, the line says how many were timed
+    steps, warmup = max(1, min(args.steps, args.ref_max_steps)), min(args.warmup, 2)
+    res = cpu_reference_run(steps, warmup, B, args.ref_nodes)
+    line = dict(metric=METRIC, value=res["value"], unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=warmup, ms_per_step=res["ms_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload=f"ComplEx d={D}, {NEG} negatives, batch {B} ({res['C']} chunks), both-side corruption, SoftmaxCE-SUM, Adagrad; "
                                      f"reference CPU path (InMemory host table {args.ref_nodes} rows)", timing="wall clock, host only"),
@@ -498,6 +501,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32", "bf16"])
     ap.add_argument("--ref-nodes", type=int, default=2_000_000, help="host table rows for the CPU reference arm")
     ap.add_argument("--ref-batch", type=int, default=0, help="batch of the CPU reference arm (0 = --batch)")
+    ap.add_argument("--ref-max-steps", type=int, default=24, help="--impl reference: upper bound on the timed CPU batches")
     ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gpu-sync-interval", type=int, default=16,

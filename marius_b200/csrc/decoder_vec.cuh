@@ -190,8 +190,8 @@ struct PrepArgs {
     __nv_bfloat16 *Neg_hi[2], *Neg_lo[2];  // or null
 };
 
-// negative rows: emb[negs[side][j]] -> fp32 copy and/or bf16 hi/lo.  Items = the rows of dst_negs then src_negs; 8 rows per warp step,
-// two rows in flight per lane.
+// negative rows: emb[negs[side][j]] -> fp32 copy and/or bf16 hi/lo.  Items = the rows of dst_negs then src_negs, dealt round-robin to the
+// warps; two rows in flight per lane.
 template <int CH>  // float4 chunks per lane: d <= 128 * CH
 __global__ void __launch_bounds__(kThreads) neg_rows_kernel(PrepArgs a) {
     const int lane = threadIdx.x & 31;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kThreads) neg_rows_kernel(PrepArgs a) {
 }
 
 // edge rows: relation operator + positive scores for both corruption sides, adjusted rows as fp32 and/or bf16 hi/lo.  Items = the Bp
-// (padded) positives; 4 edges per warp step.  CHV = float4 chunks per lane of a full row (DOT / DistMult) or of a complex half (ComplEx).
+// (padded) positives, dealt round-robin to the warps.  CHV = float4 chunks per lane of a full row (DOT / DistMult) or of a complex half (ComplEx).
 template <int DEC, int CHV>  // MB_DECODER_*: relation operator fixed at compile time (DOT == identity)
 __global__ void __launch_bounds__(kThreads) edge_rows_kernel(PrepArgs a) {
     const int lane = threadIdx.x & 31;
