@@ -72,16 +72,16 @@ struct mb_context {
     char* ws = nullptr;
     size_t ws_bytes = 0;
     // device staging for mb_train_step_host
-    int64_t* h_uniq = nullptr;
-    int64_t* h_edges = nullptr;
-    int64_t* h_dneg = nullptr;
-    int64_t* h_sneg = nullptr;
+    // host-buffer steps: the index tensors of step i+1 cross PCIe on the copy stream, into one of two device slots, while step i runs
+    int64_t* pf[2] = {nullptr, nullptr};
+    size_t pf_cap[2] = {0, 0};
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
     float* h_loss = nullptr;
     float* h_loss_pinned = nullptr;  // two pinned host landing slots of the step's loss, used alternately (mb_train_step_host_async keeps
                                      // one step in flight while the caller reads the previous step's loss)
     int loss_slot = 0;
     cudaEvent_t ev_loss[2] = {nullptr, nullptr};
-    size_t h_uniq_cap = 0, h_edges_cap = 0, h_dneg_cap = 0, h_sneg_cap = 0;
     std::vector<void*> ipc_mappings;      // peer shards opened with mb_ipc_import (closed in mb_destroy)
     cudaStream_t side = nullptr;          // index plans (slot / relation sorts) overlap the forward pass here
     cudaStream_t side2 = nullptr;         // the dNeg contraction runs here, concurrently with dA + edge_backward
@@ -279,7 +279,9 @@ static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
     p.has_rel = (b->edge_cols == 3) && (b->decoder != MB_DECODER_DOT) && b->rel != nullptr;
     p.sides = (p.has_rel && b->inv_rel != nullptr && b->src_negs != nullptr) ? 2 : 1;  // use_inverse_relations_ (decoder_methods.cpp:90)
     p.n_slots = 2 * p.B + 2 * p.CN;
-    p.use_tc = (precision != MB_PREC_FP32) && gemm_tc_supported(p.d, p.N) && p.Bc > 0;
+    // tensor-core contractions take their bf16 hi/lo operands from the vectorised row kernels (d <= 512); wider rows use the general-d
+    // row kernels with the fp32 FFMA contraction
+    p.use_tc = (precision != MB_PREC_FP32) && gemm_tc_supported(p.d, p.N) && p.Bc > 0 && p.d <= 512;
     p.Ng = p.use_tc ? ((int64_t)p.N + 63) / 64 * 64 : p.N;
 }
 
@@ -579,6 +581,9 @@ mb_status mb_create(int device, mb_context** out) {
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_loss_pinned, 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copied[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copied[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_loss[0], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_loss[1], cudaEventDisableTiming);
     // The index plans are chains of small kernels that must finish before the node update.  They share the GPU with grid-filling row
@@ -616,10 +621,11 @@ void mb_destroy(mb_context* ctx) {
     }
     cudaSetDevice(ctx->device);
     if (ctx->ws) cudaFree(ctx->ws);
-    if (ctx->h_uniq) cudaFree(ctx->h_uniq);
-    if (ctx->h_edges) cudaFree(ctx->h_edges);
-    if (ctx->h_dneg) cudaFree(ctx->h_dneg);
-    if (ctx->h_sneg) cudaFree(ctx->h_sneg);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->pf[i]) cudaFree(ctx->pf[i]);
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+    }
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
     if (ctx->h_loss) cudaFree(ctx->h_loss);
     if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
     for (auto& ev : ctx->ev_loss)
@@ -1088,7 +1094,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     fill_plan_dims(probe, ub, precision);
     const bool vec = decoder_vec_ok(table, ld, (int)ub->d, probe.has_rel, ub->rel, probe.sides == 2 ? ub->inv_rel : nullptr, probe.sides);
     const bool eligible = graphs_on(ctx) && vec && probe.use_tc && tc_tile_config() == 1024 && ub->B > 0 && ub->U <= cap_u;
-    if (!eligible && !host_inputs) {
+    if (!eligible && !host_inputs && loss_host == nullptr) {
         return run_train(ctx, ub, nullptr, 0, nullptr, 0, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, nullptr, nullptr, nullptr,
                          rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh);
     }
@@ -1283,8 +1289,43 @@ static mb_status host_step_enqueue(mb_context* ctx, const mb_batch* hb, const mb
     MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
     MB_CUDA_TRY(cudaSetDevice(ctx->device));
     const int slot = ctx->loss_slot;
-    MB_TRY(train_step_any(ctx, hb, true, table, state_table, ld, unique_ids_host, lr, reduction, precision, nullptr, ctx->h_loss_pinned + slot, rel_grad,
-                          inv_rel_grad, st, shards));
+    static const bool prefetch = [] { const char* e = getenv("MB_H2D_PREFETCH"); return e ? atoi(e) != 0 : true; }();
+    if (prefetch && hb != nullptr && hb->B > 0 && hb->edges != nullptr && hb->dst_negs != nullptr) {
+        // Batch::to on its own stream (batch.cpp:21-60 uses a pool stream + record_stream the same way): the four index tensors go into
+        // device slot `slot` over the copy stream, so the PCIe transfer of this batch runs while the previous batch computes; the step
+        // itself then takes device inputs (its graph starts with device-to-device copies into the fixed staging buffers).
+        const int64_t n_u = hb->U, n_e = hb->B * hb->edge_cols, n_n = (int64_t)hb->C * hb->N;
+        const bool has_s = hb->src_negs != nullptr;
+        const size_t need = (size_t)(n_u + n_e + n_n + (has_s ? n_n : 0));
+        if (need > ctx->pf_cap[slot]) {
+            MB_CUDA_TRY(cudaEventSynchronize(ctx->ev_loss[slot]));  // the slot's previous step has consumed it
+            if (ctx->pf[slot]) MB_CUDA_TRY(cudaFree(ctx->pf[slot]));
+            ctx->pf[slot] = nullptr;
+            ctx->pf_cap[slot] = 0;
+            MB_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ctx->pf[slot]), sizeof(int64_t) * (need + need / 8 + 1024)));
+            ctx->pf_cap[slot] = need + need / 8 + 1024;
+        }
+        int64_t* d_u = ctx->pf[slot];
+        int64_t* d_e = d_u + n_u;
+        int64_t* d_dn = d_e + n_e;
+        int64_t* d_sn = d_dn + n_n;
+        MB_CUDA_TRY(cudaStreamWaitEvent(ctx->copy, ctx->ev_loss[slot], 0));  // (a no-op unless the caller broke the two-in-flight rule)
+        MB_CUDA_TRY(cudaMemcpyAsync(d_u, unique_ids_host, sizeof(int64_t) * n_u, cudaMemcpyHostToDevice, ctx->copy));
+        MB_CUDA_TRY(cudaMemcpyAsync(d_e, hb->edges, sizeof(int64_t) * n_e, cudaMemcpyHostToDevice, ctx->copy));
+        MB_CUDA_TRY(cudaMemcpyAsync(d_dn, hb->dst_negs, sizeof(int64_t) * n_n, cudaMemcpyHostToDevice, ctx->copy));
+        if (has_s) MB_CUDA_TRY(cudaMemcpyAsync(d_sn, hb->src_negs, sizeof(int64_t) * n_n, cudaMemcpyHostToDevice, ctx->copy));
+        MB_CUDA_TRY(cudaEventRecord(ctx->ev_copied[slot], ctx->copy));
+        MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_copied[slot], 0));
+        mb_batch db = *hb;
+        db.edges = d_e;
+        db.dst_negs = d_dn;
+        db.src_negs = has_s ? d_sn : nullptr;
+        MB_TRY(train_step_any(ctx, &db, false, table, state_table, ld, d_u, lr, reduction, precision, nullptr, ctx->h_loss_pinned + slot, rel_grad,
+                              inv_rel_grad, st, shards));
+    } else {
+        MB_TRY(train_step_any(ctx, hb, true, table, state_table, ld, unique_ids_host, lr, reduction, precision, nullptr, ctx->h_loss_pinned + slot, rel_grad,
+                              inv_rel_grad, st, shards));
+    }
     MB_CUDA_TRY(cudaEventRecord(ctx->ev_loss[slot], st));
     ctx->loss_slot = slot ^ 1;
     *ticket = slot;

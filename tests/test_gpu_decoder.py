@@ -349,3 +349,20 @@ def test_async_host_steps_match_sync_host_steps(ops):
     assert torch.equal(t1, t2) and torch.equal(s1, s2)
     assert {ops.train_step_host_async(ctx_b, ops.COMPLEX, t2, s2, *batches[0][:2], rel, inv_rel, *batches[0][2:], 0.1)[0] for _ in range(1)} <= {0, 1}
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_wide_rows_take_the_general_path(ops, ctx, prec):
+    """d > 512 is outside the vectorised row kernels (4 chunks of 16 B per lane): the general-d kernels take over, same results."""
+    p = ops.PREC_FP32 if prec == "fp32" else ops.PREC_BF16X3
+    rng = np.random.default_rng(77)
+    num_nodes, R, B, C, N, d = 3000, 4, 96, 2, 64, 520
+    table = rng.uniform(-0.2, 0.2, (num_nodes, d)).astype(np.float32)
+    rel, inv_rel = rng.uniform(-1, 1, (R, d)).astype(np.float32), rng.uniform(-1, 1, (R, d)).astype(np.float32)
+    uniq, edges, dn, sn = O.make_batch(rng, num_nodes, R, B, C, N)
+    t, st = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    loss = ops.train_step(ctx, ops.DISTMULT, t, st, dev(uniq), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, ops.REDUCTION_SUM, p)
+    ref_t, ref_s = table.copy(), np.zeros_like(table)
+    res = O.train_step_on_table(O.DISTMULT, ref_t, ref_s, uniq, edges, rel, inv_rel, dn, sn, 0.1, O.REDUCTION_SUM, acc=np.float64)
+    assert rel_err(t, ref_t) < TOL and rel_err(st, ref_s) < TOL
+    assert abs(float(loss.item()) - float(res.loss)) <= TOL * abs(float(res.loss))
