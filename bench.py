@@ -49,13 +49,27 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
-def make_batches(rng, num_nodes, n_batches, B):
-    from oracle import marius_oracle as O
+def synthetic_batch(rng, src, dst, relid, src_negs, dst_negs):
+    """Batch assembly of the synthetic inputs on the host (numpy): unique-id mapping over cat(src, dst, src_negs, dst_negs), the
+    order DataLoader::edgeSample uses (dataloader.cpp:398-461).  Returns (unique ids, local edges [B,3], local dst_negs, local src_negs)."""
+    B, (C, N) = src.shape[0], src_negs.shape
+    uniq, inv = np.unique(np.concatenate([src, dst, src_negs.reshape(-1), dst_negs.reshape(-1)]), return_inverse=True)
+    uniq, inv = uniq.astype(np.int64), inv.astype(np.int64).reshape(-1)
+    edges = np.ascontiguousarray(np.stack([inv[:B], relid, inv[B:2 * B]], axis=1))
+    return uniq, edges, np.ascontiguousarray(inv[2 * B + C * N:].reshape(C, N)), np.ascontiguousarray(inv[2 * B:2 * B + C * N].reshape(C, N))
 
+
+def make_batches(rng, num_nodes, n_batches, B):
+    """Uniform edges and uniform negatives over the whole table (negative.cpp:342)."""
     C = max(B // CHUNK, 1)
     out = []
     for _ in range(n_batches):
-        out.append(O.make_batch(rng, num_nodes, NUM_REL, B, C, NEG))
+        src = rng.integers(0, num_nodes, size=B, dtype=np.int64)
+        dst = rng.integers(0, num_nodes, size=B, dtype=np.int64)
+        relid = rng.integers(0, NUM_REL, size=B, dtype=np.int64)
+        sn = rng.integers(0, num_nodes, size=(C, NEG), dtype=np.int64)
+        dn = rng.integers(0, num_nodes, size=(C, NEG), dtype=np.int64)
+        out.append(synthetic_batch(rng, src, dst, relid, sn, dn))
     return out, C
 
 
@@ -63,8 +77,6 @@ def make_sharded_batches(rng, rows_per_rank, rank, world, n_batches, B):
     """Bucket-wise routing: sources and both negative pools come from the rank's own partition, destinations are
     uniform over ALL partitions, so (world-1)/world of the destination rows -- ~22 % of a batch's unique rows at 8 GPUs -- cross
     NVLink.  Returns [(unique GLOBAL ids sorted, edges local, dst_negs local, src_negs local)]."""
-    from oracle import marius_oracle as O
-
     C = max(B // CHUNK, 1)
     lo = rank * rows_per_rank
     out = []
@@ -74,9 +86,7 @@ def make_sharded_batches(rng, rows_per_rank, rank, world, n_batches, B):
         relid = rng.integers(0, NUM_REL, size=B, dtype=np.int64)
         sn = rng.integers(lo, lo + rows_per_rank, size=(C, NEG), dtype=np.int64)
         dn = rng.integers(lo, lo + rows_per_rank, size=(C, NEG), dtype=np.int64)
-        uniq, inv = O.map_tensors(np.concatenate([src, dst, sn.reshape(-1), dn.reshape(-1)]))
-        edges = np.ascontiguousarray(np.stack([inv[:B], relid, inv[B:2 * B]], axis=1))
-        out.append((uniq, edges, np.ascontiguousarray(inv[2 * B + C * NEG:].reshape(C, NEG)), np.ascontiguousarray(inv[2 * B:2 * B + C * NEG].reshape(C, NEG))))
+        out.append(synthetic_batch(rng, src, dst, relid, sn, dn))
     return out, C
 
 
@@ -241,8 +251,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from marius_b200 import _lib, ops
-    from oracle import marius_oracle as O
+    from marius_b200 import _lib, ops  # the measured arm imports nothing from oracle/
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -1,4 +1,4 @@
-"""tools/peer_check.py -- 2+ rank check of the peer-memory sharded step (run under torchrun, one rank per GPU).
+"""tests/peer_check.py -- 2+ rank check of the peer-memory sharded step (run under torchrun, one rank per GPU).
 Rank r builds a batch over the WHOLE global id space restricted to ids == r (mod world): the batches of different ranks touch
 disjoint rows, so there are no cross-rank races and the final tables must equal the oracle applying every batch once."""
 import os

@@ -10,8 +10,8 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
+import bench
 from marius_b200 import ops
-from oracle import marius_oracle as O
 
 
 def main():
@@ -31,7 +31,8 @@ def main():
     loss = torch.zeros(1, device=dev)
     ctx = ops.Context(0)
     rng = np.random.default_rng(0)
-    batches = [tuple(torch.from_numpy(x).to(dev) for x in O.make_batch(rng, args.nodes, R, B, C, NEG)) for _ in range(args.steps + 2)]
+    host_batches, _ = bench.make_batches(rng, args.nodes, args.steps + 2, B)
+    batches = [tuple(torch.from_numpy(x).to(dev) for x in b) for b in host_batches]
     for i in range(2):
         u, e, dn, sn = batches[i]
         ops.train_step(ctx, ops.COMPLEX, table, state, u, e, rels[0], rels[1], dn, sn, 0.1, ops.REDUCTION_SUM, ops.PREC_BF16X3, loss=loss, rel_grad=rg, inv_rel_grad=irg)
