@@ -363,6 +363,10 @@ def run_ours(args):
     # ---- value: indices resident in HBM, device-timed, max over ranks
     for i in range(W):
         step_resident(i)
+    if world > 1:
+        # the first collective of a given size loads NCCL's kernel for it and sets its channels up (~15 ms, measured): with a sync interval
+        # longer than the warm-up that one-time cost would otherwise land inside the timed steps
+        dist.all_reduce(rel_grads)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
