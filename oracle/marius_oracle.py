@@ -235,6 +235,38 @@ def apply_score_filter(scores: np.ndarray, filt: Optional[np.ndarray]) -> np.nda
     return scores
 
 
+def compute_filter_corruption(edges: np.ndarray, corruption_nodes: np.ndarray, inverse: bool, graph_edges: Optional[np.ndarray] = None) -> np.ndarray:
+    """compute_filter_corruption_cpu (data/samplers/negative.cpp:62-195): the [F,2] (row, column) pairs whose negative score must be
+    masked because the corrupted triple is a true edge.
+
+    ``graph_edges`` given  -> GLOBAL filter (``filtered`` evaluation, negative.cpp:152-163): the negatives are all nodes
+        (``arange(num_nodes)``), so for batch edge i every graph edge with the same kept endpoint (source, or destination when
+        ``inverse``) and the same relation contributes (i, its corrupted endpoint's node id).  Order: by batch edge, then in the
+        order of the graph's edge list sorted (stably) by the kept endpoint.
+    ``graph_edges`` None   -> LOCAL filter against the batch itself (negative.cpp:164-182): (i, j) if replacing the corrupted
+        endpoint of edge i by negative j of i's chunk gives another edge of the batch (first match per negative)."""
+    has_rel = edges.shape[1] == 3
+    tup, cor = ((edges.shape[1] - 1), 0) if inverse else (0, edges.shape[1] - 1)
+    nodes = edges[:, tup]
+    pool = graph_edges if graph_edges is not None else edges
+    pool = pool[np.argsort(pool[:, tup], kind="stable")]
+    keys = pool[:, tup]
+    starts, ends = np.searchsorted(keys, nodes, side="left"), np.searchsorted(keys, nodes + 1, side="left")
+    num_chunks = corruption_nodes.shape[0]
+    chunk_size = int(math.ceil(edges.shape[0] / num_chunks))
+    out = []
+    for i in range(edges.shape[0]):
+        cand = pool[starts[i]:ends[i]]
+        if has_rel:
+            cand = cand[cand[:, 1] == edges[i, 1]]
+        if graph_edges is not None:
+            out.extend((i, int(c)) for c in cand[:, cor])
+        else:
+            present = set(int(c) for c in cand[:, cor])
+            out.extend((i, j) for j, n in enumerate(corruption_nodes[i // chunk_size]) if int(n) in present)
+    return np.array(out, dtype=np.int64).reshape(-1, 2)
+
+
 def compute_ranks(pos: np.ndarray, neg: np.ndarray) -> np.ndarray:
     """LinkPredictionReporter::computeRanks (reporting/reporting.cpp:56-58): ``(neg >= pos.unsqueeze(1)).sum(1) + 1`` as int64.
     Padding rows (pos = 0, all-zero scores) get rank N + 1, exactly as in the reference."""

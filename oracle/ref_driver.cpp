@@ -24,6 +24,8 @@
 
 #include "common/util.h"
 #include "data/batch.h"
+#include "data/graph.h"
+#include "data/samplers/negative.h"
 #include "nn/decoders/edge/complex.h"
 #include "nn/decoders/edge/decoder_methods.h"
 #include "nn/decoders/edge/distmult.h"
@@ -272,6 +274,35 @@ int ref_evaluate_batch(int decoder_type, int d, int num_rel, const float *rel, c
     } catch (const std::exception &e) {
         g_last_error = e.what();
         return 1;
+    }
+}
+
+// compute_filter_corruption_cpu (negative.cpp:62-195).  graph_edges != NULL: global ("filtered" evaluation) filter against a graph whose
+// edge list is graph_edges [G,3] (sorted here by source / destination exactly as MariusGraph's callers do, with a stable argsort);
+// graph_edges == NULL: local filter against the batch.  Writes up to cap (row, column) pairs into out and returns the number of pairs
+// (or -1 on error; a count > cap means the buffer was too small).
+int64_t ref_compute_filter(const int64_t *edges, int64_t B, int cols, const int64_t *corruption_nodes, int C, int N, int inverse,
+                           const int64_t *graph_edges, int64_t G, int64_t num_nodes, int64_t *out, int64_t cap) {
+    try {
+        torch::Tensor e = i64(edges, {B, (int64_t)cols}).clone();
+        torch::Tensor negs = i64(corruption_nodes, {C, N}).clone();
+        shared_ptr<MariusGraph> graph = nullptr;
+        bool global = graph_edges != nullptr;
+        if (global) {
+            torch::Tensor ge = i64(graph_edges, {G, (int64_t)cols}).clone();
+            torch::Tensor by_src = ge.index_select(0, ge.select(1, 0).argsort(true));
+            torch::Tensor by_dst = ge.index_select(0, ge.select(1, -1).argsort(true));
+            graph = std::make_shared<MariusGraph>(by_src, by_dst, num_nodes);
+            graph->all_src_sorted_edges_ = by_src;
+            graph->all_dst_sorted_edges_ = by_dst;
+        }
+        torch::Tensor f = compute_filter_corruption_cpu(graph, e, negs, inverse != 0, global, LocalFilterMode::ALL, torch::Tensor()).contiguous();
+        int64_t n = f.size(0);
+        if (n <= cap && n > 0) std::memcpy(out, f.data_ptr<int64_t>(), sizeof(int64_t) * 2 * n);
+        return n;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return -1;
     }
 }
 

@@ -63,6 +63,8 @@ def lib():
         _lib.ref_evaluate_batch.argtypes = [C.c_int, C.c_int, C.c_int, _F, _F, _F, C.c_int64, _I, C.c_int64, _I, _I, C.c_int, C.c_int, _I, C.c_int64, _I,
                                             C.c_int64, _I, _I, _F, _F, _F, _F]
         _lib.ref_ranking_metrics.argtypes = [_I, C.c_int64, C.POINTER(C.c_double)]
+        _lib.ref_compute_filter.argtypes = [_I, C.c_int64, C.c_int, _I, C.c_int, C.c_int, C.c_int, _I, C.c_int64, C.c_int64, _I, C.c_int64]
+        _lib.ref_compute_filter.restype = C.c_int64
     return _lib
 
 
@@ -182,3 +184,19 @@ def ranking_metrics(ranks: np.ndarray) -> dict:
     if lib().ref_ranking_metrics(_ip(r), r.shape[0], out):
         raise RuntimeError(lib().ref_last_error().decode())
     return {"mean_rank": out[0], "mrr": out[1], "hits@1": out[2], "hits@3": out[3], "hits@10": out[4]}
+
+
+def compute_filter(edges: np.ndarray, corruption_nodes: np.ndarray, inverse: bool, graph_edges: Optional[np.ndarray] = None, num_nodes: int = 0):
+    """Runs the reference compute_filter_corruption_cpu (global filter against graph_edges, or local filter against the batch)."""
+    e = np.ascontiguousarray(edges, dtype=np.int64)
+    negs = np.ascontiguousarray(corruption_nodes, dtype=np.int64)
+    g = np.ascontiguousarray(graph_edges, dtype=np.int64) if graph_edges is not None else None
+    cap = max(1, e.shape[0] * negs.shape[1] if g is None else 4 * (g.shape[0] + e.shape[0]))
+    out = np.zeros((cap, 2), np.int64)
+    n = lib().ref_compute_filter(_ip(e), e.shape[0], e.shape[1], _ip(negs), negs.shape[0], negs.shape[1], int(bool(inverse)), _ip(g),
+                                 0 if g is None else g.shape[0], int(num_nodes), _ip(out), cap)
+    if n < 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    if n > cap:
+        raise RuntimeError("filter buffer too small")
+    return out[:n].copy()

@@ -4,7 +4,7 @@ Run in the build container (needs /root/reference):   make -C oracle && python t
 Every array in tests/golden/*.npz is an input to, or an output of, the reference C++ itself
 (oracle/_ref/libmarius_ref.so = the reference's TUs compiled in place + oracle/ref_driver.cpp):
   InMemory::indexRead/indexAdd, PartitionBuffer::{indexRead,indexAdd,getGlobalToLocalMap,getNextAdmit,getNextEvict},
-  map_tensors, Model::forward_lp, Model::train_batch, Model::evaluate_batch (+ LinkPredictionReporter::computeRanks, ranking metrics).
+  map_tensors, Model::forward_lp, Model::train_batch, Model::evaluate_batch (+ LinkPredictionReporter::computeRanks, ranking metrics), compute_filter_corruption_cpu.
 The fixtures travel to the GPU box; /root/reference does not.
 """
 import os
@@ -66,6 +66,34 @@ def eval_case(name, kind, B, C, N, d, num_nodes, num_rel, seed, n_filter, all_no
     print(name, "U", U, metrics)
 
 
+def filtered_eval_case(name, kind, num_nodes, num_rel, num_graph_edges, B, d, seed):
+    """The reference's filtered evaluation end to end: global score filters built by compute_filter_corruption_cpu from the graph
+    (negative.cpp:62-195), negatives = all nodes (negative.cpp:355), Model::evaluate_batch -> ranks; plus the local (in-batch) filter of
+    the same edges against sampled negatives."""
+    rng = np.random.default_rng(seed)
+    graph = np.unique(np.stack([rng.integers(0, num_nodes, num_graph_edges), rng.integers(0, num_rel, num_graph_edges),
+                                rng.integers(0, num_nodes, num_graph_edges)], axis=1).astype(np.int64), axis=0)
+    graph = graph[rng.permutation(len(graph))]
+    edges = np.ascontiguousarray(graph[rng.choice(len(graph), B, replace=False)])
+    all_nodes = np.arange(num_nodes, dtype=np.int64).reshape(1, num_nodes)
+    dst_filter = R.compute_filter(edges, all_nodes, False, graph_edges=graph, num_nodes=num_nodes)
+    src_filter = R.compute_filter(edges, all_nodes, True, graph_edges=graph, num_nodes=num_nodes)
+    local_negs = rng.integers(0, num_nodes, (4, 50)).astype(np.int64)
+    local_dst = R.compute_filter(edges, local_negs, False)
+    local_src = R.compute_filter(edges, local_negs, True)
+    emb = rng.uniform(-0.5, 0.5, (num_nodes, d)).astype(np.float32)
+    rel = rng.uniform(-1, 1, (num_rel, d)).astype(np.float32)
+    inv_rel = rng.uniform(-1, 1, (num_rel, d)).astype(np.float32)
+    ref = R.evaluate_batch(kind, emb, edges, rel, inv_rel, all_nodes, all_nodes.copy(), dst_filter, src_filter)
+    metrics = R.ranking_metrics(np.concatenate([ref["ranks"], ref["inv_ranks"]]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), kind=kind, B=B, C=1, N=num_nodes, d=d, graph=graph, edges=edges, dst_negs=all_nodes,
+                        src_negs=all_nodes, emb=emb, rel=rel, inv_rel=inv_rel, dst_filter=dst_filter, src_filter=src_filter, local_negs=local_negs,
+                        local_dst_filter=local_dst, local_src_filter=local_src,
+                        metrics=np.array([metrics[k] for k in ("mean_rank", "mrr", "hits@1", "hits@3", "hits@10")]),
+                        **{"ref_" + k: v for k, v in ref.items()})
+    print(name, "graph edges", len(graph), "filter sizes", dst_filter.shape[0], src_filter.shape[0], local_dst.shape[0], local_src.shape[0], metrics)
+
+
 def storage_case():
     rng = np.random.default_rng(7)
     table = rng.standard_normal((257, 24)).astype(np.float32)
@@ -114,4 +142,5 @@ if __name__ == "__main__":
     eval_case("eval_distmult_pad", O.DISTMULT, 7, 3, 5, 8, 40, 3, 21, 0)                      # padded rows get rank N + 1
     eval_case("eval_complex_filter", O.COMPLEX, 96, 2, 64, 32, 500, 7, 22, 200)               # sampled negatives + score filters
     eval_case("eval_distmult_all", O.DISTMULT, 50, 1, 0, 16, 120, 5, 23, 60, all_nodes=True)  # filtered evaluation against all nodes
+    filtered_eval_case("eval_filtered_graph", O.COMPLEX, 320, 6, 4000, 64, 32, 24)              # global + local filters from a graph
     train_case("train_complex_d100", O.COMPLEX, 200, 2, 100, 100, 14541, 237, O.REDUCTION_SUM, 6, emb_scale=0.1)  # FB15k-237-sized

@@ -238,3 +238,54 @@ def test_edge_sample_matches_map_tensors_golden(golden_dir):
         assert np.array_equal(ru, uniq) and np.array_equal(rm[:40], local[:, 0]) and np.array_equal(rm[80:140].reshape(2, 30), s_loc)
     u2, l2, s2, d2 = O.edge_sample(edges[:, [0, 2]], None, dn)  # 2-column edges, no inverse side
     assert s2 is None and l2.shape == (40, 2) and np.array_equal(u2[d2], dn)
+
+
+# ---- (6) score-filter construction (negative.cpp:62-195) -----------------------------------------------
+def test_filter_construction_known_answers():
+    # graph: 0 -r0-> 1, 0 -r0-> 2, 0 -r1-> 3, 4 -r0-> 1 ; batch edge (0, r0, 1)
+    graph = np.array([[0, 0, 1], [0, 0, 2], [0, 1, 3], [4, 0, 1]], np.int64)
+    edges = np.array([[0, 0, 1]], np.int64)
+    all_nodes = np.arange(5, dtype=np.int64).reshape(1, 5)
+    # corrupting the destination: every true (0, r0, *) destination is masked, including the positive's own
+    assert O.compute_filter_corruption(edges, all_nodes, False, graph_edges=graph).tolist() == [[0, 1], [0, 2]]
+    # corrupting the source: every true (*, r0, 1) source
+    assert O.compute_filter_corruption(edges, all_nodes, True, graph_edges=graph).tolist() == [[0, 0], [0, 4]]
+    # local filter: negatives [2, 3, 1] of the only chunk against the batch {(0,r0,1), (0,r0,2)} -> columns of nodes 2 and 1
+    batch = np.array([[0, 0, 1], [0, 0, 2]], np.int64)
+    assert O.compute_filter_corruption(batch, np.array([[2, 3, 1]], np.int64), False).tolist() == [[0, 0], [0, 2], [1, 0], [1, 2]]
+
+
+def test_golden_filter_construction_and_filtered_eval(golden_dir):
+    g = np.load(os.path.join(golden_dir, "eval_filtered_graph.npz"))
+    all_nodes = g["dst_negs"]
+    # integer work: bit-exact, including the order of the pairs
+    assert np.array_equal(O.compute_filter_corruption(g["edges"], all_nodes, False, graph_edges=g["graph"]), g["dst_filter"])
+    assert np.array_equal(O.compute_filter_corruption(g["edges"], all_nodes, True, graph_edges=g["graph"]), g["src_filter"])
+    assert np.array_equal(O.compute_filter_corruption(g["edges"], g["local_negs"], False), g["local_dst_filter"])
+    assert np.array_equal(O.compute_filter_corruption(g["edges"], g["local_negs"], True), g["local_src_filter"])
+    # the positive's own endpoint is always among the filtered columns of its row (it is a true edge of the graph)
+    df = set(map(tuple, g["dst_filter"].tolist()))
+    assert all((i, int(e[2])) in df for i, e in enumerate(g["edges"]))
+    # filtered evaluation end to end with the oracle-built filters
+    ranks, inv_ranks, sc = O.evaluate_batch(int(g["kind"]), g["emb"], g["edges"], g["rel"], g["inv_rel"], all_nodes, g["src_negs"],
+                                            O.compute_filter_corruption(g["edges"], all_nodes, False, graph_edges=g["graph"]),
+                                            O.compute_filter_corruption(g["edges"], all_nodes, True, graph_edges=g["graph"]))
+    assert ranks_match_up_to_ties(ranks, g["ref_ranks"], g["ref_pos"], g["ref_neg"])
+    assert ranks_match_up_to_ties(inv_ranks, g["ref_inv_ranks"], g["ref_inv_pos"], g["ref_inv_neg"])
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (make -C oracle)")
+def test_filter_construction_against_reference_library():
+    rng = np.random.default_rng(8)
+    num_nodes = 40
+    graph = np.unique(np.stack([rng.integers(0, num_nodes, 400), rng.integers(0, 3, 400), rng.integers(0, num_nodes, 400)], axis=1).astype(np.int64), axis=0)
+    graph = graph[rng.permutation(len(graph))]
+    edges = graph[rng.choice(len(graph), 30, replace=False)]
+    all_nodes = np.arange(num_nodes, dtype=np.int64).reshape(1, -1)
+    negs = rng.integers(0, num_nodes, (3, 25)).astype(np.int64)
+    for inverse in (False, True):
+        assert np.array_equal(O.compute_filter_corruption(edges, all_nodes, inverse, graph_edges=graph),
+                              R.compute_filter(edges, all_nodes, inverse, graph_edges=graph, num_nodes=num_nodes))
+        assert np.array_equal(O.compute_filter_corruption(edges[:, [0, 2]], all_nodes, inverse, graph_edges=graph[:, [0, 2]]),
+                              R.compute_filter(edges[:, [0, 2]], all_nodes, inverse, graph_edges=graph[:, [0, 2]], num_nodes=num_nodes))
+        assert np.array_equal(O.compute_filter_corruption(edges, negs, inverse), R.compute_filter(edges, negs, inverse))
