@@ -980,7 +980,7 @@ mb_status mb_decoder_forward(mb_context* ctx, const mb_batch* batch, const float
     return MB_OK;
 }
 
-static mb_status filter_checked(mb_context* ctx, float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, cudaStream_t st) {
+static mb_status filter_checked(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, cudaStream_t st) {
     if (F == 0) return MB_OK;
     MB_REQUIRE(filter != nullptr && scores != nullptr, "null filter / scores");
     int* flag = nullptr;
@@ -991,7 +991,6 @@ static mb_status filter_checked(mb_context* ctx, float* scores, int64_t rows, in
     cudaError_t e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFreeAsync(flag, st);
-    (void)ctx;
     MB_TRY(rs);
     MB_CUDA_TRY(e);
     MB_REQUIRE(host_flag == 0, "score filter index out of range");
@@ -1000,7 +999,7 @@ static mb_status filter_checked(mb_context* ctx, float* scores, int64_t rows, in
 
 mb_status mb_apply_score_filter(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, void* stream) {
     MB_REQUIRE(rows >= 0 && N >= 0 && F >= 0 && ld >= N, "bad dimensions");
-    return filter_checked(nullptr, scores, rows, N, ld, filter, F, (cudaStream_t)stream);
+    return filter_checked(scores, rows, N, ld, filter, F, (cudaStream_t)stream);
 }
 
 mb_status mb_compute_ranks(const float* pos, const float* neg, int64_t rows, int64_t N, int64_t ld, int64_t* ranks, void* stream) {
@@ -1035,10 +1034,10 @@ mb_status mb_evaluate_batch(mb_context* ctx, const mb_batch* batch, const float*
     if (p.Bc == 0) {  // no positives: nothing to rank
         return MB_OK;
     }
-    MB_TRY(filter_checked(ctx, p.S, p.Bp, p.N, p.N, dst_filter, Fd, st));
+    MB_TRY(filter_checked(p.S, p.Bp, p.N, p.N, dst_filter, Fd, st));
     MB_TRY(launch_ranks(p.pos, p.S, p.Bp, p.N, p.N, ranks, st));
     if (p.sides == 2) {
-        MB_TRY(filter_checked(ctx, S1, p.Bp, p.N, p.N, src_filter, Fs, st));
+        MB_TRY(filter_checked(S1, p.Bp, p.N, p.N, src_filter, Fs, st));
         MB_TRY(launch_ranks(p.pos + p.Bp, S1, p.Bp, p.N, p.N, inv_ranks, st));
     }
     if (pos) MB_CUDA_TRY(cudaMemcpyAsync(pos, p.pos, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
