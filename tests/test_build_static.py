@@ -1,0 +1,52 @@
+"""Static checks of the built sm_100a library (no GPU needed): the hot kernels exist, do not spill, and the SASS contains the
+tensor-core / TMA / NVLink-reduction instructions the design relies on (mnemonics per B200_PROFILING.md: tcgen05.mma -> UTC*MMA,
+cp.async.bulk.tensor -> UTMALDG / UTMASTG)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "marius_b200", "lib", "libmarius_b200.so")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(LIB) and os.path.exists(CUOBJDUMP)), reason="needs the built library and cuobjdump")
+
+
+@pytest.fixture(scope="module")
+def resources():
+    out = subprocess.run([CUOBJDUMP, "--dump-resource-usage", LIB], capture_output=True, text=True, timeout=300).stdout
+    res = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out):
+        res[m.group(1)] = dict(reg=int(m.group(2)), stack=int(m.group(3)), shared=int(m.group(4)), local=int(m.group(5)))
+    return res
+
+
+def test_built_for_sm_100a():
+    out = subprocess.run([CUOBJDUMP, "--list-elf", LIB], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+
+
+def test_hot_kernels_exist_and_do_not_spill(resources):
+    hot = ["gemm_tc_group_kernel", "neg_rows_kernelILi4E", "edge_rows_kernelILi2ELi2E", "edge_backward_kernelILi2ELi2E", "loss_kernelILi8E",
+           "segment_reduce_kernelILi2ELi4E", "fetch_remote_rows_kernelILi4ELb0E", "fetch_remote_rows_kernelILi4ELb1E", "gather_rows_kernel", "rank_kernel",
+           "sample_negatives_kernel"]
+    for name in hot:
+        found = [(k, v) for k, v in resources.items() if name in k]
+        assert found, f"kernel {name} not in the library"
+        for k, v in found:
+            assert v["local"] == 0 and v["stack"] == 0, f"{k} spills: {v}"
+    # the persistent contraction must leave the row kernels room in the register file (192 threads x regs <= 1/2 of 64 K)
+    gemm = [v for k, v in resources.items() if "gemm_tc_group_kernel" in k][0]
+    assert gemm["reg"] * 192 <= 32768
+
+
+def test_sass_has_tcgen05_tma_and_system_reductions():
+    sass = subprocess.run([CUOBJDUMP, "-sass", LIB], capture_output=True, text=True, timeout=600).stdout
+    assert re.search(r"UTC[A-Z]*MMA", sass), "no tcgen05.mma (UTC*MMA) in the SASS"
+    assert "UTCHMMA.2CTA" in sass, "the grouped contraction is a cta_group::2 kernel"
+    assert "UTMALDG" in sass and "UTMASTG" in sass, "no TMA tensor loads / stores in the SASS"
+    assert re.search(r"REDG\.E\.ADD\.F32x4[.A-Z]*\.SYS", sass), "remote Adagrad deltas use 128-bit system-scope reductions"
+    assert "WGMMA" not in sass and "HMMA.16" not in sass  # neither Hopper wgmma nor legacy mma.sync anywhere
