@@ -208,8 +208,9 @@ mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, fl
  * rows per SM in flight (NVLink latency is ~5x HBM latency), the decoder kernels then read local memory only; the update reads the
  * owner's Adagrad state row and applies delta_e / delta_s with fire-and-forget vector reductions (red.global.sys.add.v4.f32) at the
  * owner's HBM -- exactly the reference's indexAdd of both deltas.  The only cross-GPU traffic is the rows a batch needs: one row
- * in (embedding) + one row in (state) + two rows out per remote row, and there is no collective on the row path.  Rows touched concurrently by two ranks follow the reference's unlocked
- * (bounded-staleness) update semantics (storage/buffer.cpp:459).  Up to 8 shards. */
+ * in (embedding) + one row in (state) + two rows out per remote row, and there is no collective on the row path.  Rows touched
+ * concurrently by two ranks follow the reference's unlocked (bounded-staleness) update semantics (storage/buffer.cpp:459,
+ * SURVEY.md 3.2).  Up to 8 shards. */
 typedef struct mb_shards {
     float* tables[8];
     float* states[8];
@@ -231,8 +232,9 @@ mb_status mb_train_step_sharded_host(mb_context* ctx, const mb_batch* host_batch
                                      float* inv_rel_grad, void* stream);
 
 /* Same call with HOST index buffers (pinned or pageable) -- what a reference-side caller holding a CPU Batch would pass
- * (Batch::to, data/batch.cpp:21-60, moves exactly these tensors): copies unique_ids / edges / negatives to the device on
- * `stream`, runs mb_train_step, copies the loss back into *loss_host and synchronises the stream.          */
+ * (Batch::to, data/batch.cpp:21-60, moves exactly these tensors): copies unique_ids / edges / negatives to the device (on the
+ * context's copy stream, into one of two device slots, as Batch::to uses a pool stream; MB_H2D_PREFETCH=0 keeps the copies on
+ * `stream`), runs mb_train_step, copies the loss back into *loss_host and waits for the step.                                   */
 mb_status mb_train_step_host(mb_context* ctx, const mb_batch* host_batch, float* table, float* state_table, int64_t num_rows, int64_t ld,
                              const int64_t* unique_ids_host, float lr, int reduction, int precision, float* loss_host, float* rel_grad,
                              float* inv_rel_grad, void* stream);
