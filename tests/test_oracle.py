@@ -289,3 +289,34 @@ def test_filter_construction_against_reference_library():
         assert np.array_equal(O.compute_filter_corruption(edges[:, [0, 2]], all_nodes, inverse, graph_edges=graph[:, [0, 2]]),
                               R.compute_filter(edges[:, [0, 2]], all_nodes, inverse, graph_edges=graph[:, [0, 2]], num_nodes=num_nodes))
         assert np.array_equal(O.compute_filter_corruption(edges, negs, inverse), R.compute_filter(edges, negs, inverse))
+
+
+# ---- (7) size-independent properties of the integer / index work (the same properties the GPU tests check at full size) ----------
+@pytest.mark.parametrize("seed", range(5))
+def test_properties_ranks_filters_assembly(seed):
+    rng = np.random.default_rng(1000 + seed)
+    rows, N = int(rng.integers(1, 60)), int(rng.integers(1, 90))
+    neg = np.round(rng.standard_normal((rows, N)).astype(np.float32), 1)  # heavy ties
+    pos = np.round(rng.standard_normal(rows).astype(np.float32), 1)
+    ranks = O.compute_ranks(pos, neg)
+    assert ranks.min() >= 1 and ranks.max() <= N + 1
+    assert np.array_equal(ranks, O.compute_ranks(pos, neg[:, rng.permutation(N)]))            # order of the negatives is irrelevant
+    assert np.all(O.compute_ranks(pos + 1.0, neg) <= ranks)                                    # a better positive never ranks worse
+    F = int(rng.integers(0, rows * N))
+    filt = np.stack([rng.integers(0, rows, F), rng.integers(0, N, F)], axis=1).astype(np.int64)
+    once = O.apply_score_filter(neg.copy(), filt)
+    assert np.array_equal(once, O.apply_score_filter(once.copy(), filt))                       # idempotent
+    assert np.all(O.compute_ranks(pos, once) <= ranks)                                         # filtering never worsens a rank
+    full = np.stack([np.repeat(np.arange(rows), N), np.tile(np.arange(N), rows)], axis=1)
+    assert np.all(O.compute_ranks(pos, O.apply_score_filter(neg.copy(), full)) == 1)           # everything filtered -> rank 1
+    # batch assembly round trip: local ids index the sorted unique list back to the global ids, for both edge widths
+    num_nodes, B, C, Nn = int(rng.integers(2, 500)), int(rng.integers(1, 200)), int(rng.integers(1, 4)), int(rng.integers(1, 50))
+    edges = np.stack([rng.integers(0, num_nodes, B), rng.integers(0, 5, B), rng.integers(0, num_nodes, B)], axis=1).astype(np.int64)
+    sn, dn = O.sample_negatives(num_nodes, C, Nn, seed, 0, True), O.sample_negatives(num_nodes, C, Nn, seed, 0, False)
+    uniq, local, s_loc, d_loc = O.edge_sample(edges, sn, dn)
+    assert np.all(np.diff(uniq) > 0) and uniq.min() >= 0 and uniq.max() < num_nodes
+    assert np.array_equal(uniq[local[:, 0]], edges[:, 0]) and np.array_equal(uniq[local[:, 2]], edges[:, 2]) and np.array_equal(local[:, 1], edges[:, 1])
+    assert np.array_equal(uniq[s_loc], sn) and np.array_equal(uniq[d_loc], dn)
+    assert len(uniq) == len(set(edges[:, 0]) | set(edges[:, 2]) | set(sn.reshape(-1)) | set(dn.reshape(-1)))
+    u2, l2, s2, d2 = O.edge_sample(edges[:, [0, 2]], None, dn)
+    assert s2 is None and np.array_equal(u2[l2[:, 0]], edges[:, 0]) and np.array_equal(u2[l2[:, 1]], edges[:, 2]) and np.array_equal(u2[d2], dn)
