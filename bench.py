@@ -203,6 +203,8 @@ def cpu_reference_run(steps, warmup, B, num_nodes, seed=0):
     state = np.zeros((num_nodes, D), np.float32)
     batches, C = make_batches(rng, num_nodes, max(steps, 1), B)
     if R.available():
+        # torchrun exports OMP_NUM_THREADS=1 to every rank: the CPU arm must use all host cores whatever launched it
+        R.set_num_threads(os.cpu_count() or 1)
         uniq = np.concatenate([b[0] for b in batches])
         off = np.zeros(len(batches) + 1, np.int64)
         off[1:] = np.cumsum([len(b[0]) for b in batches])
@@ -244,6 +246,185 @@ def run_reference_arm(args):
                 e2e=dict(value=res["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ------------------------------------------------------------------------------------------------------ parity (checker, never timed)
+PARITY_TOL = 1e-4
+
+
+def _errs(a, b):
+    """(max|a-b| / max|b|,  max elementwise |a-b| / max(|b|, tau)) with tau = rms(b) -- the tau SURVEY.md 8d asks to be stated."""
+    a, b = np.asarray(a, np.float64).reshape(-1), np.asarray(b, np.float64).reshape(-1)
+    if b.size == 0:
+        return 0.0, 0.0
+    diff = np.abs(a - b)
+    tau = max(float(np.sqrt(np.mean(b * b))), 1e-30)
+    return float(diff.max() / max(np.abs(b).max(), 1e-30)), float((diff / np.maximum(np.abs(b), tau)).max())
+
+
+def parity_single(ops, ctx, dev, prec, B, rows=2_000_000, seed=11, rel_tables=None):
+    """One bench-shape batch (B positives, C = B/1000 chunks, 1000 negatives, ComplEx d=400, both sides) on a `rows`-row table, through the
+    C ABI (mb_edge_sample -> mb_gather_rows -> mb_decoder_forward -> mb_train_step) against oracle/_ref = the reference's own
+    map_tensors / InMemory::indexRead / Model::forward_lp / Model::train_batch (model.cpp:290-333, storage.cpp:606-673).  Outside every timed region."""
+    import torch
+
+    from oracle import marius_oracle as O
+    from oracle import ref_lib as R
+
+    if not R.available():
+        return dict(checked=False, why="oracle/_ref not built")
+    R.set_num_threads(os.cpu_count() or 1)
+    C = max(B // CHUNK, 1)
+    rng = np.random.default_rng(seed)
+    table_h = rng.uniform(-0.1, 0.1, (rows, D)).astype(np.float32)
+    state_h = (rng.uniform(0, 1, (rows, D)) < 0.25).astype(np.float32) * rng.uniform(0, 0.5, (rows, D)).astype(np.float32)  # part of the rows already trained
+    if rel_tables is None:
+        rel_h = rng.uniform(-1, 1, (NUM_REL, D)).astype(np.float32)
+        inv_h = rng.uniform(-1, 1, (NUM_REL, D)).astype(np.float32)
+    else:
+        rel_h, inv_h = rel_tables
+    src = rng.integers(0, rows, size=B, dtype=np.int64)
+    dst = rng.integers(0, rows, size=B, dtype=np.int64)
+    relid = rng.integers(0, NUM_REL, size=B, dtype=np.int64)
+    sn = rng.integers(0, rows, size=(C, NEG), dtype=np.int64)
+    dn = rng.integers(0, rows, size=(C, NEG), dtype=np.int64)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = dict(checked=True, tol=PARITY_TOL, shape=f"ComplEx d={D} B={B} C={C} N={NEG}, table {rows} rows", oracle="oracle/_ref (reference C++)",
+               tau="elementwise error = |a-b| / max(|b|, rms(b)); global error = max|a-b| / max|b|")
+    # (1) unique-id mapping: bit-exact
+    raw_edges = np.ascontiguousarray(np.stack([src, relid, dst], axis=1))
+    uq_d, num_d, e_loc, s_loc, d_loc = ops.edge_sample(ctx, t(raw_edges), t(sn), t(dn), rows)
+    U = int(num_d.item())
+    uq_ref, inv = R.map_tensors(np.concatenate([src, dst, sn.reshape(-1), dn.reshape(-1)]))
+    e_ref = np.ascontiguousarray(np.stack([inv[:B], relid, inv[B:2 * B]], axis=1))
+    sn_ref = np.ascontiguousarray(inv[2 * B:2 * B + C * NEG].reshape(C, NEG))
+    dn_ref = np.ascontiguousarray(inv[2 * B + C * NEG:].reshape(C, NEG))
+    out["unique_ids_bit_exact"] = bool(U == len(uq_ref) and np.array_equal(uq_d[:U].cpu().numpy(), uq_ref) and np.array_equal(e_loc.cpu().numpy(), e_ref)
+                                       and np.array_equal(s_loc.cpu().numpy(), sn_ref) and np.array_equal(d_loc.cpu().numpy(), dn_ref))
+    out["unique_rows"] = U
+    uq = uq_d[:U].contiguous()
+    # (2) gathered rows: bit-exact
+    table, state = t(table_h), t(state_h)
+    emb_d, st_d = ops.gather_rows(table, uq), ops.gather_rows(state, uq)
+    emb_ref, st_ref = R.index_read(table_h, uq_ref), R.index_read(state_h, uq_ref)
+    out["gathered_rows_bit_exact"] = bool(np.array_equal(emb_d.cpu().numpy(), emb_ref) and np.array_equal(st_d.cpu().numpy(), st_ref))
+    # (3) scores, loss, deltas: the reference's Model::train_batch on the gathered rows
+    ref = R.train_batch(O.COMPLEX, emb_ref, st_ref, e_ref, rel_h, inv_h, dn_ref, sn_ref, LR, O.REDUCTION_SUM)
+    rel, inv_rel = t(rel_h), t(inv_h)
+    pos, neg, ipos, ineg = ops.decoder_forward(ctx, ops.COMPLEX, emb_d, e_loc, rel, inv_rel, d_loc, s_loc, prec)
+    for name, a, b in (("pos", pos, ref["pos"]), ("neg", neg, ref["neg"]), ("inv_pos", ipos, ref["inv_pos"]), ("inv_neg", ineg, ref["inv_neg"])):
+        g, e = _errs(a.cpu().numpy(), b)
+        out[f"{name}_err"] = g
+        out[f"{name}_err_elementwise"] = e
+    del pos, neg, ipos, ineg
+    # (4) the fused step on the table: loss, relation gradients, updated table / state rows, deltas
+    rg, irg = torch.empty_like(rel), torch.empty_like(inv_rel)
+    loss = ops.train_step(ctx, ops.COMPLEX, table, state, uq, e_loc, rel, inv_rel, d_loc, s_loc, LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
+    torch.cuda.synchronize()
+    out["loss_err"] = abs(float(loss.item()) - float(ref["loss"][0])) / abs(float(ref["loss"][0]))
+    new_e, new_s = ops.gather_rows(table, uq).cpu().numpy(), ops.gather_rows(state, uq).cpu().numpy()
+    out["delta_e_err"], out["delta_e_err_elementwise"] = _errs(new_e - emb_ref, ref["delta_e"])
+    out["delta_s_err"], out["delta_s_err_elementwise"] = _errs(new_s - st_ref, ref["delta_s"])
+    out["updated_rows_err"], out["updated_rows_err_elementwise"] = _errs(new_e, emb_ref + ref["delta_e"])
+    out["updated_state_err"], out["updated_state_err_elementwise"] = _errs(new_s, st_ref + ref["delta_s"])
+    out["rel_grad_err"] = _errs(rg.cpu().numpy(), ref["rel_grad"])[0]
+    out["inv_rel_grad_err"] = _errs(irg.cpu().numpy(), ref["inv_rel_grad"])[0]
+    # untouched rows stay bit-identical
+    mask = np.ones(rows, bool)
+    mask[uq_ref] = False
+    probe = np.flatnonzero(mask)[:: max(1, rows // 4096)]
+    out["untouched_rows_bit_exact"] = bool(np.array_equal(table[torch.from_numpy(probe).to(dev)].cpu().numpy(), table_h[probe]))
+    keys = [k for k in out if k.endswith("_err")]
+    out["max_err"] = max(out[k] for k in keys)
+    out["ok"] = bool(out["unique_ids_bit_exact"] and out["gathered_rows_bit_exact"] and out["untouched_rows_bit_exact"] and out["max_err"] <= PARITY_TOL)
+    del table, state
+    return out
+
+
+def parity_sharded(ops, ctx, dev, prec, rank, world, rows=65536, B=2000, seed=23, overlap=True):
+    """N > 1: one step of the sharded path at d=400 / 1000 negatives per chunk inside the bench's process group, on separate small
+    shards.  Every rank draws its batch over the WHOLE global id space (overlap=True: the batches of different ranks share rows), all
+    ranks step once, and every rank compares ITS shard with the expectation built from oracle/_ref gradients of every rank's batch on
+    the pre-step table, applied in the order the sharded step defines: the owner's own contribution first, then the
+    senders' in rank order, each as one sparse-Adagrad step (batch.cpp:62-79)."""
+    import torch
+    import torch.distributed as dist
+
+    from marius_b200.dist import PeerShardedTable
+    from oracle import marius_oracle as O
+    from oracle import ref_lib as R
+
+    if not R.available():
+        return dict(checked=False, why="oracle/_ref not built")
+    R.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+    C = max(B // CHUNK, 1)
+    total = rows * world
+    rng = np.random.default_rng(seed)
+    full = rng.uniform(-0.1, 0.1, (total, D)).astype(np.float32)
+    full_s = (rng.uniform(0, 1, (total, D)) < 0.25).astype(np.float32) * rng.uniform(0, 0.5, (total, D)).astype(np.float32)
+    rel_h = rng.uniform(-1, 1, (NUM_REL, D)).astype(np.float32)
+    inv_h = rng.uniform(-1, 1, (NUM_REL, D)).astype(np.float32)
+    batches = []
+    for r in range(world):
+        brng = np.random.default_rng(seed + 100 + r)
+        if overlap:
+            pool = brng.integers(0, total, size=3 * B, dtype=np.int64)  # a small pool per rank + a pool shared by all ranks: plenty of shared rows
+            shared = np.random.default_rng(seed + 99).integers(0, total, size=B, dtype=np.int64)
+            pool = np.concatenate([pool, shared])
+            pick = lambda size: pool[brng.integers(0, len(pool), size=size)]
+        else:
+            pick = lambda size: brng.integers(0, total // world, size=size, dtype=np.int64) * world + r
+        src, dst, relid = pick(B), pick(B), brng.integers(0, NUM_REL, size=B, dtype=np.int64)
+        sn, dn = pick((C, NEG)), pick((C, NEG))
+        uniq, inv = O.map_tensors(np.concatenate([src, dst, sn.reshape(-1), dn.reshape(-1)]))
+        edges = np.ascontiguousarray(np.stack([inv[:B], relid, inv[B:2 * B]], axis=1))
+        batches.append((uniq, edges, np.ascontiguousarray(inv[2 * B + C * NEG:].reshape(C, NEG)), np.ascontiguousarray(inv[2 * B:2 * B + C * NEG].reshape(C, NEG))))
+    lo, hi = rank * rows, (rank + 1) * rows
+    table = torch.from_numpy(full[lo:hi].copy()).to(dev)
+    state = torch.from_numpy(full_s[lo:hi].copy()).to(dev)
+    pctx = ops.Context(dev.index)
+    pst = PeerShardedTable(table, state, pctx)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    uniq, edges, dn, sn = batches[rank]
+    rel, inv_rel = t(rel_h), t(inv_h)
+    rg, irg = torch.empty_like(rel), torch.empty_like(inv_rel)
+    loss = pst.train_step(ops.COMPLEX, t(uniq), t(edges), rel, inv_rel, t(dn), t(sn), LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
+    torch.cuda.synchronize()
+    dist.barrier()
+    # expectation for MY shard: gradients of every rank's batch on the pre-step table (reference C++), contributions in the defined order
+    exp_t, exp_s = full[lo:hi].copy(), full_s[lo:hi].copy()
+    my_loss = None
+    contrib = {}
+    for r, (u, e, dnn, snn) in enumerate(batches):
+        res = R.train_batch(O.COMPLEX, np.ascontiguousarray(full[u]), np.ascontiguousarray(full_s[u]), e, rel_h, inv_h, dnn, snn, LR, O.REDUCTION_SUM)
+        if r == rank:
+            my_loss = float(res["loss"][0])
+        mine = (u >= lo) & (u < hi)
+        contrib[r] = (u[mine] - lo, res["grad"][mine])
+    shared_rows = 0
+    order = [rank] + [r for r in range(world) if r != rank]
+    seen = np.zeros(rows, np.int32)
+    for r in order:
+        idx, g = contrib[r]
+        seen[idx] += 1
+        s_new = exp_s[idx] + g * g                                 # batch.cpp:67-69
+        exp_t[idx] = exp_t[idx] + (-LR * g / (np.sqrt(s_new) + np.float32(1e-10))).astype(np.float32)
+        exp_s[idx] = s_new
+    shared_rows = int((seen > 1).sum())
+    got_t, got_s = table.cpu().numpy(), state.cpu().numpy()
+    et, es = _errs(got_t, exp_t)[0], _errs(got_s, exp_s)[0]
+    el = abs(float(loss.item()) - my_loss) / abs(my_loss)
+    remote = int(((uniq // rows) != rank).sum())
+    vals = torch.tensor([et, es, el, float(remote), float(shared_rows)], device=dev, dtype=torch.float64)
+    gathered = [torch.zeros_like(vals) for _ in range(world)]
+    dist.all_gather(gathered, vals)
+    per_rank = [dict(rank=i, table_err=float(g[0]), state_err=float(g[1]), loss_err=float(g[2]), remote_rows=int(g[3]), rows_updated_by_several_ranks=int(g[4]))
+                for i, g in enumerate(gathered)]
+    mx = max(max(p["table_err"], p["state_err"], p["loss_err"]) for p in per_rank)
+    del pst
+    return dict(checked=True, tol=PARITY_TOL, shape=f"ComplEx d={D} B={B} C={C} N={NEG}, {world} shards x {rows} rows, batches over the whole id space"
+                + (" (rows shared between ranks)" if overlap else " (disjoint rows per rank)"), oracle="oracle/_ref gradients + ordered owner-side Adagrad",
+                per_rank=per_rank, max_err=mx, ok=bool(mx <= PARITY_TOL and all(p["remote_rows"] > 0 for p in per_rank)))
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
@@ -477,6 +658,20 @@ def run_ours(args):
         except Exception as ex:  # the baseline is reported, never required
             cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="unavailable", sample=str(ex)[:200])
 
+    # ---- parity (outside every timed region): the measured path against the reference's CPU path, at the bench shape (N = 1) or through the
+    # sharded protocol inside this process group (N > 1)
+    parity = None
+    if not args.no_parity:
+        try:
+            if world == 1:
+                parity = parity_single(ops, ctx, dev, prec, B, rows=min(args.ref_nodes, rows))
+            else:
+                parity = parity_sharded(ops, ctx, dev, prec, rank, world, overlap=not args.parity_disjoint)
+        except Exception as ex:  # a failed check is reported as such, never hidden
+            parity = dict(checked=False, ok=False, why=f"{type(ex).__name__}: {ex}"[:300])
+            if world > 1:
+                raise
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=step_ms, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -494,7 +689,7 @@ def run_ours(args):
                                 unique_rows_per_step=U_mean, step_hbm_gbs_algorithmic=step_hbm, step_hbm_frac=step_hbm / pk["hbm_gbs"],
                                 stage_ms={k: round(v, 4) for k, v in per_stage.items()}, stage_sum_ms=step_stage_ms, last_loss=last_loss),
                     clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4), gpu_launches=int(launches),
-                    roofline=roof, cpu_baseline=cpu, impl="marius_b200")
+                    roofline=roof, cpu_baseline=cpu, parity=parity, impl="marius_b200")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -517,6 +712,8 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=24, help="--impl reference: upper bound on the timed CPU batches")
     ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (one bench-shape batch against the reference's CPU path, untimed)")
+    ap.add_argument("--parity-disjoint", action="store_true", help="N > 1 parity: give every rank disjoint rows (no row updated by two ranks)")
     ap.add_argument("--gpu-sync-interval", type=int, default=16,
                     help="N > 1: all-reduce the dense relation gradients every this many batches (the reference's gpu_sync_interval, default 16)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],

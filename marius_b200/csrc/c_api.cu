@@ -78,6 +78,7 @@ struct mb_context {
     cudaStream_t copy = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
     float* h_loss = nullptr;
+    int* d_flag = nullptr;           // persistent device error flag (score-filter range check): checked once per evaluate call
     float* h_loss_pinned = nullptr;  // two pinned host landing slots of the step's loss, used alternately (mb_train_step_host_async keeps
                                      // one step in flight while the caller reads the previous step's loss)
     int loss_slot = 0;
@@ -176,19 +177,6 @@ struct StageTimer {
     }
 };
 
-// tcgen05 tile configuration (gemm_tc.cu): 256 = BLOCK_N 256 / BLOCK_K 32 / 4 stages (default), 2560 = 256 / 64 / 2, 128 = 128 / 64 / 3,
-// 512 / 5120 = 2-CTA pairs (cta_group::2) with BLOCK_K 64 / 3 stages or BLOCK_K 32 / 6 stages,
-// 1024 (default) = grouped, table-scheduled 2-CTA kernel (gemm_tc_group.cu): dA and dNeg share one launch.
-// MB_TC_CFG overrides it for A/B measurements.
-static int tc_tile_config() {
-    static int cfg = [] {
-        const char* e = getenv("MB_TC_CFG");
-        int v = e ? atoi(e) : 1024;
-        return (v == 256 || v == 2560 || v == 128 || v == 512 || v == 5120 || v == 1024) ? v : 1024;
-    }();
-    return cfg;
-}
-
 static int bits_for(uint64_t max_value) {
     int b = 1;
     while (b < 64 && (max_value >> b) != 0) b++;
@@ -285,13 +273,10 @@ static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
     p.Ng = p.use_tc ? ((int64_t)p.N + 63) / 64 * 64 : p.N;
 }
 
-static mb_status tc_contract(int cfg, const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb,
+static mb_status tc_contract(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb,
                              int64_t sBb, bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, cudaStream_t st) {
-    if (cfg == 1024) {
-        TcGroupProblem g{A_hi, A_lo, lda, sAb, a_mn ? 1 : 0, B_hi, B_lo, ldb, sBb, b_mn ? 1 : 0, D, ldd, sDb, M, N, K, batches};
-        return gemm_tc_grouped(&g, 1, passes, st);
-    }
-    return gemm_tc(A_hi, A_lo, lda, sAb, a_mn, B_hi, B_lo, ldb, sBb, b_mn, D, ldd, sDb, M, N, K, batches, passes, cfg, st);
+    TcGroupProblem g{A_hi, A_lo, lda, sAb, a_mn ? 1 : 0, B_hi, B_lo, ldb, sBb, b_mn ? 1 : 0, D, ldd, sDb, M, N, K, batches};
+    return gemm_tc_grouped(&g, 1, passes, st);
 }
 
 // forward: adjusted rows A, positive scores, negative rows, score GEMM.  S0/S1 are the score outputs per side ([Bp,N] each).
@@ -320,7 +305,7 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
         float* S = l == 0 ? S0 : S1;
         int64_t aoff = (int64_t)l * p.Bp * d, noff = (int64_t)l * p.CN * d;
         if (p.use_tc) {
-            MB_TRY(tc_contract(tc_tile_config(), p.A_hl + aoff, p.A_hl + a_half + aoff, d, p.Bc * d, false, p.Neg_hl + noff, p.Neg_hl + n_half + noff, d,
+            MB_TRY(tc_contract(p.A_hl + aoff, p.A_hl + a_half + aoff, d, p.Bc * d, false, p.Neg_hl + noff, p.Neg_hl + n_half + noff, d,
                                (int64_t)p.N * d, false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, st));
         } else {
             MB_TRY(gemm_simt(p.A + aoff, d, 1, p.Bc * d, p.NegE + noff, 1, d, (int64_t)p.N * d, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, st));
@@ -465,10 +450,9 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     }
     const int passes = precision == MB_PREC_BF16 ? 1 : 3;
     const int batches = p.sides * p.C;
-    const int tc_cfg = tc_tile_config();
     bool dneg_forked = false;
     float* gneg = p.gcat + 2 * p.B * d;  // d dst_negs | d src_negs, [sides][C][N][d]
-    if (p.Bc > 0 && p.use_tc && tc_cfg == 1024) {
+    if (p.Bc > 0 && p.use_tc) {
         // dA = G . Neg and dNeg = G^T . A in ONE grouped, cost-balanced persistent launch (gemm_tc_group.cu)
         const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
         StageTimer tm(ctx, ST_GEMM_DA, st);
@@ -477,10 +461,8 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
             {p.G_hl, p.G_hl + g_half, p.Ng, p.Bc * p.Ng, 1, p.A_hl, p.A_hl + a_half, d, p.Bc * d, 1, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches}};
         MB_TRY(gemm_tc_grouped(g, 2, passes, st));
     } else if (p.Bc > 0) {
-        const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
         {
-            // dNeg = G^T . A : independent of dA / edge_backward, so it runs on the second side stream; the tail wave of one persistent
-            // GEMM then overlaps the head of the other (each has only ~2.2 waves of tiles at B = 10k)
+            // fp32 FFMA path.  dNeg = G^T . A is independent of dA / edge_backward, so it runs on the second side stream
             cudaStream_t s2 = overlap ? ctx->side2 : st;
             if (overlap) {
                 MB_CUDA_TRY(cudaEventRecord(ctx->ev_fork2, st));
@@ -488,20 +470,12 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
                 dneg_forked = true;
             }
             StageTimer tm(ctx, ST_GEMM_DNEG, s2);
-            if (p.use_tc)
-                MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.Ng, p.Bc * p.Ng, true, p.A_hl, p.A_hl + a_half, d, p.Bc * d, true, gneg, d, (int64_t)p.N * d,
-                               p.N, d, (int)p.Bc, batches, passes, tc_cfg, s2));
-            else
-                MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, s2));
+            MB_TRY(gemm_simt(p.S, 1, p.N, p.Bc * p.N, p.A, d, 1, p.Bc * d, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches, s2));
             if (overlap) MB_CUDA_TRY(cudaEventRecord(ctx->ev_join2, s2));
         }
         {
             StageTimer tm(ctx, ST_GEMM_DA, st);  // dA = G . Neg
-            if (p.use_tc)
-                MB_TRY(gemm_tc(p.G_hl, p.G_hl + g_half, p.Ng, p.Bc * p.Ng, false, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, true, p.dA, d,
-                               p.Bc * d, (int)p.Bc, d, p.N, batches, passes, tc_cfg, st));
-            else
-                MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
+            MB_TRY(gemm_simt(p.S, p.N, 1, p.Bc * p.N, p.NegE, d, 1, (int64_t)p.N * d, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches, st));
         }
     } else {
         MB_CUDA_TRY(cudaMemsetAsync(gneg, 0, sizeof(float) * 2 * p.CN * d, st));
@@ -580,6 +554,7 @@ mb_status mb_create(int device, mb_context** out) {
     mb_context* c = new mb_context();
     c->device = device;
     cudaError_t e = cudaMalloc(&c->h_loss, sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_flag, sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_loss_pinned, 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copied[0], cudaEventDisableTiming);
@@ -627,6 +602,7 @@ void mb_destroy(mb_context* ctx) {
     }
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     if (ctx->h_loss) cudaFree(ctx->h_loss);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
     for (auto& ev : ctx->ev_loss)
         if (ev) cudaEventDestroy(ev);
@@ -1034,11 +1010,26 @@ mb_status mb_evaluate_batch(mb_context* ctx, const mb_batch* batch, const float*
     if (p.Bc == 0) {  // no positives: nothing to rank
         return MB_OK;
     }
-    MB_TRY(filter_checked(p.S, p.Bp, p.N, p.N, dst_filter, Fd, st));
+    // both filters report out-of-range indices through the context's persistent flag: one read-back per call, no allocation
+    const bool any_filter = Fd > 0 || (p.sides == 2 && Fs > 0);
+    if (any_filter) MB_CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
+    if (Fd > 0) {
+        MB_REQUIRE(dst_filter != nullptr, "null filter");
+        MB_TRY(launch_score_filter(p.S, p.Bp, p.N, p.N, dst_filter, Fd, ctx->d_flag, st));
+    }
     MB_TRY(launch_ranks(p.pos, p.S, p.Bp, p.N, p.N, ranks, st));
     if (p.sides == 2) {
-        MB_TRY(filter_checked(S1, p.Bp, p.N, p.N, src_filter, Fs, st));
+        if (Fs > 0) {
+            MB_REQUIRE(src_filter != nullptr, "null filter");
+            MB_TRY(launch_score_filter(S1, p.Bp, p.N, p.N, src_filter, Fs, ctx->d_flag, st));
+        }
         MB_TRY(launch_ranks(p.pos + p.Bp, S1, p.Bp, p.N, p.N, inv_ranks, st));
+    }
+    if (any_filter) {
+        int host_flag = 0;
+        MB_CUDA_TRY(cudaMemcpyAsync(&host_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MB_CUDA_TRY(cudaStreamSynchronize(st));
+        MB_REQUIRE(host_flag == 0, "score filter index out of range");
     }
     if (pos) MB_CUDA_TRY(cudaMemcpyAsync(pos, p.pos, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
     if (inv_pos && p.sides == 2) MB_CUDA_TRY(cudaMemcpyAsync(inv_pos, p.pos + p.Bp, sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
@@ -1092,7 +1083,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     Plan probe;
     fill_plan_dims(probe, ub, precision);
     const bool vec = decoder_vec_ok(table, ld, (int)ub->d, probe.has_rel, ub->rel, probe.sides == 2 ? ub->inv_rel : nullptr, probe.sides);
-    const bool eligible = graphs_on(ctx) && vec && probe.use_tc && tc_tile_config() == 1024 && ub->B > 0 && ub->U <= cap_u;
+    const bool eligible = graphs_on(ctx) && vec && probe.use_tc && ub->B > 0 && ub->U <= cap_u;
     if (!eligible && !host_inputs && loss_host == nullptr) {
         return run_train(ctx, ub, nullptr, 0, nullptr, 0, table, state_table, ld, unique_ids, lr, reduction, precision, loss_dev, nullptr, nullptr, nullptr,
                          rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh);
@@ -1159,7 +1150,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
         if (ctx->sg.warm == 0) {
             // first sight of this signature: run eagerly (allocations, cudaFuncSetAttribute, tile tables happen here, outside capture)
             ctx->sg.warm = 1;
-            MB_CUDA_TRY(cudaMemsetAsync(ctx->g_uniq, 0, sizeof(int64_t) * cap_u, st));
+            MB_CUDA_TRY(cudaMemsetAsync(ctx->g_uniq, 0xFF, sizeof(int64_t) * cap_u, st));  // ids beyond U = -1 (padding)
             MB_TRY(stage_inputs());
             MB_TRY(run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr,
                              nullptr, nullptr, rel_grad, inv_rel_grad, UpdateMode::kFusedTable, st, nullptr, sh));
@@ -1171,11 +1162,14 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
         MB_CUDA_TRY(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
         mb_status rs = MB_OK;
         {
+            // the graph runs with U = capacity: every replay first resets the id staging buffer to -1, so the entries beyond this batch's
+            // U are padding (never a stale id of an earlier batch, which the sharded step would fetch over NVLink for nothing)
+            cudaError_t c0 = cudaMemsetAsync(ctx->g_uniq, 0xFF, sizeof(int64_t) * cap_u, gs);
             cudaError_t c1 = cudaMemcpyAsync(ctx->g_uniq, unique_ids, sizeof(int64_t) * ub->U, kind, gs);
             cudaError_t c2 = cudaMemcpyAsync(ctx->g_edges, ub->edges, sizeof(int64_t) * n_e, kind, gs);
             cudaError_t c3 = cudaMemcpyAsync(ctx->g_dneg, ub->dst_negs, sizeof(int64_t) * n_n, kind, gs);
             cudaError_t c4 = has_sneg ? cudaMemcpyAsync(ctx->g_sneg, ub->src_negs, sizeof(int64_t) * n_n, kind, gs) : cudaSuccess;
-            if (c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess) rs = MB_ERR_CUDA;
+            if (c0 != cudaSuccess || c1 != cudaSuccess || c2 != cudaSuccess || c3 != cudaSuccess || c4 != cudaSuccess) rs = MB_ERR_CUDA;
         }
         if (rs == MB_OK)
             rs = run_train(ctx, &gb, nullptr, 0, nullptr, 0, table, state_table, ld, ctx->g_uniq, lr, reduction, precision, loss_target, nullptr, nullptr,
@@ -1217,7 +1211,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
             else if (dst == ctx->g_sneg) ctx->sg.n_sneg = nd;
             else if (loss_host && dst == loss_host) ctx->sg.n_loss = nd;
         }
-        if (!ctx->sg.n_uniq || !ctx->sg.n_edges || !ctx->sg.n_dneg || (has_sneg && !ctx->sg.n_sneg)) {
+        if (!ctx->sg.n_uniq || !ctx->sg.n_edges || !ctx->sg.n_dneg || (has_sneg && !ctx->sg.n_sneg) || (loss_host && !ctx->sg.n_loss)) {
             cudaGraphExecDestroy(exec);
             cudaGraphDestroy(graph);
             ctx->graphs_enabled = 0;
@@ -1233,7 +1227,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_edges, ctx->g_edges, ub->edges, sizeof(int64_t) * n_e, kind));
     MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_dneg, ctx->g_dneg, ub->dst_negs, sizeof(int64_t) * n_n, kind));
     if (has_sneg) MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_sneg, ctx->g_sneg, ub->src_negs, sizeof(int64_t) * n_n, kind));
-    if (loss_host && ctx->sg.n_loss)  // the loss lands in this call's slot
+    if (loss_host)  // the loss lands in this call's slot
         MB_CUDA_TRY(cudaGraphExecMemcpyNodeSetParams1D(ctx->sg.exec, ctx->sg.n_loss, loss_host, loss_target, sizeof(float), cudaMemcpyDeviceToHost));
     MB_CUDA_TRY(cudaEventRecord(ctx->ev_in, st));
     MB_CUDA_TRY(cudaStreamWaitEvent(ctx->gstream, ctx->ev_in, 0));
@@ -1377,7 +1371,8 @@ mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* 
     __nv_bfloat16* b_hl = place.take<__nv_bfloat16>(2 * nb);
     MB_TRY(launch_split(A, na, a_hl, a_hl + na, st));
     MB_TRY(launch_split(B, nb, b_hl, b_hl + nb, st));
-    return tc_contract(block_n, a_hl, a_hl + na, a_mn ? M : K, (int64_t)M * K, a_mn != 0, b_hl, b_hl + nb, b_mn ? N : K, (int64_t)N * K, b_mn != 0, D, N,
+    (void)block_n;  // (kept in the ABI; there is one tensor-core kernel)
+    return tc_contract(a_hl, a_hl + na, a_mn ? M : K, (int64_t)M * K, a_mn != 0, b_hl, b_hl + nb, b_mn ? N : K, (int64_t)N * K, b_mn != 0, D, N,
                        (int64_t)M * N, M, N, K, batches, precision == MB_PREC_BF16 ? 1 : 3, st);
 }
 

@@ -1,13 +1,15 @@
-// gemm_tc_group.cu -- grouped, table-scheduled 2-CTA tcgen05 GEMM.
+// gemm_tc_group.cu -- grouped, table-scheduled 2-CTA tcgen05 GEMM (the only tensor-core contraction kernel of the library).
 //
-// Same CTA-pair kernel as gemm_tc2_kernel (gemm_tc.cu) with two changes that matter at the named shape (ComplEx d=400,
-// 1000 negatives, batch 10k: each backward contraction has only 160 cluster tiles for 74 CTA pairs = 2.16 waves):
+// One persistent CTA pair per two SMs (cta_group::2), warp-specialised (TMA producer / MMA issuer / 4 epilogue warps), with two
+// properties that matter at the named shape (ComplEx d=400, 1000 negatives: each backward contraction has few cluster tiles per
+// CTA pair, 2.16 waves at batch 10k):
 //   (1) up to two independent problems (dA = G.Neg and dNeg = G^T.A) share ONE persistent launch: operand majors, shapes and
 //       tensor maps are per-problem run-time data, so the tail of one contraction is filled with tiles of the other;
 //   (2) tiles are handed out from a host-built table: tiles sorted by cost (ragged N tiles are cheaper), assigned to CTA pairs
 //       in snake order (longest-processing-time-first), so every pair gets the same work within one small tile.
 // All three warp roles read the same table entries, so no in-kernel tile broadcast is needed.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -351,6 +353,11 @@ std::mutex& table_mutex() {
 
 }  // namespace
 
+bool gemm_tc_supported(int64_t a_inner, int64_t b_inner) {
+    // TMA: 16-byte global strides => inner extents (bf16) multiples of 8
+    return (a_inner % 8 == 0) && (b_inner % 8 == 0) && encode_fn() != nullptr;
+}
+
 mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st) {
     if (n < 1 || n > 2) {
         set_error("gemm_tc_grouped: 1 or 2 problems");
@@ -526,10 +533,11 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     }
     p.table = tv.dev_ptr;
     p.rounds = tv.rounds;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // function attributes are per device (one process may drive several: the reference's device_models_): opt in once on each
+    static std::atomic<bool> attr_set[64];
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
         MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
     gemm_tc_group_kernel<<<2 * clusters, kTcThreads, G_SMEM_TOTAL, st>>>(maps, p);
     MB_LAUNCH_CHECK();

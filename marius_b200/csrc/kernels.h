@@ -76,12 +76,8 @@ mb_status launch_ranks(const float* pos, const float* neg, int64_t rows, int64_t
 mb_status gemm_simt(const float* A, int64_t sAm, int64_t sAk, int64_t sAb, const float* B, int64_t sBk, int64_t sBn, int64_t sBb, float* C, int64_t ldc,
                     int64_t sCb, int M, int N, int K, int batches, cudaStream_t st);
 
-// gemm_tc.cu
-bool gemm_tc_supported(int64_t a_inner, int64_t b_inner);
-mb_status gemm_tc(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb, int64_t sBb,
-                  bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, int block_n, cudaStream_t st);
-
 // gemm_tc_group.cu : up to two contractions in one table-scheduled persistent 2-CTA launch
+bool gemm_tc_supported(int64_t a_inner, int64_t b_inner);
 struct TcGroupProblem {
     const void *A_hi, *A_lo;
     int64_t lda, sAb;
