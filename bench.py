@@ -317,18 +317,37 @@ def parity_single(ops, ctx, dev, prec, B, rows=2_000_000, seed=11, rel_tables=No
         out[f"{name}_err"] = g
         out[f"{name}_err_elementwise"] = e
     del pos, neg, ipos, ineg
-    # (4) the fused step on the table: loss, relation gradients, updated table / state rows, deltas
+    # (4) Model::train_batch on the gathered rows: loss, node gradients, Adagrad deltas, relation gradients
+    tb = ops.train_batch(ctx, ops.COMPLEX, emb_d, st_d, e_loc, rel, inv_rel, d_loc, s_loc, LR, ops.REDUCTION_SUM, prec)
+    torch.cuda.synchronize()
+    out["loss_err"] = abs(float(tb["loss"].item()) - float(ref["loss"][0])) / abs(float(ref["loss"][0]))
+    out["grad_err"], out["grad_err_elementwise"] = _errs(tb["grad"].cpu().numpy(), ref["grad"])
+    out["delta_s_err"], out["delta_s_err_elementwise"] = _errs(tb["delta_s"].cpu().numpy(), ref["delta_s"])
+    # delta_e = -lr * g / (sqrt(s + g^2) + 1e-10) is DISCONTINUOUS in g where the state is 0 (first Adagrad step of a row: -lr * sign(g)), so an
+    # element whose reference gradient is within rounding noise of 0 can legitimately come out with the other sign.  Those elements
+    # (|g_ref| < 1e-3 rms(g_ref), counted below) are compared through g and delta_s only; every other element must match.
+    g_ref = ref["grad"]
+    cond = np.abs(g_ref) >= 1e-3 * float(np.sqrt(np.mean(g_ref.astype(np.float64) ** 2)))
+    de = tb["delta_e"].cpu().numpy()
+    out["delta_e_err"], out["delta_e_err_elementwise"] = _errs(de[cond], ref["delta_e"][cond])
+    out["delta_e_ill_conditioned_elements"] = int((~cond).sum())
+    out["delta_e_sign_flips_among_them"] = int((np.sign(de[~cond]) != np.sign(ref["delta_e"][~cond])).sum())
+    out["delta_e_elements"] = int(cond.size)
+    out["rel_grad_err"] = _errs(tb["rel_grad"].cpu().numpy(), ref["rel_grad"])[0]
+    out["inv_rel_grad_err"] = _errs(tb["inv_rel_grad"].cpu().numpy(), ref["inv_rel_grad"])[0]
+    # (5) the fused step on the table (mb_train_step: gather fused away, Adagrad + scatter fused into the update kernel) must leave exactly
+    # the rows `emb + delta_e`, `state + delta_s` of (4) behind, bit for bit, and report the same loss / relation gradients
     rg, irg = torch.empty_like(rel), torch.empty_like(inv_rel)
     loss = ops.train_step(ctx, ops.COMPLEX, table, state, uq, e_loc, rel, inv_rel, d_loc, s_loc, LR, ops.REDUCTION_SUM, prec, rel_grad=rg, inv_rel_grad=irg)
     torch.cuda.synchronize()
-    out["loss_err"] = abs(float(loss.item()) - float(ref["loss"][0])) / abs(float(ref["loss"][0]))
-    new_e, new_s = ops.gather_rows(table, uq).cpu().numpy(), ops.gather_rows(state, uq).cpu().numpy()
-    out["delta_e_err"], out["delta_e_err_elementwise"] = _errs(new_e - emb_ref, ref["delta_e"])
-    out["delta_s_err"], out["delta_s_err_elementwise"] = _errs(new_s - st_ref, ref["delta_s"])
-    out["updated_rows_err"], out["updated_rows_err_elementwise"] = _errs(new_e, emb_ref + ref["delta_e"])
+    new_e, new_s = ops.gather_rows(table, uq), ops.gather_rows(state, uq)
+    out["fused_step_equals_batch_step_bit_exact"] = bool(torch.equal(new_e, emb_d + tb["delta_e"]) and torch.equal(new_s, st_d + tb["delta_s"])
+                                                         and torch.equal(loss.reshape(-1), tb["loss"].reshape(-1)) and torch.equal(rg, tb["rel_grad"])
+                                                         and torch.equal(irg, tb["inv_rel_grad"]))
+    new_e, new_s = new_e.cpu().numpy(), new_s.cpu().numpy()
+    out["updated_rows_err"], out["updated_rows_err_elementwise"] = _errs(new_e[cond], (emb_ref + ref["delta_e"])[cond])
     out["updated_state_err"], out["updated_state_err_elementwise"] = _errs(new_s, st_ref + ref["delta_s"])
-    out["rel_grad_err"] = _errs(rg.cpu().numpy(), ref["rel_grad"])[0]
-    out["inv_rel_grad_err"] = _errs(irg.cpu().numpy(), ref["inv_rel_grad"])[0]
+    del tb
     # untouched rows stay bit-identical
     mask = np.ones(rows, bool)
     mask[uq_ref] = False
@@ -336,7 +355,8 @@ def parity_single(ops, ctx, dev, prec, B, rows=2_000_000, seed=11, rel_tables=No
     out["untouched_rows_bit_exact"] = bool(np.array_equal(table[torch.from_numpy(probe).to(dev)].cpu().numpy(), table_h[probe]))
     keys = [k for k in out if k.endswith("_err")]
     out["max_err"] = max(out[k] for k in keys)
-    out["ok"] = bool(out["unique_ids_bit_exact"] and out["gathered_rows_bit_exact"] and out["untouched_rows_bit_exact"] and out["max_err"] <= PARITY_TOL)
+    out["ok"] = bool(out["unique_ids_bit_exact"] and out["gathered_rows_bit_exact"] and out["untouched_rows_bit_exact"]
+                     and out["fused_step_equals_batch_step_bit_exact"] and out["max_err"] <= PARITY_TOL)
     del table, state
     return out
 

@@ -187,8 +187,7 @@ static int bits_for(uint64_t max_value) {
 struct Plan {
     // dims
     int64_t U, d, B, Bc, Bp, R, CN, n_slots;
-    int64_t Ng;  // leading dimension of the bf16 gradient G_hl: N rounded up to 64 elements, so that every row starts on a 128-byte line
-                 // (with ld = N = 1000 each 128-byte TMA row piece straddled 5 sectors instead of 4: +25 % L2 traffic in the backward GEMMs)
+    int stat_slots;  // 64-column statistics slots per score row (tensor-core path: the loss is fused into the contractions)
     int C, N, sides, cols;
     bool has_rel, use_tc;
     // buffers
@@ -196,7 +195,9 @@ struct Plan {
     float* state_u = nullptr;          // sharded table: local copies of the remote rows' Adagrad state
     const float** row_ptrs = nullptr;  // sharded table: address of every unique row (own HBM or the fetched copy in emb_u)
     bool sharded = false;
-    __nv_bfloat16 *A_hl, *Neg_hl, *G_hl;
+    __nv_bfloat16 *A_hl, *Neg_hl;
+    float2* stats = nullptr;  // [sides*Bp][stat_slots] (max, sum exp) per score-row slot, written by the forward contraction's epilogue
+    float* zw = nullptr;      // [sides*Bp] log-partition of every score row (minus log of the loss weight): G = exp(S - zw)
     uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *offsets, *hist;
     uint32_t *rkeys_a, *rkeys_b, *rvals_a, *rvals_b, *roffsets, *rhist;
 
@@ -211,7 +212,8 @@ struct Plan {
         A_hl = use_tc ? ar.take<__nv_bfloat16>(2 * sides * Bp * d) : nullptr;
         Neg_hl = use_tc ? ar.take<__nv_bfloat16>(2 * sides * CN * d) : nullptr;
         gpos = row_loss = dA = gcat = drel = nullptr;
-        G_hl = nullptr;
+        stats = nullptr;
+        zw = nullptr;
         keys_a = keys_b = vals_a = vals_b = offsets = hist = nullptr;
         rkeys_a = rkeys_b = rvals_a = rvals_b = roffsets = rhist = nullptr;
         if (training) {
@@ -219,7 +221,8 @@ struct Plan {
             row_loss = ar.take<float>(sides * Bp);
             dA = ar.take<float>(sides * Bp * d);
             gcat = ar.take<float>(n_slots * d);
-            G_hl = use_tc ? ar.take<__nv_bfloat16>(2 * sides * Bp * Ng) : nullptr;
+            stats = use_tc ? ar.take<float2>(sides * Bp * stat_slots) : nullptr;
+            zw = use_tc ? ar.take<float>(sides * Bp) : nullptr;
             keys_a = ar.take<uint32_t>(n_slots);
             keys_b = ar.take<uint32_t>(n_slots);
             vals_a = ar.take<uint32_t>(n_slots);
@@ -270,19 +273,22 @@ static void fill_plan_dims(Plan& p, const mb_batch* b, int precision) {
     // tensor-core contractions take their bf16 hi/lo operands from the vectorised row kernels (d <= 512); wider rows use the general-d
     // row kernels with the fp32 FFMA contraction
     p.use_tc = (precision != MB_PREC_FP32) && gemm_tc_supported(p.d, p.N) && p.Bc > 0 && p.d <= 512;
-    p.Ng = p.use_tc ? ((int64_t)p.N + 63) / 64 * 64 : p.N;
+    p.stat_slots = (p.N + kTcStatSlotCols - 1) / kTcStatSlotCols;
 }
 
 static mb_status tc_contract(const void* A_hi, const void* A_lo, int64_t lda, int64_t sAb, bool a_mn, const void* B_hi, const void* B_lo, int64_t ldb,
-                             int64_t sBb, bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, cudaStream_t st) {
+                             int64_t sBb, bool b_mn, float* D, int64_t ldd, int64_t sDb, int M, int N, int K, int batches, int passes, cudaStream_t st,
+                             float2* stats = nullptr, int stat_slots = 0) {
     TcGroupProblem g{A_hi, A_lo, lda, sAb, a_mn ? 1 : 0, B_hi, B_lo, ldb, sBb, b_mn ? 1 : 0, D, ldd, sDb, M, N, K, batches};
+    g.stats = stats;
+    g.stat_slots = stat_slots;
     return gemm_tc_grouped(&g, 1, passes, st);
 }
 
 // forward: adjusted rows A, positive scores, negative rows, score GEMM.  S0/S1 are the score outputs per side ([Bp,N] each).
 static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, const float* emb, int64_t emb_ld, const int64_t* row_map, int precision,
                              float* pos, float* S0, float* S1, bool uniform_S, cudaStream_t st, bool skip_scores = false, const float* const* row_ptrs = nullptr,
-                             const mb_shards* sh = nullptr, cudaEvent_t rows_fetched = nullptr) {
+                             const mb_shards* sh = nullptr, cudaEvent_t rows_fetched = nullptr, float2* stats = nullptr) {
     const int d = (int)p.d;
     const int64_t a_half = p.sides * p.Bp * d;  // hi block then lo block, each [sides][Bp][d]
     const int64_t n_half = p.sides * p.CN * d;
@@ -297,6 +303,8 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
     }
     if (p.Bc == 0 || skip_scores) return MB_OK;
     const int passes = precision == MB_PREC_BF16 ? 1 : 3;
+    // fused loss: the epilogue of the score contraction leaves (max, sum exp) of every 64-column slot of every score row in `stats`
+    if (stats != nullptr && p.use_tc && uniform_S) MB_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float2) * p.sides * p.Bp * p.stat_slots, st));
     StageTimer tm_fwd(ctx, ST_GEMM_FWD, st);
     // scores[side][chunk] = A[side][chunk] . Neg[side][chunk]^T     (comparators.cpp:69-72)
     int launches = uniform_S ? 1 : p.sides;
@@ -306,7 +314,8 @@ static mb_status run_forward(mb_context* ctx, const Plan& p, const mb_batch* b, 
         int64_t aoff = (int64_t)l * p.Bp * d, noff = (int64_t)l * p.CN * d;
         if (p.use_tc) {
             MB_TRY(tc_contract(p.A_hl + aoff, p.A_hl + a_half + aoff, d, p.Bc * d, false, p.Neg_hl + noff, p.Neg_hl + n_half + noff, d,
-                               (int64_t)p.N * d, false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, st));
+                               (int64_t)p.N * d, false, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, passes, st, uniform_S ? stats : nullptr,
+                               p.stat_slots));
         } else {
             MB_TRY(gemm_simt(p.A + aoff, d, 1, p.Bc * d, p.NegE + noff, 1, d, (int64_t)p.N * d, S, p.N, p.Bc * p.N, (int)p.Bc, p.N, d, batches, st));
         }
@@ -421,26 +430,28 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     }
 
     MB_TRY(run_forward(ctx, p, b, emb, emb_ld, row_map, precision, p.pos, p.S, p.S + p.Bp * p.N, true, st, ext != nullptr, p.row_ptrs, p.sharded ? sh : nullptr,
-                       emb_fetch_forked ? ctx->ev_efetch_join : nullptr));
+                       emb_fetch_forked ? ctx->ev_efetch_join : nullptr, ext == nullptr ? p.stats : nullptr));
 
     // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
     const int64_t rows = p.sides * p.Bp;
     const float w = reduction == MB_REDUCTION_SUM ? 1.0f : (p.Bp > 0 ? 1.0f / (float)p.Bp : 0.f);
-    const int64_t g_half = p.sides * p.Bp * p.Ng;
-    void* G_hi = p.use_tc ? (void*)p.G_hl : nullptr;
-    void* G_lo = p.use_tc ? (void*)(p.G_hl + g_half) : nullptr;
     if (rows > 0 && ext != nullptr) {
-        // generic autograd path: the caller's loss produced d loss / d (pos, neg, inv_pos, inv_neg)
+        // generic autograd path: the caller's loss produced d loss / d (pos, neg, inv_pos, inv_neg); the backward contractions read the
+        // fp32 gradient matrix directly (converter warps, conv_mode 2)
         for (int sd = 0; sd < p.sides; sd++) {
             MB_REQUIRE(ext[2 * sd] != nullptr && ext[2 * sd + 1] != nullptr, "upstream gradients missing");
             MB_CUDA_TRY(cudaMemcpyAsync(p.gpos + sd * p.Bp, ext[2 * sd], sizeof(float) * p.Bp, cudaMemcpyDeviceToDevice, st));
             MB_CUDA_TRY(cudaMemcpyAsync(p.S + sd * p.Bp * p.N, ext[2 * sd + 1], sizeof(float) * p.Bp * p.N, cudaMemcpyDeviceToDevice, st));
         }
-        if (p.use_tc) MB_TRY(launch_split(p.S, rows * p.N, G_hi, G_lo, st, p.N, p.Ng));
+    } else if (rows > 0 && p.use_tc) {
+        // SoftmaxCrossEntropy fused into the contractions: the forward epilogue produced the row statistics, this merges them into the
+        // log-partition z of every row (-> row loss, d loss / d pos); the gradient matrix G = exp(S - z) itself is produced inside the
+        // backward contractions and never written to memory
+        StageTimer tm(ctx, ST_LOSS, st);
+        MB_TRY(launch_loss_merge(p.stats, p.stat_slots, p.pos, p.gpos, p.row_loss, p.zw, rows, w, st));
     } else if (rows > 0) {
         StageTimer tm(ctx, ST_LOSS, st);
-        // the tensor-core path consumes only the bf16 hi/lo gradient; the fp32 copy is written for the SIMT path only
-        MB_TRY(launch_loss(p.S, p.use_tc ? nullptr : p.S, p.pos, p.gpos, p.row_loss, G_hi, G_lo, rows, p.N, w, st, p.Ng));
+        MB_TRY(launch_loss(p.S, p.S, p.pos, p.gpos, p.row_loss, nullptr, nullptr, rows, p.N, w, st, p.N));
     }
     if (loss && ext == nullptr) {
         if (rows > 0)
@@ -456,9 +467,19 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         // dA = G . Neg and dNeg = G^T . A in ONE grouped, cost-balanced persistent launch (gemm_tc_group.cu)
         const int64_t a_half = p.sides * p.Bp * d, n_half = p.sides * p.CN * d;
         StageTimer tm(ctx, ST_GEMM_DA, st);
+        // A operand of both problems = G, produced from the fp32 scores (or the upstream gradient matrix) inside the kernel
         TcGroupProblem g[2] = {
-            {p.G_hl, p.G_hl + g_half, p.Ng, p.Bc * p.Ng, 0, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, 1, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches},
-            {p.G_hl, p.G_hl + g_half, p.Ng, p.Bc * p.Ng, 1, p.A_hl, p.A_hl + a_half, d, p.Bc * d, 1, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches}};
+            {nullptr, nullptr, 0, 0, 0, p.Neg_hl, p.Neg_hl + n_half, d, (int64_t)p.N * d, 1, p.dA, d, p.Bc * d, (int)p.Bc, d, p.N, batches},
+            {nullptr, nullptr, 0, 0, 1, p.A_hl, p.A_hl + a_half, d, p.Bc * d, 1, gneg, d, (int64_t)p.N * d, p.N, d, (int)p.Bc, batches}};
+        for (auto& q : g) {
+            q.conv_src = p.S;
+            q.conv_z = ext == nullptr ? p.zw : nullptr;
+            q.conv_ld = p.N;
+            q.conv_sb = p.Bc * (int64_t)p.N;
+            q.conv_rows = (int)p.Bc;
+            q.conv_cols = p.N;
+            q.conv_mode = ext == nullptr ? 1 : 2;
+        }
         MB_TRY(gemm_tc_grouped(g, 2, passes, st));
     } else if (p.Bc > 0) {
         {

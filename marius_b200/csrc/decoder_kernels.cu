@@ -448,6 +448,40 @@ mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_l
     return MB_OK;
 }
 
+// Fused SoftmaxCrossEntropy, second half (the first half is the epilogue of the score contraction, gemm_tc_group.cu): merge the
+// per-slot (max, sum exp) statistics of a score row with its positive score into z = log(e^pos + sum_j e^neg_j)  (loss.cpp:57-66),
+// then  row_loss = (z - pos) w ,  d loss / d pos = (e^(pos - z) - 1) w ,  zw = (z - log w) log2 e  so that  d loss / d neg_j = exp2(neg_j log2 e - zw).
+__global__ void __launch_bounds__(256) loss_merge_kernel(const float2* __restrict__ stats, int slots, const float* __restrict__ pos,
+                                                          float* __restrict__ gpos, float* __restrict__ row_loss, float* __restrict__ zw, int64_t rows,
+                                                          float w, float log_w) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float p = pos[i];
+    const float2* st = stats + i * slots;
+    float m = p;
+    for (int t = 0; t < slots; t++) {
+        const float2 x = st[t];
+        if (x.y > 0.f) m = fmaxf(m, x.x);  // a slot no tile wrote has sum == 0
+    }
+    float sum = expf(p - m);
+    for (int t = 0; t < slots; t++) {
+        const float2 x = st[t];
+        if (x.y > 0.f) sum += x.y * expf(x.x - m);
+    }
+    const float z = m + logf(sum);
+    gpos[i] = (expf(p - z) - 1.0f) * w;
+    row_loss[i] = (z - p) * w;
+    zw[i] = (z - log_w) * 1.4426950408889634f;  // pre-scaled by log2(e): the converter warps evaluate exp2(S * log2 e - zw)
+}
+
+mb_status launch_loss_merge(const float2* stats, int slots, const float* pos, float* gpos, float* row_loss, float* zw, int64_t rows, float w,
+                            cudaStream_t st) {
+    if (rows == 0) return MB_OK;
+    loss_merge_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(stats, slots, pos, gpos, row_loss, zw, rows, w, logf(w));
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
 mb_status launch_loss_reduce(const float* row_loss, int64_t n, float* loss, cudaStream_t st) {
     loss_reduce_kernel<<<1, 1024, 0, st>>>(row_loss, n, loss);
     MB_LAUNCH_CHECK();

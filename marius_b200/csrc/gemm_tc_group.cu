@@ -41,6 +41,14 @@ struct GProblem {
     int64_t ldd, sDb;
     int M, N, K, batches;
     int a_mn, b_mn, tma_store;
+    // forward: per-(row, 64-column slot) softmax statistics of the score tile (null: none)
+    float2* stats;
+    int stat_slots;
+    // backward (CONV kernel): the A operand is produced in shared memory from the fp32 matrix `conv_src` [batches][conv_rows][conv_cols]
+    const float* conv_src;
+    const float* conv_z;  // [batches][conv_rows] per-row shift (conv_mode 1) or null
+    int64_t conv_ld, conv_sb;
+    int conv_rows, conv_cols, conv_mode;
 };
 struct GParams {
     GProblem prob[2];
@@ -53,7 +61,40 @@ struct GMaps {
     CUtensorMap m[2][5];  // per problem: A_hi, A_lo, B_hi, B_lo, D
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_tc_group_kernel(const __grid_constant__ GMaps maps, const GParams p) {
+constexpr int kConvWarps = 4;
+constexpr int kConvThreads = kTcThreads + 32 * kConvWarps;  // 320: producer, MMA, 4 epilogue warps, 4 converter warps
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 4 fp32 -> 4 bf16 hi + 4 bf16 lo (x ~= hi + lo), one 8-byte shared-memory store each
+__device__ __forceinline__ void split4_store(uint32_t dst_hi, uint32_t dst_lo, const float (&g)[4], bool want_lo) {
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(g[2 * i + 1]), "f"(g[2 * i]));  // first operand -> upper half
+        const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[i]) : "f"(g[2 * i + 1] - h1), "f"(g[2 * i] - h0));
+    }
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst_hi), "r"(h[0]), "r"(h[1]) : "memory");
+    if (want_lo) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst_lo), "r"(l[0]), "r"(l[1]) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// CONV = false: both operands come from global bf16 hi/lo arrays through TMA (192 threads).
+// CONV = true : the A operand of every problem of the launch is produced by four converter warps from an fp32 matrix (the scores S):
+//               G = exp(S - z_row) (the SoftmaxCrossEntropy gradient, loss.cpp:50-67) or G = S, split into bf16 hi/lo and written
+//               straight into the stage's swizzled operand tiles -- the gradient matrix never exists in global memory (320 threads).
+template <bool CONV>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads : kTcThreads, 1) gemm_tc_group_kernel(const __grid_constant__ GMaps maps, const GParams p) {
     constexpr int TMEM_COLS = 2 * GTILE_N;
     constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
     extern __shared__ uint8_t smem_raw[];
@@ -64,6 +105,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
     auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * GSTAGES + b); };
     auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * GSTAGES + 2 + b); };
     const uint32_t tmem_holder = bar_base + 8u * (2 * GSTAGES + 4);
+    auto raw_bar = [&](int s) { return bar_base + 8u * (2 * GSTAGES + 6 + s); };  // CONV: this CTA's fp32 score tile of stage s has landed
     volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
@@ -73,14 +115,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
     const int lo_mult = p.passes == 3 ? 2 : 1;
-    const uint32_t stage_tx_pair = (uint32_t)(2 * lo_mult * (G_A_TILE + G_B_TILE));
+    const uint32_t stage_tx_pair = (uint32_t)(2 * lo_mult * ((CONV ? 0 : G_A_TILE) + G_B_TILE));
 
     if (warp == 0 && lane == 0) {
         for (int q = 0; q < 2; q++)
             for (int j = 0; j < 5; j++) prefetch_tmap(&maps.m[q][j]);
         for (int s = 0; s < GSTAGES; s++) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), CONV ? 1 + 2 * kConvWarps : 1);  // + one arrival per converter warp of both CTAs
             mbar_init(empty_bar(s), 1);
+            mbar_init(raw_bar(s), 1);
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(tfull_bar(b), 1);
@@ -129,7 +172,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
                         if (leader) mbar_arrive(full_bar(stage));
                     } else {
                         if (leader) mbar_expect_tx(full_bar(stage), stage_tx_pair);
-                        if (!a_mn) {
+                        if (CONV) {
+                            // this CTA's fp32 score tile goes into the stage's A region (hi + lo tiles = exactly its 32 KB) and is converted
+                            // in place by the converter warps; it completes on this CTA's own raw barrier
+                            mbar_expect_tx(raw_bar(stage), 2 * G_A_TILE);
+                            if (!a_mn)
+                                tma_load_3d(sA_hi, mA_hi, raw_bar(stage), k0, m0, b);  // box {64 K columns, 128 M rows}
+                            else
+                                tma_load_3d(sA_hi, mA_hi, raw_bar(stage), m0, k0, b);  // box {128 M columns, 64 K rows}
+                        } else if (!a_mn) {
                             tma_load_3d_2sm(sA_hi, mA_hi, lbar, k0, m0, b);
                             if (three) tma_load_3d_2sm(sA_lo, mA_lo, lbar, k0, m0, b);
                         } else {
@@ -224,7 +275,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
                 }
             }
         }
-    } else {
+    } else if (!CONV || warp < 6) {
         // ================= epilogue warps 2..5 (both CTAs) =================
         const int q = warp & 3;
         int local_tile = 0;
@@ -252,8 +303,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
             const int n_chunks = (p.debug_flags & 8) ? 0 : (n_lim - n0 + 31) / 32;  // bit 3: ablation, no epilogue at all
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GTILE_N);
             uint32_t ra[32], rb[32];
+            // forward contraction: running (max, sum exp) of this thread's score row over the tile's columns -- the SoftmaxCrossEntropy
+            // statistics (loss.cpp:57-66), merged over the row's column tiles by loss_merge_kernel
+            float m_run = -INFINITY, l_run = 0.f;
+            const bool want_stats = !CONV && pr.stats != nullptr;
             auto emit = [&](const uint32_t (&rg)[32], int c) {
                 const int col0 = n0 + c * 32;
+                if (want_stats) {
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int v = 0; v < 32; v++)
+                        if (col0 + v < pr.N) cm = fmaxf(cm, __uint_as_float(rg[v]));
+                    const float mn = fmaxf(m_run, cm);
+                    const float mnl = mn * kLog2e;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int v = 0; v < 32; v++)
+                        if (col0 + v < pr.N) acc += ex2_approx(fmaf(__uint_as_float(rg[v]), kLog2e, -mnl));
+                    l_run = fmaf(l_run, ex2_approx((m_run - mn) * kLog2e), acc);
+                    m_run = mn;
+                }
                 if (pr.tma_store) {
                     if (!(p.debug_flags & 1))
                         stage_and_store(rg, smem_base + G_EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, mD, col0,
@@ -277,11 +346,98 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) gemm_
                     emit(rb, c + 1);
                 }
             }
+            if (want_stats && row < pr.M && n_chunks > 0)
+                pr.stats[((int64_t)b * pr.M + row) * pr.stat_slots + (n0 >> 6)] = make_float2(m_run, l_run);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);
         }
         if (elect_one()) bulk_wait_all();
+    } else {
+        // ================= converter warps 6..9 (both CTAs, CONV only): fp32 scores -> G -> bf16 hi/lo operand tiles, in place =================
+        // The producer's TMA drops this CTA's fp32 score tile (32 KB, row-major, no swizzle) into the stage's A region; these warps read it
+        // into registers, synchronise among themselves, and overwrite the region with the operand tiles the tensor core expects:
+        // 128 shared-memory rows of 128 bytes (64 bf16), SWIZZLE_128B (16-byte chunk index XOR (row & 7)), hi tile then lo tile --
+        // exactly what the TMA loads of the non-CONV kernel produce:
+        //   K-major A (dA = G . Neg):    operand row i = M row m0 + i,                   its 64 elements = K columns k0 .. k0 + 63
+        //   MN-major A (dNeg = G^T . A): operand row i = 64 * slab + K row (k0 + i % 64), its 64 elements = M columns m0 + 64 * slab ..
+        // Either way an operand row is 64 consecutive elements of one score row.  16 threads handle a row (one float4 each: conflict-free
+        // loads, and their 8-byte stores cover one 128-byte operand row = all 32 banks); the S prefetch depth is the stage ring itself.
+        const int ct = (int)threadIdx.x - kTcThreads;
+        const int t16 = ct & 15, rsub = ct >> 4;  // float4 index within the operand row, row within a pass of 8 rows
+        int stage = 0;
+        uint32_t phase = 0;
+        int4 e_next = p.table[cluster_id];
+        for (int r = 0; r < p.rounds; r++) {
+            const int4 e = e_next;
+            if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+            if (e.x < 0) continue;
+            const GProblem& pr = p.prob[e.x & 0xff];
+            const int b = e.y;
+            const int m_base = e.z + (int)rank * BLOCK_M;
+            const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
+            const bool a_mn = pr.a_mn != 0, want_lo = p.passes == 3, expo = pr.conv_mode == 1;
+            const float* zb = expo ? pr.conv_z + (int64_t)b * pr.conv_rows : nullptr;
+            // per-row shift (already scaled by log2 e) of the 16 operand rows this thread touches in k-block kb.  The loads are issued one
+            // k-block ahead and NOTHING consumes them until the conversion (an in-order warp stalls at the first use of a load result)
+            float zc[16], zn[16];
+            auto load_z = [&](int kb, float (&z)[16]) {
+                if (!expo) return;
+                const int k0 = kb * GBLOCK_K;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int i = rsub + 8 * j;
+                    const int srow = a_mn ? k0 + (i & 63) : m_base + i;
+                    z[j] = __ldg(zb + min(srow, pr.conv_rows - 1));
+                }
+            };
+            auto convert = [&](int kb, const float (&z)[16]) {
+                mbar_wait(raw_bar(stage), phase);
+                const uint32_t sA = smem_base + stage * G_STAGE;
+                const int k0 = kb * GBLOCK_K;
+                float4 v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int i = rsub + 8 * j;
+                    // raw tile: K-major [128 rows][64 floats]; MN-major [64 K rows][128 floats] (operand row i = K row i % 64, slab i / 64)
+                    const uint32_t off = a_mn ? (uint32_t)(i & 63) * 512u + (uint32_t)(i & 64) * 4u + 16u * t16 : (uint32_t)i * 256u + 16u * t16;
+                    v[j] = lds_f4(sA + off);
+                }
+                named_barrier_sync(1, 32 * kConvWarps);  // every converter thread holds its part of the raw tile: the region may be overwritten
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const int i = rsub + 8 * j;
+                    float g[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    if (expo) {
+                        // out-of-range elements (TMA zero-filled them): exp2(0 - inf) = 0 keeps them zero
+                        const int srow = a_mn ? k0 + (i & 63) : m_base + i;
+                        const int scol = a_mn ? m_base + (i & 64) + 4 * t16 : k0 + 4 * t16;
+                        const float zz = (srow < pr.conv_rows && scol < pr.conv_cols) ? z[j] : INFINITY;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) g[q] = ex2_approx(fmaf(g[q], kLog2e, -zz));
+                    }
+                    const uint32_t off = (uint32_t)i * 128u + (uint32_t)(((t16 >> 1) ^ (i & 7)) << 4) + (uint32_t)(t16 & 1) * 8u;
+                    split4_store(sA + off, sA + G_A_TILE + off, g, want_lo);
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(full_bar(stage), 0);
+                if (++stage == GSTAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            };
+            load_z(0, zc);
+#pragma unroll 1
+            for (int kb = 0; kb < num_k_blocks; kb += 2) {
+                if (kb + 1 < num_k_blocks) load_z(kb + 1, zn);
+                convert(kb, zc);
+                if (kb + 1 < num_k_blocks) {
+                    if (kb + 2 < num_k_blocks) load_z(kb + 2, zc);
+                    convert(kb + 1, zn);
+                }
+            }
+        }
     }
 
     tc_fence_before();
@@ -331,11 +487,11 @@ mb_status bf16_map(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
 
 // tile tables are pure functions of the shapes: build once, keep on the device
 struct TableKey {
-    int dev, clusters, n;
+    int dev, clusters, n, slot64;
     int M[2], N[2], K[2], batches[2];
     bool operator<(const TableKey& o) const {
-        return std::tie(dev, clusters, n, M[0], N[0], K[0], batches[0], M[1], N[1], K[1], batches[1]) <
-               std::tie(o.dev, o.clusters, o.n, o.M[0], o.N[0], o.K[0], o.batches[0], o.M[1], o.N[1], o.K[1], o.batches[1]);
+        return std::tie(dev, clusters, n, slot64, M[0], N[0], K[0], batches[0], M[1], N[1], K[1], batches[1]) <
+               std::tie(o.dev, o.clusters, o.n, o.slot64, o.M[0], o.N[0], o.K[0], o.batches[0], o.M[1], o.N[1], o.K[1], o.batches[1]);
     }
 };
 struct TableVal {
@@ -372,6 +528,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     const int clusters_max = sm_count() / 2;
     GMaps maps;
     std::memset(&maps, 0, sizeof(maps));
+    bool conv = false, with_stats = false;
     GParams p;
     std::memset(&p, 0, sizeof(p));
     p.passes = passes;
@@ -391,7 +548,19 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
             return MB_ERR_INVALID;
         }
         const bool lo = passes == 3;
-        if (!g.a_mn) {
+        const bool conv_i = g.conv_mode != 0;
+        if (i == 0) conv = conv_i;
+        if (conv_i != conv) {
+            set_error("gemm_tc_grouped: all problems of a launch must agree on conv_mode");
+            return MB_ERR_INVALID;
+        }
+        if (conv_i) {
+            if (g.conv_src == nullptr || (g.conv_mode == 1 && g.conv_z == nullptr) || (reinterpret_cast<uintptr_t>(g.conv_src) & 15u) || (g.conv_ld % 4) ||
+                (g.conv_sb % 4) || (g.conv_cols % 8) || g.conv_rows != (g.a_mn ? g.K : g.M) || g.conv_cols != (g.a_mn ? g.M : g.K)) {
+                set_error("gemm_tc_grouped: bad conv operand (alignment / extents)");
+                return MB_ERR_INVALID;
+            }
+        } else if (!g.a_mn) {
             MB_TRY(bf16_map(&maps.m[i][0], g.A_hi, g.K, g.M, g.batches, g.lda, g.sAb, BLOCK_M));
             MB_TRY(bf16_map(&maps.m[i][1], lo ? g.A_lo : g.A_hi, g.K, g.M, g.batches, g.lda, g.sAb, BLOCK_M));
         } else {
@@ -415,7 +584,22 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) tma_store = false;
         }
-        if (!tma_store) maps.m[i][4] = maps.m[i][0];
+        if (!tma_store) maps.m[i][4] = maps.m[i][2];
+        if (conv_i) {
+            // the fp32 score matrix, loaded as plain row-major tiles (no swizzle) into the stage's A region
+            cuuint64_t dims[3] = {(cuuint64_t)g.conv_cols, (cuuint64_t)g.conv_rows, (cuuint64_t)g.batches};
+            cuuint64_t strides[2] = {(cuuint64_t)g.conv_ld * 4, (cuuint64_t)(g.batches == 1 ? (int64_t)g.conv_rows * g.conv_ld : g.conv_sb) * 4};
+            cuuint32_t box[3] = {g.a_mn ? 128u : 64u, g.a_mn ? 64u : 128u, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = encode_fn()(&maps.m[i][0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.conv_src), dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled (score matrix) failed with CUresult " + std::to_string((int)r));
+                return MB_ERR_CUDA;
+            }
+            maps.m[i][1] = maps.m[i][2];  // (never used: a valid descriptor for prefetch.tensormap)
+        }
         GProblem& q = p.prob[i];
         q.D = g.D;
         q.ldd = g.ldd;
@@ -427,6 +611,20 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
         q.a_mn = g.a_mn;
         q.b_mn = g.b_mn;
         q.tma_store = tma_store ? 1 : 0;
+        q.stats = conv_i ? nullptr : g.stats;
+        q.stat_slots = g.stat_slots;
+        q.conv_src = g.conv_src;
+        q.conv_z = g.conv_z;
+        q.conv_ld = g.conv_ld;
+        q.conv_sb = g.conv_sb;
+        q.conv_rows = g.conv_rows;
+        q.conv_cols = g.conv_cols;
+        q.conv_mode = g.conv_mode;
+        if (q.stats != nullptr && (g.stat_slots < (g.N + kTcStatSlotCols - 1) / kTcStatSlotCols)) {
+            set_error("gemm_tc_grouped: stat_slots too small");
+            return MB_ERR_INVALID;
+        }
+        with_stats = with_stats || q.stats != nullptr;
         key.M[i] = g.M;
         key.N[i] = g.N;
         key.K[i] = g.K;
@@ -439,6 +637,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     }
     int clusters = (int)std::min<int64_t>(clusters_max, total_tiles);
     key.clusters = clusters;
+    key.slot64 = with_stats ? 1 : 0;  // statistics slots are 64 columns wide: column pieces of the tail tiles must start on multiples of 64
     TableVal tv;
     {
         std::lock_guard<std::mutex> lk(table_mutex());
@@ -501,7 +700,8 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
             };
             int best_tail = 0, best_piece = GTILE_N;
             int64_t best_span = schedule(base, nullptr);
-            for (int piece : {192, 128, 96, 64})
+            for (int piece : {192, 128, 96, 64}) {
+                if (with_stats && piece % kTcStatSlotCols != 0) continue;
                 for (int k = 1; k <= 16; k++) {
                     const int tail = clusters * k / 4;
                     const int64_t span = schedule(build(tail, piece), nullptr);
@@ -511,6 +711,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
                         best_piece = piece;
                     }
                 }
+            }
             const std::vector<Tile> tiles = build(best_tail, best_piece);
             std::vector<std::vector<int>> per_pair;
             schedule(tiles, &per_pair);
@@ -536,10 +737,14 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     // function attributes are per device (one process may drive several: the reference's device_models_): opt in once on each
     static std::atomic<bool> attr_set[64];
     if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
-        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
+        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
+        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
         if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
-    gemm_tc_group_kernel<<<2 * clusters, kTcThreads, G_SMEM_TOTAL, st>>>(maps, p);
+    if (conv)
+        gemm_tc_group_kernel<true><<<2 * clusters, kConvThreads, G_SMEM_TOTAL, st>>>(maps, p);
+    else
+        gemm_tc_group_kernel<false><<<2 * clusters, kTcThreads, G_SMEM_TOTAL, st>>>(maps, p);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

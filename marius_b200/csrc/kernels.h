@@ -33,6 +33,7 @@ mb_status launch_split(const float* x, int64_t n, void* hi, void* lo, cudaStream
 mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w, cudaStream_t st,
                            int64_t ldg = 0);
 mb_status launch_loss_reduce(const float* row_loss, int64_t n, float* loss, cudaStream_t st);
+mb_status launch_loss_merge(const float2* stats, int slots, const float* pos, float* gpos, float* row_loss, float* zw, int64_t rows, float w, cudaStream_t st);
 mb_status launch_edge_backward(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int d,
                                int decoder, const float* A0, const float* A1, const float* dA0, const float* dA1, const float* gpos0,
                                const float* gpos1, float* gcat, float* drel0, float* drel1, cudaStream_t st);
@@ -88,7 +89,20 @@ struct TcGroupProblem {
     float* D;
     int64_t ldd, sDb;
     int M, N, K, batches;
+    // optional, forward contraction: softmax statistics of every output row, one (max, sum exp(x - max)) pair per 64-column slot
+    // [batches * M][stat_slots]; the buffer must be zeroed before the launch (a slot no tile wrote has sum == 0)
+    float2* stats = nullptr;
+    int stat_slots = 0;
+    // optional, backward contractions: the A operand is not read from A_hi / A_lo but produced on the fly from the fp32 matrix
+    // conv_src [batches][conv_rows][conv_cols] (leading dimension conv_ld, batch stride conv_sb):
+    //   conv_mode 1: A = exp2(conv_src * log2 e - conv_z[row])  (conv_z pre-scaled by log2 e)   conv_mode 2: A = conv_src
+    // a_mn == 0: A[m][k] = f(conv_src[m][k]) ; a_mn == 1: A[m][k] = f(conv_src[k][m]).  All problems of a launch must agree on conv_mode != 0.
+    const float* conv_src = nullptr;
+    const float* conv_z = nullptr;
+    int64_t conv_ld = 0, conv_sb = 0;
+    int conv_rows = 0, conv_cols = 0, conv_mode = 0;
 };
+constexpr int kTcStatSlotCols = 64;
 mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st);
 
 }  // namespace mb

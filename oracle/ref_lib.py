@@ -44,7 +44,9 @@ def lib():
     if _lib is None:
         import torch  # noqa: F401  (libtorch must be loaded before the reference library resolves its symbols)
 
-        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        # RTLD_LOCAL: the reference defines classes (Model, DistMult, PartitionBuffer ...) whose names the product's host adapters keep; its
+        # symbols must never be visible to marius_b200/lib/_host*.so when both are loaded in one test process
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
         _lib.ref_last_error.restype = C.c_char_p
         _lib.ref_num_threads.restype = C.c_int
         _lib.ref_set_num_threads.argtypes = [C.c_int]

@@ -384,5 +384,6 @@ def test_bench_shape_parity_vs_reference(ops, ctx):
         pytest.skip("oracle/_ref not built")
     res = bench.parity_single(ops, ctx, torch.device("cuda", 0), ops.PREC_BF16X3, 50000, rows=2_000_000)
     assert res["checked"] and res["unique_ids_bit_exact"] and res["gathered_rows_bit_exact"] and res["untouched_rows_bit_exact"], res
+    assert res["fused_step_equals_batch_step_bit_exact"], res
     assert res["max_err"] <= TOL, res
     assert res["ok"], res
