@@ -32,6 +32,8 @@ PYBIND11_MODULE(_host, m) {
         .def("load", &Storage::load)
         .def("write", &Storage::write)
         .def("unload", &Storage::unload, py::arg("write") = false)
+        .def("shuffle", &Storage::shuffle)
+        .def("sort", &Storage::sort, py::arg("src"))
         .def("getDim0", &Storage::getDim0);
 
     py::class_<InMemory, Storage, shared_ptr<InMemory>>(m, "InMemory")
@@ -67,7 +69,49 @@ PYBIND11_MODULE(_host, m) {
         .def("hasSwap", &PartitionBuffer::hasSwap)
         .def("performNextSwap", &PartitionBuffer::performNextSwap)
         .def("sync", &PartitionBuffer::sync)
-        .def("getNumInMemory", &PartitionBuffer::getNumInMemory);
+        .def("getNumInMemory", &PartitionBuffer::getNumInMemory)
+        .def("getBufferState", &PartitionBuffer::getBufferState)
+        .def("bufferTensor", &PartitionBuffer::bufferTensor);
+
+    // storage_wrap.cpp: the Storage facade over the buffer (storage.h:90-145)
+    py::class_<PartitionBufferStorage, Storage, shared_ptr<PartitionBufferStorage>>(m, "PartitionBufferStorage")
+        .def(py::init([](string filename, int64_t dim0, int64_t dim1, int num_partitions, int buffer_capacity, bool prefetching, int fine_to_coarse_ratio,
+                         torch::Device device) {
+                 auto o = std::make_shared<PartitionBufferOptions>();
+                 o->num_partitions = num_partitions;
+                 o->buffer_capacity = buffer_capacity;
+                 o->prefetching = prefetching;
+                 o->fine_to_coarse_ratio = fine_to_coarse_ratio;
+                 return std::make_shared<PartitionBufferStorage>(filename, dim0, dim1, o, device);
+             }),
+             py::arg("filename"), py::arg("dim0_size"), py::arg("dim1_size"), py::arg("num_partitions"), py::arg("buffer_capacity"),
+             py::arg("prefetching") = true, py::arg("fine_to_coarse_ratio") = 1, py::arg("device") = torch::Device(torch::kCUDA, 0))
+        .def(py::init([](string filename, torch::Tensor data, int num_partitions, int buffer_capacity, bool prefetching, int fine_to_coarse_ratio,
+                         torch::Device device) {
+                 auto o = std::make_shared<PartitionBufferOptions>();
+                 o->num_partitions = num_partitions;
+                 o->buffer_capacity = buffer_capacity;
+                 o->prefetching = prefetching;
+                 o->fine_to_coarse_ratio = fine_to_coarse_ratio;
+                 return std::make_shared<PartitionBufferStorage>(filename, data, o, device);
+             }),
+             py::arg("filename"), py::arg("data"), py::arg("num_partitions"), py::arg("buffer_capacity"), py::arg("prefetching") = true,
+             py::arg("fine_to_coarse_ratio") = 1, py::arg("device") = torch::Device(torch::kCUDA, 0))
+        .def("append", &PartitionBufferStorage::append, py::arg("values"))
+        .def("hasSwap", &PartitionBufferStorage::hasSwap)
+        .def("performNextSwap", &PartitionBufferStorage::performNextSwap)
+        .def("getGlobalToLocalMap", &PartitionBufferStorage::getGlobalToLocalMap, py::arg("get_current"))
+        .def("sync", &PartitionBufferStorage::sync)
+        .def("setBufferOrdering", &PartitionBufferStorage::setBufferOrdering, py::arg("buffer_states"))
+        .def("getNextAdmit", &PartitionBufferStorage::getNextAdmit)
+        .def("getNextEvict", &PartitionBufferStorage::getNextEvict)
+        .def("getNumInMemory", &PartitionBufferStorage::getNumInMemory)
+        .def("getRandomIds", &PartitionBufferStorage::getRandomIds, py::arg("size"))
+        .def("adagradUpdate",
+             [](PartitionBufferStorage& self, PartitionBufferStorage& state, torch::Tensor indices, torch::Tensor gradients, float lr) {
+                 self.buffer_->adagradUpdate(*state.buffer_, indices, gradients, lr);
+             },
+             py::arg("state"), py::arg("indices"), py::arg("gradients"), py::arg("learning_rate"));
 
     // edge_decoder_wrap.cpp:8-22
     py::class_<EdgeDecoder, shared_ptr<EdgeDecoder>>(m, "EdgeDecoder")

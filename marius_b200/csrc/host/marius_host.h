@@ -13,9 +13,15 @@
 //   nn/model.h          Model                        Model (forward_lp / train_batch / evaluate-side scores)
 // Error conventions follow common/exception.h:12-42 (all derive std::runtime_error).
 #pragma once
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 
 #include <torch/extension.h>
+#include <ATen/cuda/CUDAEvent.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
 
 #include <memory>
 #include <string>
@@ -109,8 +115,11 @@ class InMemory : public Storage {
 /** storage/buffer.h:16-41 */
 class Partition {
    public:
+    std::mutex* lock_;
+    std::condition_variable* cv_;
     int partition_id_;
     bool present_ = false;
+    bool evicting_ = false;  // an asynchronous write-back of this partition is in flight (buffer.cpp:276-281): readers of the file wait
     int64_t partition_size_;
     int embedding_size_;
     int64_t total_size_;
@@ -118,8 +127,12 @@ class Partition {
     int64_t file_offset_;
     int buffer_idx_ = -1;
     Partition(int partition_id, int64_t partition_size, int embedding_size, int64_t idx_offset, int64_t file_offset)
-        : partition_id_(partition_id), partition_size_(partition_size), embedding_size_(embedding_size),
-          total_size_(partition_size * embedding_size * 4), idx_offset_(idx_offset), file_offset_(file_offset) {}
+        : lock_(new std::mutex()), cv_(new std::condition_variable()), partition_id_(partition_id), partition_size_(partition_size),
+          embedding_size_(embedding_size), total_size_(partition_size * embedding_size * 4), idx_offset_(idx_offset), file_offset_(file_offset) {}
+    ~Partition() {
+        delete lock_;
+        delete cv_;
+    }
 };
 
 /** Flat fp32 row-major file of all partitions back to back (storage/buffer.cpp:65-116; the embeddings.bin format, constants.h:39-42) */
@@ -133,23 +146,89 @@ class PartitionedFile {
     void writePartition(const void* host_addr, Partition* partition);
 };
 
+/** One set of staging buffers for `n` partitions: pinned host memory (the file side) + HBM slots (the slab side), with its own copy
+ *  stream; the two asynchronous blocks below are built on it. */
+struct SwapStaging {
+    vector<torch::Tensor> host;  // pinned, [partition_size, d] fp32 each
+    vector<torch::Tensor> dev;   // HBM,    [partition_size, d] fp32 each
+    c10::cuda::CUDAStream stream = c10::cuda::getDefaultCUDAStream();
+    void init(int n, int64_t rows, int64_t d, torch::Device device);
+};
+
+/** LookaheadBlock (buffer.h:43-76, buffer.cpp:118-220) for an HBM slab: a reader thread brings the partitions of the NEXT admit set from
+ *  the file into pinned memory and on into spare HBM slots over its copy stream while training runs on the current buffer state;
+ *  move_to_buffer is then a device-to-device copy ordered on the trainer's stream. */
+class LookaheadBlock {
+    PartitionedFile* partitioned_file_;
+    vector<Partition*> partitions_;
+    SwapStaging staging_;
+    torch::Device device_;
+    at::cuda::CUDAEvent moved_event_;  // the last move_to_buffer's copies out of the HBM slots (recorded on the trainer's stream)
+    std::mutex lock_;
+    std::condition_variable cv_;
+    std::thread* thread_ = nullptr;
+    std::atomic<bool> present_{false}, done_{false};
+    string error_;
+    void run();
+
+   public:
+    LookaheadBlock(int64_t partition_rows, int64_t d, PartitionedFile* partitioned_file, int num_per_lookahead, torch::Device device);
+    ~LookaheadBlock();
+    void start(vector<Partition*> first_partitions);
+    void stop();
+    /** copies the prefetched partitions into `slab_addrs` (device pointers of the evicted slots), then starts prefetching `next_partitions` */
+    void move_to_buffer(vector<torch::Tensor> slab_slots, vector<int64_t> buffer_idxs, vector<Partition*> next_partitions);
+};
+
+/** AsyncWriteBlock (buffer.h:78-110, buffer.cpp:222-322) for an HBM slab: async_write snapshots the evicted slots into spare HBM on the
+ *  trainer's stream (so the slots are free for the admitted partitions at once); a writer thread drains them to pinned memory and the file. */
+class AsyncWriteBlock {
+    PartitionedFile* partitioned_file_;
+    vector<Partition*> partitions_;
+    SwapStaging staging_;
+    torch::Device device_;
+    at::cuda::CUDAEvent staged_event_;  // the snapshot copies of the last async_write (recorded on the trainer's stream)
+    std::mutex lock_;
+    std::condition_variable cv_;
+    std::thread* thread_ = nullptr;
+    std::atomic<bool> present_{false}, done_{false};
+    string error_;
+    void run();
+
+   public:
+    AsyncWriteBlock(int64_t partition_rows, int64_t d, PartitionedFile* partitioned_file, int num_per_evict, torch::Device device);
+    ~AsyncWriteBlock();
+    void start();
+    void stop();
+    void async_write(vector<Partition*> partitions, vector<torch::Tensor> slab_slots);
+    void wait_idle();  // every queued write-back has reached the file
+};
+
 /** PartitionBuffer (storage/buffer.h:116-190) with the slab in HBM: `capacity` partitions resident on the GPU, the rest in the
- *  backing file; swaps follow the caller-supplied buffer-state sequence (BETA/COMET orderings are reused unchanged). */
+ *  backing file; swaps follow the caller-supplied buffer-state sequence (BETA/COMET orderings are reused unchanged).  With
+ *  prefetching the swap engine is asynchronous (LookaheadBlock / AsyncWriteBlock above): HBM holds capacity + 2 * fine_to_coarse_ratio
+ *  partition slots, and performNextSwap costs two device-to-device partition copies instead of a disk + PCIe round trip. */
 class PartitionBuffer {
     int capacity_, num_partitions_, fine_to_coarse_ratio_, embedding_size_;
     int64_t partition_size_, total_embeddings_;
     bool loaded_ = false, prefetching_;
     torch::Device device_;
     torch::Tensor buffer_tensor_view_;  // [capacity * partition_size, embedding_size] fp32 in HBM
-    torch::Tensor staging_;             // pinned host bounce buffer, one partition
+    torch::Tensor staging_;             // pinned host bounce buffer, one partition (synchronous paths: load / sync / no prefetching)
     vector<Partition*> partition_table_;
     string filename_;
     PartitionedFile* partitioned_file_;
-    torch::Tensor buffer_state_;
-    vector<torch::Tensor> buffer_states_;
+    LookaheadBlock* lookahead_block_ = nullptr;
+    AsyncWriteBlock* async_write_block_ = nullptr;
+    vector<int> buffer_state_;                // partition ids resident now, by position
+    vector<vector<int>> buffer_states_;       // the whole ordering (cached on the host: no per-element tensor reads)
     size_t state_pos_ = 0;  // index of the NEXT state in buffer_states_
     void admit(vector<Partition*> admit_partitions, vector<int64_t> buffer_idxs);
     void evict(vector<Partition*> evict_partitions);
+    torch::Tensor slot(int64_t buffer_idx, int64_t rows);
+    void startThreads();
+    void stopThreads();
+    vector<int> admitOf(size_t next_pos, const vector<int>& current);
 
    public:
     PartitionBuffer(int capacity, int num_partitions, int fine_to_coarse_ratio, int64_t partition_size, int embedding_size, int64_t total_embeddings,
@@ -163,6 +242,7 @@ class PartitionBuffer {
     Indices getRandomIds(int64_t size);
     torch::Tensor indexRead(torch::Tensor indices);
     torch::Tensor getGlobalToLocalMap(bool get_current);
+    torch::Tensor getBufferState();
     void indexAdd(torch::Tensor indices, torch::Tensor values);
     void adagradUpdate(PartitionBuffer& state, torch::Tensor indices, torch::Tensor gradients, float learning_rate);
     void setBufferOrdering(vector<torch::Tensor> buffer_states);
@@ -172,6 +252,55 @@ class PartitionBuffer {
     int64_t getNumInMemory() { return buffer_tensor_view_.defined() ? buffer_tensor_view_.size(0) : 0; }
     torch::Tensor bufferTensor() { return buffer_tensor_view_; }
 };
+
+/** storage/storage.h:90-145: the Storage facade GraphModelStorage holds for buffered node embeddings / optimizer state */
+struct PartitionBufferOptions {  // configuration/options.h (the fields the buffer reads)
+    int num_partitions = 1;
+    int buffer_capacity = 1;
+    bool prefetching = true;
+    int fine_to_coarse_ratio = 1;
+    torch::Dtype dtype = torch::kFloat32;
+};
+
+class PartitionBufferStorage : public Storage {
+    bool loaded_ = false;
+
+   public:
+    PartitionBuffer* buffer_ = nullptr;
+    shared_ptr<PartitionBufferOptions> options_;
+    PartitionBufferStorage(string filename, int64_t dim0_size, int64_t dim1_size, shared_ptr<PartitionBufferOptions> options,
+                           torch::Device device = torch::Device(torch::kCUDA, 0));
+    PartitionBufferStorage(string filename, torch::Tensor data, shared_ptr<PartitionBufferOptions> options,
+                           torch::Device device = torch::Device(torch::kCUDA, 0));
+    ~PartitionBufferStorage();
+    void rangePut(int64_t offset, torch::Tensor values);
+    void append(torch::Tensor values);
+    void load() override;
+    void unload(bool perform_write) override;
+    void write() override;
+    torch::Tensor indexRead(Indices indices) override;
+    void indexAdd(Indices indices, torch::Tensor values) override;
+    torch::Tensor range(int64_t offset, int64_t n) override;
+    void indexPut(Indices indices, torch::Tensor values) override;
+    void rangePut(int64_t offset, int64_t n, torch::Tensor values) override;
+    void shuffle() override;
+    void sort(bool src) override;
+    Indices getRandomIds(int64_t size) { return buffer_->getRandomIds(size); }
+    bool hasSwap() { return buffer_->hasSwap(); }
+    void performNextSwap() { buffer_->performNextSwap(); }
+    torch::Tensor getGlobalToLocalMap(bool get_current) { return buffer_->getGlobalToLocalMap(get_current); }
+    void sync() { buffer_->sync(); }
+    void setBufferOrdering(vector<torch::Tensor> buffer_states) { buffer_->setBufferOrdering(buffer_states); }
+    std::vector<int> getNextAdmit() { return buffer_->getNextAdmit(); }
+    std::vector<int> getNextEvict() { return buffer_->getNextEvict(); }
+    int64_t getNumInMemory() { return buffer_->getNumInMemory(); }
+};
+
+// shared helpers of storage.cpp / buffer.cpp
+void mbh_check_indices(const Indices& indices);
+void mbh_check_values(const torch::Tensor& table, const Indices& indices, const torch::Tensor& values);
+torch::Tensor mbh_device_rows_read(const torch::Tensor& table, Indices indices);
+void mbh_device_rows_scatter(torch::Tensor& table, Indices indices, torch::Tensor values, bool add);
 
 // ---- decoders --------------------------------------------------------------------------------------------------
 /** nn/decoders/edge/edge_decoder.h:13-31 restricted to the DotCompare family the kernels implement */

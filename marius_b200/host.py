@@ -25,7 +25,7 @@ _spec = importlib.util.spec_from_file_location("_host", _EXT)
 _host = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(_host)
 
-Storage, InMemory, PartitionBuffer = _host.Storage, _host.InMemory, _host.PartitionBuffer
+Storage, InMemory, PartitionBuffer, PartitionBufferStorage = _host.Storage, _host.InMemory, _host.PartitionBuffer, _host.PartitionBufferStorage
 EdgeDecoder, DistMult, ComplEx = _host.EdgeDecoder, _host.DistMult, _host.ComplEx
 Batch, Model, LossFunction, SoftmaxCrossEntropy = _host.Batch, _host.Model, _host.LossFunction, _host.SoftmaxCrossEntropy
 node_corrupt_forward, only_pos_forward = _host.node_corrupt_forward, _host.only_pos_forward
@@ -33,7 +33,7 @@ LinkPredictionReporter, Hitsk, MeanRank, MeanReciprocalRank = _host.LinkPredicti
 MariusRuntimeException = _host.MariusRuntimeException
 set_default_precision, default_precision = _host.set_default_precision, _host.default_precision
 
-storage = SimpleNamespace(Storage=Storage, InMemory=InMemory, PartitionBuffer=PartitionBuffer)
+storage = SimpleNamespace(Storage=Storage, InMemory=InMemory, PartitionBuffer=PartitionBuffer, PartitionBufferStorage=PartitionBufferStorage)
 data = SimpleNamespace(Batch=Batch)
 report = SimpleNamespace(LinkPredictionReporter=LinkPredictionReporter, Hitsk=Hitsk, MeanRank=MeanRank, MeanReciprocalRank=MeanReciprocalRank)
 nn = SimpleNamespace(Model=Model, SoftmaxCrossEntropy=SoftmaxCrossEntropy, LossFunction=LossFunction,

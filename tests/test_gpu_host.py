@@ -154,16 +154,26 @@ def test_inmemory_index_read_add_put(host, tmp_path):
     assert torch.equal(disk, exp)
 
 
+@pytest.fixture(params=[False, True], ids=["sync", "prefetching"])
+def prefetching(request):
+    """both swap engines: synchronous (buffer.cpp:635-683 without prefetching) and LookaheadBlock / AsyncWriteBlock (buffer.cpp:118-322)"""
+    return request.param
+
+
 class TestPartitionBuffer:
     # test_buffer.cpp:20-75 fixture: 45 rows, 5 partitions of 10 (last 5), capacity 2, ordering of TestPartitionBufferOrdering
     total, nparts, psize, d, cap = 45, 5, 10, 16, 2
     states = [[0, 1], [0, 2], [0, 3], [0, 4], [1, 4], [1, 3], [1, 2], [3, 2], [4, 2], [4, 3]]
 
+    @pytest.fixture(autouse=True)
+    def _mode(self, prefetching):
+        self.prefetching = prefetching
+
     def make(self, host, tmp_path):
         rand = torch.randn(self.total, self.d)
         fn = str(tmp_path / "pb.bin")
         rand.numpy().tofile(fn)
-        pb = host.storage.PartitionBuffer(self.cap, self.nparts, 1, self.psize, self.d, self.total, fn, False, CUDA)
+        pb = host.storage.PartitionBuffer(self.cap, self.nparts, 1, self.psize, self.d, self.total, fn, self.prefetching, CUDA)
         pb.setBufferOrdering([torch.tensor(s) for s in self.states])
         pb.load()
         return pb, rand, fn
@@ -212,6 +222,7 @@ class TestPartitionBuffer:
         vals = torch.ones(10, self.d)
         pb.indexAdd(ids, vals)
         pb.performNextSwap()  # evicts partition 1
+        pb.sync()  # (with prefetching the write-back is asynchronous: sync() returns once it has reached the file)
         disk = torch.from_numpy(np.fromfile(fn, dtype=np.float32).reshape(self.total, self.d))
         assert torch.equal(disk[10:20], rand[10:20] + 1)
         # partition 2 now lives in slot 1: buffer-local row 10 is global row 20
@@ -224,7 +235,7 @@ class TestPartitionBuffer:
         g = np.load(os.path.join(golden_dir, "partition_buffer.npz"))
         fn = str(tmp_path / "pbg.bin")
         g["table"].tofile(fn)
-        pb = host.storage.PartitionBuffer(int(g["cap"]), int(g["nparts"]), 1, int(g["psize"]), int(g["d"]), int(g["total"]), fn, False, CUDA)
+        pb = host.storage.PartitionBuffer(int(g["cap"]), int(g["nparts"]), 1, int(g["psize"]), int(g["d"]), int(g["total"]), fn, self.prefetching, CUDA)
         pb.setBufferOrdering([torch.from_numpy(s) for s in g["states"]])
         pb.load()
         idx = torch.from_numpy(g["idx"])
@@ -237,6 +248,65 @@ class TestPartitionBuffer:
             pb.performNextSwap()
         pb.unload(True)
         assert np.array_equal(np.fromfile(fn, dtype=np.float32).reshape(g["table"].shape), g["file_after"])
+
+
+    def test_updates_survive_a_full_epoch_of_swaps(self, host, tmp_path):
+        """Every buffer state: add a known value to random resident rows, swap.  After the epoch the file equals the host-side replay
+        exactly, whatever the swap engine (asynchronous write-backs / lookahead reads must never lose or reorder an update)."""
+        pb, rand, fn = self.make(host, tmp_path)
+        exp = rand.clone()
+        g = torch.Generator().manual_seed(5)
+        si = 0
+        while True:
+            state = self.states[si]
+            local = torch.unique(torch.randint(0, 2 * self.psize, (12,), generator=g))
+            # buffer-local row -> global row through the current map
+            m = pb.getGlobalToLocalMap(True).cpu()
+            inv = {int(m[gid]): gid for gid in range(self.total) if int(m[gid]) >= 0}
+            local = torch.tensor([l for l in local.tolist() if l in inv])
+            vals = torch.randint(1, 50, (local.numel(), self.d), generator=g).float()
+            pb.indexAdd(local, vals)
+            for l, v in zip(local.tolist(), vals):
+                exp[inv[l]] += v
+            assert sorted(int(x) for x in pb.getBufferState()) == sorted(state)
+            if not pb.hasSwap():
+                break
+            pb.performNextSwap()
+            si += 1
+        pb.unload(True)
+        disk = torch.from_numpy(np.fromfile(fn, dtype=np.float32).reshape(self.total, self.d))
+        assert torch.equal(disk, exp)
+
+
+class TestPartitionBufferStorage:
+    """storage.cpp:67-201 / test_storage.cpp:294-464: the Storage facade GraphModelStorage holds for buffered tables."""
+
+    def test_facade(self, host, tmp_path, prefetching):
+        total, d, nparts, cap = 45, 8, 5, 2
+        rand = torch.randn(total, d)
+        fn = str(tmp_path / "pbs.bin")
+        st = host.storage.PartitionBufferStorage(fn, rand, nparts, cap, prefetching, 1, CUDA)  # appends the tensor to the file (storage.cpp:82-96)
+        assert st.dim0_size == total and st.dim1_size == d
+        assert np.array_equal(np.fromfile(fn, dtype=np.float32).reshape(total, d), rand.numpy())
+        st.setBufferOrdering([torch.tensor(s) for s in TestPartitionBuffer.states])
+        st.load()
+        assert st.getNumInMemory() == cap * 9  # partition_size = ceil(45 / 5)
+        idx = torch.arange(0, 18)
+        assert torch.equal(st.indexRead(idx).cpu(), rand[:18])
+        st.indexAdd(idx, torch.ones(18, d))
+        assert torch.equal(st.indexRead(idx).cpu(), rand[:18] + 1)
+        for bad in (lambda: st.range(0, 4), lambda: st.indexPut(idx, torch.ones(18, d)), lambda: st.rangePut(0, 4, torch.ones(4, d)),
+                    lambda: st.shuffle(), lambda: st.sort(True)):
+            with pytest.raises(RuntimeError):  # storage.cpp:178-201
+                bad()
+        assert st.hasSwap() and st.getNextAdmit() == [2] and st.getNextEvict() == [1]
+        exp = -torch.ones(total, dtype=torch.int64)
+        exp[:18] = torch.arange(18)
+        assert torch.equal(st.getGlobalToLocalMap(True).cpu(), exp)
+        st.performNextSwap()
+        st.unload(True)
+        disk = torch.from_numpy(np.fromfile(fn, dtype=np.float32).reshape(total, d))
+        assert torch.equal(disk[:18], rand[:18] + 1) and torch.equal(disk[18:], rand[18:])
 
 
 def test_train_batch_fused_on_device_tables(host):
