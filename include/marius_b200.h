@@ -202,22 +202,37 @@ mb_status mb_train_step(mb_context* ctx, const mb_batch* batch, float* table, fl
 
 /* The same fused step on a table SHARDED BY NODE PARTITION over the GPUs of one box (replaces the reference's
  * replicas-plus-shared-host-table scheme, nn/model.cpp:136-159, pipeline/pipeline_gpu.cpp:23).  Rank o owns global rows
- * [o * rows_per_rank, (o+1) * rows_per_rank); tables[o] / states[o] are the owners' base pointers as seen from THIS process: its
- * own allocation for o == rank, CUDA-IPC mappings of the peers' allocations otherwise (peer access over NVLink enabled).
- * `unique_ids` are GLOBAL row ids.  Remote rows are fetched once per step into a batch-local cache by a copy kernel that keeps many
- * rows per SM in flight (NVLink latency is ~5x HBM latency), the decoder kernels then read local memory only; the update reads the
- * owner's Adagrad state row and applies delta_e / delta_s with fire-and-forget vector reductions (red.global.sys.add.v4.f32) at the
- * owner's HBM -- exactly the reference's indexAdd of both deltas.  The only cross-GPU traffic is the rows a batch needs: one row
- * in (embedding) + one row in (state) + two rows out per remote row, and there is no collective on the row path.  Rows touched
- * concurrently by two ranks follow the reference's unlocked (bounded-staleness) update semantics (storage/buffer.cpp:459,
- * SURVEY.md 3.2).  Up to 8 shards. */
+ * [o * rows_per_rank, (o+1) * rows_per_rank); tables[o] / states[o] / exchange[o] are the owners' base pointers as seen from THIS
+ * process: its own allocations for o == rank, CUDA-IPC mappings of the peers' allocations otherwise (peer access over NVLink).
+ * `unique_ids` are GLOBAL row ids, sorted ascending (map_tensors order).  Per step and rank:
+ *   1. remote embedding rows are fetched once into a batch-local cache by a copy kernel that keeps many rows per SM in flight
+ *      (NVLink latency is ~5x HBM latency); the decoder kernels then read local memory only;
+ *   2. the update kernel applies Adagrad to the rows this rank owns and SHIPS THE GRADIENT ROW of every remote row into the owner's
+ *      inbox (plain 128-bit stores over NVLink: one row out per remote row, the Adagrad state never crosses the link);
+ *   3. every owner applies the gradient rows it received, sender by sender in rank order, each as one sparse-Adagrad step
+ *      (batch.cpp:62-79) on its own HBM.
+ * Three device-side flag barriers per step over the exchange areas (epoch counters written with st.release.sys, polled with
+ * ld.acquire.sys; no host involvement, so the step still replays as one CUDA graph) order the phases: all fetches of step t see the
+ * tables after every apply of step t-1; no row is updated while a peer may still fetch it; an inbox is applied only when complete.
+ * The result is therefore deterministic and defined: pre-step rows + the owner's own Adagrad step + one Adagrad step per sender in
+ * rank order.  All ranks must call the sharded step the same number of times (a barrier that is not met within ~2 s sets the
+ * context's error flag instead of hanging the GPU).  Cross-GPU traffic: 1 row in + 1 row out per remote row.  Up to 8 shards.
+ * single_process != 0: all shards are driven by this one call (tests; one GPU holding several shards): barriers are skipped and this
+ * call also runs step 3 for every owner. */
 typedef struct mb_shards {
     float* tables[8];
     float* states[8];
     int world;
     int64_t rows_per_rank;
     int rank; /* which shard is this process's own HBM (tables[rank] is local memory, the others are peer mappings) */
+    void* exchange[8];     /* per-owner exchange area of mb_shard_exchange_bytes(world, exchange_rows, d) bytes, zero-initialised */
+    int64_t exchange_rows; /* capacity (gradient rows) of every (owner, sender) inbox: >= 2B + 2CN of the largest batch */
+    int single_process;
 } mb_shards;
+/* bytes of one rank's exchange area: barrier flags + `world` inboxes of (count, ids[rows], gradient rows[rows][d]) */
+int64_t mb_shard_exchange_bytes(int world, int64_t exchange_rows, int64_t d);
+/* non-zero once a barrier of the sharded step timed out on this context's device (sticky) */
+mb_status mb_shard_error(mb_context* ctx, const mb_shards* shards, int* error_out);
 /* CUDA IPC plumbing for one-process-per-GPU deployments: mb_ipc_export returns the 64-byte handle of the allocation containing
  * `dev_ptr` and the offset of `dev_ptr` inside it; mb_ipc_import opens a peer's handle with the context's device current (lazy peer
  * access over NVLink) and returns the peer pointer usable in mb_shards.  Mappings are closed by mb_destroy. */

@@ -29,7 +29,8 @@ class mb_batch(C.Structure):
 
 
 class mb_shards(C.Structure):
-    _fields_ = [("tables", C.c_void_p * 8), ("states", C.c_void_p * 8), ("world", C.c_int), ("rows_per_rank", C.c_int64), ("rank", C.c_int)]
+    _fields_ = [("tables", C.c_void_p * 8), ("states", C.c_void_p * 8), ("world", C.c_int), ("rows_per_rank", C.c_int64), ("rank", C.c_int),
+                ("exchange", C.c_void_p * 8), ("exchange_rows", C.c_int64), ("single_process", C.c_int)]
 
 
 _vp, _i64, _i32, _f = C.c_void_p, C.c_int64, C.c_int, C.c_float
@@ -66,9 +67,10 @@ _SIGS = {
     "mb_ipc_import": [_vp, _vp, _i64, C.POINTER(_vp)],
     "mb_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "mb_profile_timeline": [_vp, _i32, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)],
+    "mb_shard_error": [_vp, C.POINTER(mb_shards), C.POINTER(C.c_int)],
     "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }
-EXPORTS = list(_SIGS) + ["mb_profile_num_stages", "mb_profile_stage_name", "mb_destroy", "mb_last_error", "mb_version", "mb_launch_count", "mb_build_info", "mb_workspace_bytes"]
+EXPORTS = list(_SIGS) + ["mb_profile_num_stages", "mb_profile_stage_name", "mb_destroy", "mb_last_error", "mb_version", "mb_launch_count", "mb_build_info", "mb_workspace_bytes", "mb_shard_exchange_bytes"]
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.argtypes = _args
@@ -84,6 +86,8 @@ lib.mb_profile_stage_name.argtypes = [C.c_int]
 lib.mb_profile_stage_name.restype = C.c_char_p
 lib.mb_workspace_bytes.argtypes = [_vp]
 lib.mb_workspace_bytes.restype = C.c_size_t
+lib.mb_shard_exchange_bytes.argtypes = [C.c_int, C.c_int64, C.c_int64]
+lib.mb_shard_exchange_bytes.restype = C.c_int64
 
 
 def check(status: int) -> None:

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-CUDA_SOURCES = ["c_api.cu", "storage_kernels.cu", "radix_sort.cu", "decoder_kernels.cu", "eval_kernels.cu", "sample_kernels.cu", "gemm_simt.cu", "gemm_tc_group.cu"]
+CUDA_SOURCES = ["c_api.cu", "storage_kernels.cu", "radix_sort.cu", "decoder_kernels.cu", "eval_kernels.cu", "sample_kernels.cu", "shard_kernels.cu", "gemm_simt.cu", "gemm_tc_group.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 

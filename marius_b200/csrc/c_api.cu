@@ -143,9 +143,9 @@ static mb_status ensure_ws(mb_context* ctx, size_t bytes, cudaStream_t st) {
     return MB_OK;
 }
 
-enum Stage { ST_GATHER = 0, ST_SORT, ST_REL_SORT, ST_PREP, ST_GEMM_FWD, ST_LOSS, ST_GEMM_DA, ST_GEMM_DNEG, ST_EDGE_BWD, ST_UPDATE, ST_REL_GRAD, ST_COUNT };
+enum Stage { ST_GATHER = 0, ST_SORT, ST_REL_SORT, ST_PREP, ST_GEMM_FWD, ST_LOSS, ST_GEMM_DA, ST_GEMM_DNEG, ST_EDGE_BWD, ST_UPDATE, ST_REL_GRAD, ST_EXCHANGE, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {"gather_rows", "slot_sort", "rel_sort", "edge_prep+neg_gather", "gemm_scores", "loss_grad", "gemm_dA",
-                                            "gemm_dNeg", "edge_backward", "segment_reduce+adagrad_update", "rel_grad_reduce"};
+                                            "gemm_dNeg", "edge_backward", "segment_reduce+adagrad_update", "rel_grad_reduce", "shard_barriers+owner_apply"};
 
 struct StageTimer {
     mb_context* ctx;
@@ -192,7 +192,7 @@ struct Plan {
     bool has_rel, use_tc;
     // buffers
     float *emb_u, *A, *pos, *gpos, *row_loss, *NegE, *S, *dA, *gcat, *drel;
-    float* state_u = nullptr;          // sharded table: local copies of the remote rows' Adagrad state
+    int64_t* bounds = nullptr;         // sharded table: [world + 1] owner bounds of the sorted unique-id list
     const float** row_ptrs = nullptr;  // sharded table: address of every unique row (own HBM or the fetched copy in emb_u)
     bool sharded = false;
     __nv_bfloat16 *A_hl, *Neg_hl;
@@ -204,7 +204,7 @@ struct Plan {
     void layout(Arena& ar, bool need_emb_u, bool training, bool own_scores) {
         emb_u = need_emb_u ? ar.take<float>(U * d) : nullptr;
         row_ptrs = sharded ? ar.take<const float*>(U) : nullptr;
-        state_u = sharded ? ar.take<float>(U * d) : nullptr;
+        bounds = sharded ? ar.take<int64_t>(16) : nullptr;
         A = ar.take<float>(sides * Bp * d);
         pos = ar.take<float>(sides * Bp);
         NegE = use_tc ? nullptr : ar.take<float>(sides * CN * d);
@@ -383,7 +383,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
 
     const float* emb = emb_in;
     const int64_t* row_map = nullptr;
-    bool state_fetch_forked = false, emb_fetch_forked = false;
+    bool emb_fetch_forked = false;
     if (fused) {
         // DataLoader::loadGPUParameters (dataloader.cpp:529-548).  With the vector kernels the gather is fused away: prep / backward read
         // table[unique_ids[local id]] directly (the table is not modified until the update at the end of the step, so this is the same
@@ -393,9 +393,15 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
             emb_ld = ld;
             row_map = unique_ids;
             if (p.sharded) {
-                // remote rows are copied once into the batch cache; prep / backward then address every row through row_ptrs
-                // Both fetches run on the second side stream: the embedding rows while the (local) negative rows are prepared, the state
-                // rows -- only needed by the update at the end of the step -- while the contractions keep the SMs busy.
+                // barrier 1: every rank has applied the gradient rows of the previous step, so the rows fetched below are the tables after
+                // step t-1 everywhere; then the owner bounds of this batch (and the row counts the owners will receive)
+                {
+                    StageTimer tm(ctx, ST_EXCHANGE, st);
+                    MB_TRY(launch_shard_barrier(sh, st));
+                    MB_TRY(launch_owner_bounds(sh, unique_ids, p.U, d, p.bounds, st));
+                }
+                // remote rows are copied once into the batch cache; prep / backward then address every row through row_ptrs.  The fetch
+                // runs on the second side stream while the (local) negative rows are prepared.
                 cudaStream_t fs = (overlap && ctx->side2 != nullptr) ? ctx->side2 : st;
                 if (fs != st) {
                     MB_CUDA_TRY(cudaEventRecord(ctx->ev_sfetch_fork, st));
@@ -408,14 +414,6 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
                 if (fs != st) {
                     MB_CUDA_TRY(cudaEventRecord(ctx->ev_efetch_join, fs));
                     emb_fetch_forked = true;
-                }
-                {
-                    StageTimer tm(ctx, ST_GATHER, fs);
-                    MB_TRY(launch_fetch_remote_rows(sh, unique_ids, p.U, ld, d, p.state_u, nullptr, true, fs));
-                }
-                if (fs != st) {
-                    MB_CUDA_TRY(cudaEventRecord(ctx->ev_sfetch_join, fs));
-                    state_fetch_forked = true;
                 }
             }
         } else if (sh != nullptr && sh->world > 1) {
@@ -509,7 +507,6 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     // ---- join: the slot / relation plans and the negative-row gradients are needed from here on
     if (overlap) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_slot, 0));
     if (dneg_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
-    if (state_fetch_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_sfetch_join, 0));
     // relation gradients (segmented sum of per-edge gradients by relation id) touch nothing the node update touches: they run on the
     // side stream next to it
     const bool rel_forked = need_rel && overlap;
@@ -528,13 +525,28 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         // node gradients: segmented sum over sorted slots (+ Adagrad)
         StageTimer tm(ctx, ST_UPDATE, st);
         if (fused) {
+            // barrier 2 (sharded): every rank has fetched the rows it needs -- from here on the tables may change
+            if (p.sharded) MB_TRY(launch_shard_barrier(sh, st));
             MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st,
-                                     p.sharded ? p.state_u : nullptr));
+                                     p.sharded ? p.bounds : nullptr));
         } else if (delta_e != nullptr || delta_s != nullptr) {
             MB_REQUIRE(state != nullptr && delta_e != nullptr && delta_s != nullptr, "delta_e/delta_s need state and both outputs");
             MB_TRY(launch_seg_reduce(nullptr, 1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
         } else if (grad != nullptr) {
             MB_TRY(launch_seg_reduce(nullptr, 0, p.gcat, svals, p.offsets, p.U, d, grad, d, nullptr, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, lr, st));
+        }
+    }
+    if (p.sharded) {
+        // barrier 3: every sender's gradient rows are in the owners' inboxes; each owner applies them sender by sender in rank order,
+        // every sender's rows as one sparse-Adagrad step on the owner's own HBM (one-process tests: this call serves every owner)
+        StageTimer tm(ctx, ST_EXCHANGE, st);
+        MB_TRY(launch_shard_barrier(sh, st));
+        for (int i = 0; i < sh->world; i++) {
+            if (i == sh->rank) continue;
+            if (sh->single_process)
+                MB_TRY(launch_inbox_apply(sh, i, sh->rank, ld, d, lr, p.U, st));
+            else
+                MB_TRY(launch_inbox_apply(sh, sh->rank, i, ld, d, lr, sh->exchange_rows, st));
         }
     }
     if (rel_forked) MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
@@ -712,6 +724,19 @@ mb_status mb_ipc_import(mb_context* ctx, const void* handle, int64_t offset, voi
     ctx->ipc_mappings.push_back(base);
     *ptr_out = static_cast<char*>(base) + offset;
     return MB_OK;
+}
+
+int64_t mb_shard_exchange_bytes(int world, int64_t exchange_rows, int64_t d) {
+    if (world < 1 || world > 8 || exchange_rows < 0 || d <= 0) return -1;
+    return shard_exchange_bytes(world, exchange_rows, d);
+}
+
+mb_status mb_shard_error(mb_context* ctx, const mb_shards* shards, int* error_out) {
+    MB_REQUIRE(ctx != nullptr && shards != nullptr && error_out != nullptr, "null argument");
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    *error_out = 0;
+    if (shards->world <= 1 || shards->exchange[shards->rank] == nullptr) return MB_OK;
+    return shard_error_flag(shards, error_out);
 }
 
 mb_status mb_graph_enable(mb_context* ctx, int on) {
@@ -1155,7 +1180,10 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
         for (int i = 0; i < sh->world && i < 8; i++) {
             key.push_back((uint64_t)(uintptr_t)sh->tables[i]);
             key.push_back((uint64_t)(uintptr_t)sh->states[i]);
+            key.push_back((uint64_t)(uintptr_t)sh->exchange[i]);
         }
+        key.push_back((uint64_t)sh->exchange_rows);
+        key.push_back((uint64_t)sh->single_process);
     }
     if (ctx->sg.key != key) {
         if (ctx->sg.valid || ctx->sg.exec) {
@@ -1255,7 +1283,8 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     MB_CUDA_TRY(cudaGraphLaunch(ctx->sg.exec, ctx->gstream));
     MB_CUDA_TRY(cudaEventRecord(ctx->ev_out, ctx->gstream));
     MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out, 0));
-    count_launch(sh != nullptr && sh->world > 1 ? 31 : 29);  // kernels inside the replayed graph (mb_launch_count stays an honest kernel count)
+    // kernels inside the replayed graph (mb_launch_count stays an honest kernel count); sharded: + fetch, bounds, 3 barriers, world-1 applies
+    count_launch(sh != nullptr && sh->world > 1 ? 29 + 2 + (sh->single_process ? 0 : 3) + (sh->world - 1) : 29);
     return MB_OK;
 }
 
@@ -1277,6 +1306,16 @@ static mb_status check_shards(const mb_shards* sh) {
     MB_REQUIRE(sh != nullptr && sh->world >= 1 && sh->world <= 8 && sh->rows_per_rank > 0, "bad shard description");
     MB_REQUIRE(sh->rank >= 0 && sh->rank < sh->world, "shard rank out of range");
     for (int i = 0; i < sh->world; i++) MB_REQUIRE(sh->tables[i] != nullptr && sh->states[i] != nullptr, "null shard pointer");
+    if (sh->world > 1) {
+        for (int i = 0; i < sh->world; i++) MB_REQUIRE(sh->exchange[i] != nullptr, "null exchange area (mb_shard_exchange_bytes)");
+        MB_REQUIRE(sh->exchange_rows > 0, "exchange_rows must be positive");
+    }
+    return MB_OK;
+}
+
+static mb_status check_shard_capacity(const mb_shards* sh, const mb_batch* b) {
+    if (sh != nullptr && sh->world > 1 && b != nullptr)
+        MB_REQUIRE(2 * b->B + 2 * (int64_t)b->C * b->N <= sh->exchange_rows, "batch larger than the shards' exchange_rows (2B + 2CN gradient rows per inbox)");
     return MB_OK;
 }
 
@@ -1284,6 +1323,7 @@ mb_status mb_train_step_sharded(mb_context* ctx, const mb_batch* batch, const mb
                                 int reduction, int precision, float* loss, float* rel_grad, float* inv_rel_grad, void* stream) {
     MB_REQUIRE(ctx != nullptr && unique_ids != nullptr, "null context / ids");
     MB_TRY(check_shards(shards));
+    MB_TRY(check_shard_capacity(shards, batch));
     MB_REQUIRE(batch == nullptr || ld >= batch->d, "ld < d");
     MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
     MB_REQUIRE(reduction == MB_REDUCTION_MEAN || reduction == MB_REDUCTION_SUM, "unknown reduction");
@@ -1358,6 +1398,7 @@ mb_status mb_train_step_sharded_host_async(mb_context* ctx, const mb_batch* hb, 
                                            float lr, int reduction, int precision, float* rel_grad, float* inv_rel_grad, int* ticket, void* stream) {
     MB_REQUIRE(ticket != nullptr, "ticket is null");
     MB_TRY(check_shards(shards));
+    MB_TRY(check_shard_capacity(shards, hb));
     return host_step_enqueue(ctx, hb, shards, shards->tables[shards->rank], shards->states[shards->rank], ld, unique_ids_host, lr, reduction, precision,
                              rel_grad, inv_rel_grad, (cudaStream_t)stream, ticket);
 }

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "decoder_vec.cuh"
+#include "kernels.h"
 
 namespace mb {
 
@@ -748,7 +749,7 @@ mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int6
 
 mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                             const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                            const int64_t* ids, float lr, cudaStream_t st, const float* state_cache) {
+                            const int64_t* ids, float lr, cudaStream_t st, const int64_t* owner_bounds) {
     if (n_seg == 0) return MB_OK;
     const bool vec_ok = (d % 4 == 0) && d <= 512 && al16(rows) && (!out || (al16(out) && out_ld % 4 == 0)) && (!state || (al16(state) && state_ld % 4 == 0)) &&
                         (!delta_e || (al16(delta_e) && al16(delta_s))) && (!table || (al16(table) && al16(state_table) && ld % 4 == 0));
@@ -758,7 +759,20 @@ mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, co
     }
     if (!vec_ok)
         return launch_segment_reduce(mode, rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, lr, st);
-    vec::SegVArgs a{rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, -lr, make_sp(sh), state_cache};
+    vec::SegVArgs a{rows, slots, offsets, n_seg, d, out, out_ld, state, state_ld, delta_e, delta_s, table, state_table, ld, ids, -lr, make_sp(sh), owner_bounds};
+    for (int i = 0; i < 8; i++) {
+        a.inbox_ids[i] = nullptr;
+        a.inbox_rows[i] = nullptr;
+    }
+    a.inbox_cap = 0;
+    if (sh != nullptr && sh->world > 1) {
+        if (mode == 2 && owner_bounds == nullptr) {
+            set_error("sharded update needs the owner bounds of the batch");
+            return MB_ERR_INVALID;
+        }
+        shard_inbox_ptrs(sh, d, a.inbox_ids, a.inbox_rows);
+        a.inbox_cap = sh->exchange_rows;
+    }
     int grid = warp_grid(n_seg);
 #define MB_SEG(MODE)                                                                      \
     if (d <= 128)                                                                         \

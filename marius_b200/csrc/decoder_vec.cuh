@@ -577,7 +577,11 @@ struct SegVArgs {
     const int64_t* ids;
     float neg_lr;
     ShardPtrs sp;
-    const float* state_cache;  // sharded: [n_seg, d] copies of the remote rows' Adagrad state (fetch_remote_rows_kernel<.., true>) or null
+    // sharded: the summed gradient row of a remote unique row u goes to slot u - owner_bounds[owner] of this rank's inbox at the owner
+    const int64_t* owner_bounds;  // [world + 1] positions in the sorted unique-id list (owner_bounds_kernel)
+    int64_t* inbox_ids[8];
+    float* inbox_rows[8];
+    int64_t inbox_cap;
 };
 
 __device__ __forceinline__ void adagrad4(const float4& g, const float4& s, float neg_lr, float4& de, float4& ds, float4& sn) {
@@ -611,9 +615,18 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
                         my_s = a.state_table + r * a.ld;
                     } else {  // the owner's HBM: peer-mapped over NVLink when the owner is another rank
                         const int64_t o = r / a.sp.rows_per_rank, lr_ = r - o * a.sp.rows_per_rank;
-                        my_e = a.sp.table[o] + lr_ * a.ld;
-                        my_s = a.sp.state[o] + lr_ * a.ld;
-                        my_remote = o != a.sp.rank;
+                        if (o == a.sp.rank) {
+                            my_e = a.sp.table[o] + lr_ * a.ld;
+                            my_s = a.sp.state[o] + lr_ * a.ld;
+                        } else {
+                            // remote row: only its gradient row crosses NVLink, into this rank's inbox at the owner (the owner applies Adagrad)
+                            const int64_t slot = u - __ldg(a.owner_bounds + o);
+                            my_remote = 1;
+                            if (slot < a.inbox_cap) {
+                                my_e = a.inbox_rows[o] + slot * d;
+                                a.inbox_ids[o][slot] = r;
+                            }
+                        }
                     }
                 }
                 if (my_end > my_beg) my_row = a.rows + (int64_t)__ldg(a.slots + my_beg) * d;
@@ -627,11 +640,9 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
             float* erow = shfl_ptr(my_e, k);
             float* srow = shfl_ptr(my_s, k);
             const float* row0 = shfl_ptr(my_row, k);
-            // remote row: delta_e and delta_s are ADDED at the owner with fire-and-forget reductions -- the reference's indexAdd of both
-            // deltas (dataloader.cpp:550-564) -- so only the state row crosses NVLink inbound and the embedding row is not read at all
             const bool remote = MODE == 2 && __shfl_sync(0xffffffffu, my_remote, k) != 0;
-            if (MODE == 2 && beg == end) continue;
-            const float* sread = (remote && a.state_cache != nullptr) ? a.state_cache + u * d : srow;  // remote state: the step's local copy
+            if (MODE == 2 && (beg == end || erow == nullptr)) continue;
+            const float* sread = remote ? a.rows : srow;  // (remote rows read no state: something valid, the value is unused)
             float4 e[CH], s[CH], acc[CH];
             const float* g0 = row0 ? row0 : a.rows;  // empty segment (modes 0 / 1): load something valid, add nothing
 #pragma unroll
@@ -671,8 +682,7 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
                     float4 de, ds, sn;
                     adagrad4(acc[c], s[c], a.neg_lr, de, ds, sn);
                     if (remote) {
-                        red_add4_sys(reinterpret_cast<float4*>(erow) + v, de);
-                        red_add4_sys(reinterpret_cast<float4*>(srow) + v, ds);
+                        st4(erow, v, acc[c]);  // gradient row -> inbox slot in the owner's HBM (plain 128-bit stores over NVLink)
                     } else {
                         st_stream(reinterpret_cast<float4*>(erow) + v, addrn4(e[c], de));
                         st_stream(reinterpret_cast<float4*>(srow) + v, sn);

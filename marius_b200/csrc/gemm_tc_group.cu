@@ -25,16 +25,7 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int GBLOCK_K = 64;
-constexpr int GSTAGES = 3;
 constexpr int GTILE_M = 256, GTILE_N = 256, GHALF_N = 128;
-constexpr int G_A_TILE = BLOCK_M * GBLOCK_K * 2;   // 16 KB: this CTA's 128 rows
-constexpr int G_B_TILE = GHALF_N * GBLOCK_K * 2;   // 16 KB: this CTA's half of the tile columns
-constexpr int G_STAGE = 2 * G_A_TILE + 2 * G_B_TILE;
-constexpr int G_EPI_OFFSET = GSTAGES * G_STAGE;
-constexpr int G_BAR_OFFSET = G_EPI_OFFSET + kEpilogueSmemBytes;
-constexpr int G_SMEM_TOTAL = G_BAR_OFFSET + 256 + 1024;
-static_assert(G_SMEM_TOTAL <= 232448, "shared memory budget");
 
 struct GProblem {
     float* D;
@@ -61,8 +52,8 @@ struct GMaps {
     CUtensorMap m[2][5];  // per problem: A_hi, A_lo, B_hi, B_lo, D
 };
 
-constexpr int kConvWarps = 4;
-constexpr int kConvThreads = kTcThreads + 32 * kConvWarps;  // 320: producer, MMA, 4 epilogue warps, 4 converter warps
+constexpr int kConvWarps = 8;
+constexpr int kConvThreads = kTcThreads + 32 * kConvWarps;  // 448: producer, MMA, 4 epilogue warps, 8 converter warps (2 per SM sub-partition)
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -82,6 +73,11 @@ __device__ __forceinline__ void split4_store(uint32_t dst_hi, uint32_t dst_lo, c
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst_hi), "r"(h[0]), "r"(h[1]) : "memory");
     if (want_lo) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst_lo), "r"(l[0]), "r"(l[1]) : "memory");
 }
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {  // read once per tile: keep it out of the (tiny) L1
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
@@ -89,23 +85,45 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-// CONV = false: both operands come from global bf16 hi/lo arrays through TMA (192 threads).
-// CONV = true : the A operand of every problem of the launch is produced by four converter warps from an fp32 matrix (the scores S):
-//               G = exp(S - z_row) (the SoftmaxCrossEntropy gradient, loss.cpp:50-67) or G = S, split into bf16 hi/lo and written
-//               straight into the stage's swizzled operand tiles -- the gradient matrix never exists in global memory (320 threads).
+// Shared-memory layout and pipeline geometry of the two instantiations.
+//   CONV = false (forward scores, diagnostics): k-blocks of 64, 3 operand stages of 64 KB (A hi/lo + B hi/lo), 192 threads.
+//   CONV = true  (backward contractions): the A operand of every problem is produced in the kernel from an fp32 matrix (the scores S):
+//                G = exp(S - z_row) (the SoftmaxCrossEntropy gradient, loss.cpp:50-67) or G = S.  k-blocks of 32: 4 operand stages of
+//                32 KB + a ring of 4 raw fp32 score tiles of 16 KB, so that the score tiles are in flight (TMA) several k-blocks ahead
+//                of their conversion, independently of the operand stages; 448 threads (8 converter warps).  The gradient matrix never
+//                exists in global memory.
+template <bool CONV>
+struct Geo {
+    static constexpr int BK = CONV ? 32 : 64;                 // k-block (bf16 elements)
+    static constexpr int STAGES = CONV ? 4 : 3;
+    static constexpr int A_TILE = BLOCK_M * BK * 2;           // one of hi / lo: this CTA's 128 rows
+    static constexpr int B_TILE = GHALF_N * BK * 2;           // one of hi / lo: this CTA's half of the tile columns
+    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int RAW_SLOTS = CONV ? 4 : 0;
+    static constexpr int RAW_TILE = BLOCK_M * BK * 4;         // fp32 score tile of one k-block (this CTA's part)
+    static constexpr int RAW_OFFSET = STAGES * STAGE;
+    static constexpr int EPI_OFFSET = RAW_OFFSET + RAW_SLOTS * RAW_TILE;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + kEpilogueSmemBytes;
+    static constexpr int SMEM_TOTAL = BAR_OFFSET + 256 + 1024;
+    static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+};
+
 template <bool CONV>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads : kTcThreads, 1) gemm_tc_group_kernel(const __grid_constant__ GMaps maps, const GParams p) {
+    using G = Geo<CONV>;
+    constexpr int BK = G::BK, NST = G::STAGES;
     constexpr int TMEM_COLS = 2 * GTILE_N;
     constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + G_BAR_OFFSET;
+    const uint32_t bar_base = smem_base + G::BAR_OFFSET;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (GSTAGES + s); };
-    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * GSTAGES + b); };
-    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * GSTAGES + 2 + b); };
-    const uint32_t tmem_holder = bar_base + 8u * (2 * GSTAGES + 4);
-    auto raw_bar = [&](int s) { return bar_base + 8u * (2 * GSTAGES + 6 + s); };  // CONV: this CTA's fp32 score tile of stage s has landed
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };
+    auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * NST + b); };
+    auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * NST + 2 + b); };
+    const uint32_t tmem_holder = bar_base + 8u * (2 * NST + 4);
+    auto raw_bar = [&](int s) { return bar_base + 8u * (2 * NST + 6 + s); };  // CONV: this CTA's fp32 score tile in raw slot s has landed
+    auto afull_bar = [&](int s) { return bar_base + 8u * (2 * NST + 6 + G::RAW_SLOTS + s); };  // CONV, non-leader CTA: its A tiles of stage s are written
     volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
@@ -115,16 +133,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
     const int lo_mult = p.passes == 3 ? 2 : 1;
-    const uint32_t stage_tx_pair = (uint32_t)(2 * lo_mult * ((CONV ? 0 : G_A_TILE) + G_B_TILE));
+    const uint32_t stage_tx_pair = (uint32_t)(2 * lo_mult * ((CONV ? 0 : G::A_TILE) + G::B_TILE));
 
     if (warp == 0 && lane == 0) {
         for (int q = 0; q < 2; q++)
             for (int j = 0; j < 5; j++) prefetch_tmap(&maps.m[q][j]);
-        for (int s = 0; s < GSTAGES; s++) {
-            mbar_init(full_bar(s), CONV ? 1 + 2 * kConvWarps : 1);  // + one arrival per converter warp of both CTAs
+        for (int s = 0; s < NST; s++) {
+            mbar_init(full_bar(s), CONV ? 1 + 2 : 1);  // + one arrival per CTA once its converter warps have written the A tiles
             mbar_init(empty_bar(s), 1);
-            mbar_init(raw_bar(s), 1);
         }
+        for (int s = 0; s < G::RAW_SLOTS; s++) mbar_init(raw_bar(s), 1);
+        if (CONV)
+            for (int s = 0; s < NST; s++) mbar_init(afull_bar(s), 1);
         for (int b = 0; b < 2; b++) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 8);
@@ -157,37 +177,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
             const int m0 = e.z + (int)rank * BLOCK_M;
             const int n_eff = ((min(e.x >> 8, pr.N - e.w) + 31) / 32) * 32;
             const int n0 = e.w + (int)rank * (n_eff / 2);
-            const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
+            const int num_k_blocks = (pr.K + BK - 1) / BK;
             const bool a_mn = pr.a_mn != 0, b_mn = pr.b_mn != 0, three = p.passes == 3;
             for (int kb = 0; kb < num_k_blocks; kb++) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                const uint32_t sA_hi = smem_base + stage * G_STAGE;
-                const uint32_t sA_lo = sA_hi + G_A_TILE;
-                const uint32_t sB_hi = sA_lo + G_A_TILE;
-                const uint32_t sB_lo = sB_hi + G_B_TILE;
+                const uint32_t sA_hi = smem_base + stage * G::STAGE;
+                const uint32_t sA_lo = sA_hi + G::A_TILE;
+                const uint32_t sB_hi = sA_lo + G::A_TILE;
+                const uint32_t sB_lo = sB_hi + G::B_TILE;
                 const uint32_t lbar = full_bar(stage) & kPeerMask;
-                const int k0 = kb * GBLOCK_K;
+                const int k0 = kb * BK;
                 if (elect_one()) {
                     if (p.debug_flags & 2) {  // ablation: no TMA loads, the MMAs run on whatever is in shared memory
                         if (leader) mbar_arrive(full_bar(stage));
                     } else {
                         if (leader) mbar_expect_tx(full_bar(stage), stage_tx_pair);
                         if (CONV) {
-                            // this CTA's fp32 score tile goes into the stage's A region (hi + lo tiles = exactly its 32 KB) and is converted
-                            // in place by the converter warps; it completes on this CTA's own raw barrier
-                            mbar_expect_tx(raw_bar(stage), 2 * G_A_TILE);
-                            if (!a_mn)
-                                tma_load_3d(sA_hi, mA_hi, raw_bar(stage), k0, m0, b);  // box {64 K columns, 128 M rows}
-                            else
-                                tma_load_3d(sA_hi, mA_hi, raw_bar(stage), m0, k0, b);  // box {128 M columns, 64 K rows}
+                            // the A tiles of the stage are written by the converter warps
                         } else if (!a_mn) {
                             tma_load_3d_2sm(sA_hi, mA_hi, lbar, k0, m0, b);
                             if (three) tma_load_3d_2sm(sA_lo, mA_lo, lbar, k0, m0, b);
                         } else {
 #pragma unroll
                             for (int j = 0; j < BLOCK_M / 64; j++) {
-                                tma_load_3d_2sm(sA_hi + j * (GBLOCK_K * 128), mA_hi, lbar, m0 + 64 * j, k0, b);
-                                if (three) tma_load_3d_2sm(sA_lo + j * (GBLOCK_K * 128), mA_lo, lbar, m0 + 64 * j, k0, b);
+                                tma_load_3d_2sm(sA_hi + j * (BK * 128), mA_hi, lbar, m0 + 64 * j, k0, b);
+                                if (three) tma_load_3d_2sm(sA_lo + j * (BK * 128), mA_lo, lbar, m0 + 64 * j, k0, b);
                             }
                         }
                         if (!b_mn) {
@@ -196,14 +210,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                         } else {
 #pragma unroll
                             for (int j = 0; j < GHALF_N / 64; j++) {
-                                tma_load_3d_2sm(sB_hi + j * (GBLOCK_K * 128), mB_hi, lbar, n0 + 64 * j, k0, b);
-                                if (three) tma_load_3d_2sm(sB_lo + j * (GBLOCK_K * 128), mB_lo, lbar, n0 + 64 * j, k0, b);
+                                tma_load_3d_2sm(sB_hi + j * (BK * 128), mB_hi, lbar, n0 + 64 * j, k0, b);
+                                if (three) tma_load_3d_2sm(sB_lo + j * (BK * 128), mB_lo, lbar, n0 + 64 * j, k0, b);
                             }
                         }
                     }
                 }
                 __syncwarp();
-                if (++stage == GSTAGES) {
+                if (++stage == NST) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -215,8 +229,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
             int stage = 0;
             uint32_t phase = 0;
             int local_tile = 0;
-            // descriptor words that never change: SBO = 1024 B (8 rows x 128 B), version 1, SWIZZLE_128B
-            constexpr uint32_t kDescHi = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
+            // K-major tiles: rows of BK * 2 bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row groups SBO apart, LBO unused, k-step +32 B.
+            // MN-major tiles (SWIZZLE_128B): 64-element MN slabs BK * 128 B apart (LBO), 8-k-row groups 1024 B apart (SBO), k-step +2048 B.
+            constexpr uint32_t kLayoutK = (BK * 2 == 128) ? 2u : 4u;
+            constexpr uint32_t kDescHiK = ((uint32_t)((8 * BK * 2) >> 4) & 0x3fffu) | (1u << 14) | (kLayoutK << 29);
+            constexpr uint32_t kDescHiMN = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
             const uint32_t npass = (p.debug_flags & 4) ? 0u : (uint32_t)p.passes;  // bit 2: ablation, no MMAs
             int4 e_next = p.table[cluster_id];
             for (int r = 0; r < p.rounds; r++) {
@@ -225,15 +242,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                 if (e.x < 0) continue;
                 const GProblem& pr = p.prob[e.x & 0xff];
                 const bool a_mn = pr.a_mn != 0, b_mn = pr.b_mn != 0;
-                // K-major SW128: LBO unused (16), k-step +32 B.  MN-major SW128: LBO = slab stride, k-step +2048 B.  (units of 16 B below)
-                const uint32_t a_lbo = (a_mn ? (uint32_t)(GBLOCK_K * 128) >> 4 : 1u) << 16, a_kstep = a_mn ? 2048u >> 4 : 32u >> 4;
-                const uint32_t b_lbo = (b_mn ? (uint32_t)(GBLOCK_K * 128) >> 4 : 1u) << 16, b_kstep = b_mn ? 2048u >> 4 : 32u >> 4;
+                const uint32_t a_lbo = (a_mn ? (uint32_t)(BK * 128) >> 4 : 1u) << 16, a_kstep = a_mn ? 2048u >> 4 : 32u >> 4;
+                const uint32_t b_lbo = (b_mn ? (uint32_t)(BK * 128) >> 4 : 1u) << 16, b_kstep = b_mn ? 2048u >> 4 : 32u >> 4;
+                const uint32_t a_hi32 = a_mn ? kDescHiMN : kDescHiK, b_hi32 = b_mn ? kDescHiMN : kDescHiK;
                 const int buf = local_tile & 1;
                 const uint32_t buf_phase = (uint32_t)((local_tile >> 1) & 1);
                 local_tile++;
                 const int n_eff = ((min(e.x >> 8, pr.N - e.w) + 31) / 32) * 32;
                 const uint32_t idesc = make_idesc(GTILE_M, n_eff, a_mn, b_mn);
-                const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
+                const int num_k_blocks = (pr.K + BK - 1) / BK;
                 mbar_wait(tempty_bar(buf), buf_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(buf * GTILE_N);
@@ -241,11 +258,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                 for (int kb = 0; kb < num_k_blocks; kb++) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint32_t sA_hi = (smem_base + stage * G_STAGE) >> 4;  // 16-byte units, < 2^14
-                    const uint32_t sA_lo = sA_hi + (G_A_TILE >> 4);
-                    const uint32_t sB_hi = sA_lo + (G_A_TILE >> 4);
-                    const uint32_t sB_lo = sB_hi + (G_B_TILE >> 4);
-                    const int k_valid = min(GBLOCK_K, pr.K - kb * GBLOCK_K);
+                    const uint32_t sA_hi = (smem_base + stage * G::STAGE) >> 4;  // 16-byte units, < 2^14
+                    const uint32_t sA_lo = sA_hi + (G::A_TILE >> 4);
+                    const uint32_t sB_hi = sA_lo + (G::A_TILE >> 4);
+                    const uint32_t sB_lo = sB_hi + (G::B_TILE >> 4);
+                    const int k_valid = min(BK, pr.K - kb * BK);
                     const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
                     if (elect_one()) {
 #pragma unroll
@@ -254,10 +271,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                                 const uint32_t sa = a_lbo | ((prod == 2) ? sA_lo : sA_hi);
                                 const uint32_t sb = b_lbo | ((prod == 1) ? sB_lo : sB_hi);
 #pragma unroll
-                                for (int ks = 0; ks < GBLOCK_K / UMMA_K; ks++) {
+                                for (int ks = 0; ks < BK / UMMA_K; ks++) {
                                     if (ks < ksteps) {
-                                        const uint64_t adesc = ((uint64_t)kDescHi << 32) | (uint64_t)(sa + ks * a_kstep);
-                                        const uint64_t bdesc = ((uint64_t)kDescHi << 32) | (uint64_t)(sb + ks * b_kstep);
+                                        const uint64_t adesc = ((uint64_t)a_hi32 << 32) | (uint64_t)(sa + ks * a_kstep);
+                                        const uint64_t bdesc = ((uint64_t)b_hi32 << 32) | (uint64_t)(sb + ks * b_kstep);
                                         umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
                                         accumulate = 1;
                                     }
@@ -268,7 +285,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                         if (kb == num_k_blocks - 1) umma_commit_2sm(tfull_bar(buf));
                     }
                     __syncwarp();
-                    if (++stage == GSTAGES) {
+                    if (++stage == NST) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        } else if (CONV) {
+            // Non-leader CTA, CONV: this otherwise idle warp forwards "this CTA's A tiles of the stage are written" to the leader's full
+            // barrier.  The converter warps only pay a CTA-local arrive; the cross-CTA hop happens here, off their critical path, and
+            // without a GPU-scope memory barrier (measured ~0.9 us per arrive with .release.cluster: the A tiles are settled in this CTA's
+            // shared memory -- every writer fenced and synchronised -- before this warp is told).
+            int stage = 0;
+            uint32_t phase = 0;
+            int4 e_next = p.table[cluster_id];
+            for (int r = 0; r < p.rounds; r++) {
+                const int4 e = e_next;
+                if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+                if (e.x < 0) continue;
+                const int num_k_blocks = (p.prob[e.x & 0xff].K + BK - 1) / BK;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(afull_bar(stage), phase);
+                    if (elect_one()) mbar_arrive_remote_light(full_bar(stage), 0);
+                    __syncwarp();
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -325,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                 }
                 if (pr.tma_store) {
                     if (!(p.debug_flags & 1))
-                        stage_and_store(rg, smem_base + G_EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, mD, col0,
+                        stage_and_store(rg, smem_base + G::EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, mD, col0,
                                         m0 + q * 32, b);
                     epi_chunk++;
                 } else if (row_ok) {
@@ -354,19 +394,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
         }
         if (elect_one()) bulk_wait_all();
     } else {
-        // ================= converter warps 6..9 (both CTAs, CONV only): fp32 scores -> G -> bf16 hi/lo operand tiles, in place =================
-        // The producer's TMA drops this CTA's fp32 score tile (32 KB, row-major, no swizzle) into the stage's A region; these warps read it
-        // into registers, synchronise among themselves, and overwrite the region with the operand tiles the tensor core expects:
-        // 128 shared-memory rows of 128 bytes (64 bf16), SWIZZLE_128B (16-byte chunk index XOR (row & 7)), hi tile then lo tile --
-        // exactly what the TMA loads of the non-CONV kernel produce:
-        //   K-major A (dA = G . Neg):    operand row i = M row m0 + i,                   its 64 elements = K columns k0 .. k0 + 63
-        //   MN-major A (dNeg = G^T . A): operand row i = 64 * slab + K row (k0 + i % 64), its 64 elements = M columns m0 + 64 * slab ..
-        // Either way an operand row is 64 consecutive elements of one score row.  16 threads handle a row (one float4 each: conflict-free
-        // loads, and their 8-byte stores cover one 128-byte operand row = all 32 banks); the S prefetch depth is the stage ring itself.
+        // ================= converter warps 6..13 (both CTAs, CONV only): fp32 scores -> G -> bf16 hi/lo operand tiles =================
+        // Two groups of four warps work on ALTERNATE k-blocks (group g takes the k-blocks whose running number is g mod 2), so the serial
+        // chain of one k-block (wait for the raw tile, load, synchronise, convert, fence, synchronise, arrive) may take two k-block periods
+        // of the tensor core: the groups pipeline against each other instead of splitting every k-block eight ways.
+        // Raw ring: this CTA's fp32 score tile of k-block n (128 operand rows x 32 K, 16 KB, row-major, no swizzle) is loaded by TMA into
+        // slot n % 4, RAW_SLOTS k-blocks ahead of its conversion; thread 0 of the group issues the load of k-block n + RAW_SLOTS as soon as
+        // every thread of the group has read slot n % 4 (the load cursor walks the same tile table, across tile boundaries).
+        // Operand stage: the A region gets what the TMA loads of the non-CONV kernel would produce for BK = 32:
+        //   K-major A (dA = G . Neg):    128 rows (M row m0 + i) of 64 bytes (32 K), SWIZZLE_64B: 16-byte chunk index XOR ((row >> 1) & 3)
+        //   MN-major A (dNeg = G^T . A): two slabs (64 M columns each) of 32 rows (K row k0 + r) of 128 bytes, SWIZZLE_128B
+        // hi tile then lo tile.  Thread mapping: consecutive threads take consecutive float4 of a raw row (conflict-free 128-bit loads);
+        // their 8-byte stores cover whole operand rows (all 32 banks).
+        constexpr int RS = G::RAW_SLOTS > 0 ? G::RAW_SLOTS : 2;
+        static_assert(RS % 2 == 0, "the two converter groups own alternate raw slots");
+        constexpr int kGroupThreads = 16 * kConvWarps;                       // 128
+        constexpr int kPieces = (BLOCK_M * BK / 4) / kGroupThreads;           // float4 pieces per thread per k-block (8)
         const int ct = (int)threadIdx.x - kTcThreads;
-        const int t16 = ct & 15, rsub = ct >> 4;  // float4 index within the operand row, row within a pass of 8 rows
-        int stage = 0;
-        uint32_t phase = 0;
+        const int grp = ct / kGroupThreads, gt = ct % kGroupThreads;
+        const int bar_read = 1 + 2 * grp, bar_done = 2 + 2 * grp;             // named barriers of the group
+        const uint32_t raw_base = smem_base + G::RAW_OFFSET;
+        // ---- load cursor (thread 0 of each group): walks every (tile, k-block), RAW_SLOTS ahead of the conversion
+        int lr = -1, lkb = 0, lnkb = 0;  // table round, k-block, k-blocks of that tile
+        int4 le = make_int4(-1, 0, 0, 0);
+        auto load_advance = [&]() {      // move to the next (tile, k-block); lr >= p.rounds when the table is exhausted
+            if (lr >= 0 && lr < p.rounds && ++lkb < lnkb) return;
+            lkb = 0;
+            while (++lr < p.rounds) {
+                le = p.table[lr * num_clusters + cluster_id];
+                if (le.x >= 0) {
+                    lnkb = (p.prob[le.x & 0xff].K + BK - 1) / BK;
+                    return;
+                }
+            }
+        };
+        auto load_issue = [&](int slot) {  // TMA of the score tile at the load cursor into raw slot `slot`
+            if (lr >= p.rounds) return;
+            const int pi = le.x & 0xff;
+            const GProblem& lp = p.prob[pi];
+            const int lm = le.z + (int)rank * BLOCK_M;
+            mbar_expect_tx(raw_bar(slot), G::RAW_TILE);
+            if (lp.a_mn == 0)
+                tma_load_3d(raw_base + slot * G::RAW_TILE, &maps.m[pi][0], raw_bar(slot), lkb * BK, lm, le.y);  // box {32 K columns, 128 M rows}
+            else
+                tma_load_3d(raw_base + slot * G::RAW_TILE, &maps.m[pi][0], raw_bar(slot), lm, lkb * BK, le.y);  // box {128 M columns, 32 K rows}
+        };
+        if (gt == 0) {
+            load_advance();
+            for (int s = 0; s < G::RAW_SLOTS; s++) {
+                if ((s & 1) == grp) load_issue(s);
+                load_advance();
+            }
+        }
+        int stage = 0, slot = 0;
+        uint32_t phase = 0, raw_phase = 0;
+        int n = 0;  // running k-block number
         int4 e_next = p.table[cluster_id];
         for (int r = 0; r < p.rounds; r++) {
             const int4 e = e_next;
@@ -375,66 +457,100 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
             const GProblem& pr = p.prob[e.x & 0xff];
             const int b = e.y;
             const int m_base = e.z + (int)rank * BLOCK_M;
-            const int num_k_blocks = (pr.K + GBLOCK_K - 1) / GBLOCK_K;
+            const int num_k_blocks = (pr.K + BK - 1) / BK;
             const bool a_mn = pr.a_mn != 0, want_lo = p.passes == 3, expo = pr.conv_mode == 1;
-            const float* zb = expo ? pr.conv_z + (int64_t)b * pr.conv_rows : nullptr;
-            // per-row shift (already scaled by log2 e) of the 16 operand rows this thread touches in k-block kb.  The loads are issued one
-            // k-block ahead and NOTHING consumes them until the conversion (an in-order warp stalls at the first use of a load result)
-            float zc[16], zn[16];
-            auto load_z = [&](int kb, float (&z)[16]) {
-                if (!expo) return;
-                const int k0 = kb * GBLOCK_K;
+            const int rows_lim = pr.conv_rows, cols_lim = pr.conv_cols;
+            const int lim_m = a_mn ? cols_lim : rows_lim, lim_k = a_mn ? rows_lim : cols_lim;  // extents along the tile's M / K directions
+            const bool m_interior = m_base + BLOCK_M <= lim_m;
+            const float* zb = expo ? pr.conv_z + (int64_t)b * rows_lim : nullptr;
+            // piece j of this thread: float4 index f = gt + 128 j of the raw tile
+            //   K-major  raw [128 rows][8 float4]:   row i = f >> 3, c = f & 7      -> operand row i, K elements 4c .. 4c+3
+            //   MN-major raw [32 K rows][32 float4]: K row kr = f >> 5, c = f & 31   -> slab c >> 4, operand row kr, M elements 4 (c & 15) ..
+            // zfix[j]: what is known about the piece's shift for the whole tile.  K-major: the shift itself (the piece's score row does not
+            // change with the k-block), +inf if the row lies outside the matrix.  MN-major: +inf if the piece's columns lie outside, else
+            // -inf (the shift of its row is loaded per k-block and combined with fmax).  A +inf shift turns the TMA's zero fill into
+            // exp2(0 - inf) = 0.
+            uint32_t dst_off[kPieces];
+            float zfix[kPieces];
+            const int kr0 = gt >> 5;  // MN-major: the K row of piece j is kr0 + 4 j
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int i = rsub + 8 * j;
-                    const int srow = a_mn ? k0 + (i & 63) : m_base + i;
-                    z[j] = __ldg(zb + min(srow, pr.conv_rows - 1));
+            for (int j = 0; j < kPieces; j++) {
+                const int f = gt + kGroupThreads * j;
+                if (!a_mn) {
+                    const int i = f >> 3, c = f & 7;
+                    dst_off[j] = (uint32_t)i * 64u + (uint32_t)(((c >> 1) ^ ((i >> 1) & 3)) << 4) + (uint32_t)(c & 1) * 8u;
+                    zfix[j] = (expo && m_base + i < rows_lim) ? __ldg(zb + m_base + i) : INFINITY;
+                } else {
+                    const int kr = f >> 5, c = f & 31;
+                    dst_off[j] = (uint32_t)(c >> 4) * (uint32_t)(BK * 128) + (uint32_t)kr * 128u + (uint32_t)((((c & 15) >> 1) ^ (kr & 7)) << 4) +
+                                 (uint32_t)(c & 1) * 8u;
+                    zfix[j] = (m_base + 4 * c < cols_lim) ? -INFINITY : INFINITY;
                 }
-            };
-            auto convert = [&](int kb, const float (&z)[16]) {
-                mbar_wait(raw_bar(stage), phase);
-                const uint32_t sA = smem_base + stage * G_STAGE;
-                const int k0 = kb * GBLOCK_K;
-                float4 v[16];
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int i = rsub + 8 * j;
-                    // raw tile: K-major [128 rows][64 floats]; MN-major [64 K rows][128 floats] (operand row i = K row i % 64, slab i / 64)
-                    const uint32_t off = a_mn ? (uint32_t)(i & 63) * 512u + (uint32_t)(i & 64) * 4u + 16u * t16 : (uint32_t)i * 256u + 16u * t16;
-                    v[j] = lds_f4(sA + off);
-                }
-                named_barrier_sync(1, 32 * kConvWarps);  // every converter thread holds its part of the raw tile: the region may be overwritten
-#pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const int i = rsub + 8 * j;
-                    float g[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            }
+            const int kcol = 4 * (gt & 7);  // K-major: first K column of this thread's pieces within the k-block
+#pragma unroll 1
+            for (int kb = 0; kb < num_k_blocks; kb++, n++) {
+                if ((n & 1) == grp) {
+                    const int k0 = kb * BK;
+                    const bool k_interior = k0 + BK <= lim_k;  // (warp-uniform)
+                    float z[kPieces];
                     if (expo) {
-                        // out-of-range elements (TMA zero-filled them): exp2(0 - inf) = 0 keeps them zero
-                        const int srow = a_mn ? k0 + (i & 63) : m_base + i;
-                        const int scol = a_mn ? m_base + (i & 64) + 4 * t16 : k0 + 4 * t16;
-                        const float zz = (srow < pr.conv_rows && scol < pr.conv_cols) ? z[j] : INFINITY;
+                        if (!a_mn) {
+                            const bool col_ok = k_interior || k0 + kcol < cols_lim;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) g[q] = ex2_approx(fmaf(g[q], kLog2e, -zz));
+                            for (int j = 0; j < kPieces; j++) z[j] = col_ok ? zfix[j] : INFINITY;
+                        } else {
+                            // issued before the wait for the raw tile; a batch's shifts (4 KB) stay in L1
+                            const float* zk = zb + k0 + kr0;
+#pragma unroll
+                            for (int j = 0; j < kPieces; j++) {
+                                const float zl = (k_interior || k0 + kr0 + 4 * j < rows_lim) ? __ldg(zk + 4 * j) : INFINITY;
+                                z[j] = fmaxf(zl, zfix[j]);
+                            }
+                        }
                     }
-                    const uint32_t off = (uint32_t)i * 128u + (uint32_t)(((t16 >> 1) ^ (i & 7)) << 4) + (uint32_t)(t16 & 1) * 8u;
-                    split4_store(sA + off, sA + G_A_TILE + off, g, want_lo);
+                    mbar_wait(raw_bar(slot), raw_phase);
+                    float4 v[kPieces];
+#pragma unroll
+                    for (int j = 0; j < kPieces; j++) v[j] = lds_f4(raw_base + slot * G::RAW_TILE + (uint32_t)(gt + kGroupThreads * j) * 16u);
+                    named_barrier_sync(bar_read, kGroupThreads);  // every thread of the group holds its part of the raw tile: the slot is free
+                    if (gt == 0) load_issue(slot);
+                    mbar_wait(empty_bar(stage), phase ^ 1u);  // the tensor core is done with the operand stage's previous contents
+                    const uint32_t sA = smem_base + stage * G::STAGE;
+                    if (expo) {
+#pragma unroll
+                        for (int j = 0; j < kPieces; j++) {
+                            v[j].x = ex2_approx(fmaf(v[j].x, kLog2e, -z[j]));
+                            v[j].y = ex2_approx(fmaf(v[j].y, kLog2e, -z[j]));
+                            v[j].z = ex2_approx(fmaf(v[j].z, kLog2e, -z[j]));
+                            v[j].w = ex2_approx(fmaf(v[j].w, kLog2e, -z[j]));
+                        }
+                    }
+                    if (want_lo) {
+#pragma unroll
+                        for (int j = 0; j < kPieces; j++) {
+                            const float g[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                            split4_store(sA + dst_off[j], sA + G::A_TILE + dst_off[j], g, true);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kPieces; j++) {
+                            const float g[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                            split4_store(sA + dst_off[j], sA + G::A_TILE + dst_off[j], g, false);
+                        }
+                    }
+                    fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    named_barrier_sync(bar_done, kGroupThreads);  // the CTA's A tiles are complete: one CTA-local arrival (the non-leader's is
+                    if (gt == 32) mbar_arrive(leader ? full_bar(stage) : afull_bar(stage));  // forwarded to the leader's full barrier by its warp 1)
                 }
-                fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(full_bar(stage), 0);
-                if (++stage == GSTAGES) {
+                if (gt == 0) load_advance();  // the cursor stays RAW_SLOTS k-blocks ahead of n
+                if (++stage == NST) {
                     stage = 0;
                     phase ^= 1u;
                 }
-            };
-            load_z(0, zc);
-#pragma unroll 1
-            for (int kb = 0; kb < num_k_blocks; kb += 2) {
-                if (kb + 1 < num_k_blocks) load_z(kb + 1, zn);
-                convert(kb, zc);
-                if (kb + 1 < num_k_blocks) {
-                    if (kb + 2 < num_k_blocks) load_z(kb + 2, zc);
-                    convert(kb + 1, zn);
+                if (++slot == RS) {
+                    slot = 0;
+                    raw_phase ^= 1u;
                 }
             }
         }
@@ -549,6 +665,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
         }
         const bool lo = passes == 3;
         const bool conv_i = g.conv_mode != 0;
+        const uint32_t bk = conv_i ? (uint32_t)Geo<true>::BK : (uint32_t)Geo<false>::BK;  // k-block = K rows of an MN-major box
         if (i == 0) conv = conv_i;
         if (conv_i != conv) {
             set_error("gemm_tc_grouped: all problems of a launch must agree on conv_mode");
@@ -556,23 +673,35 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
         }
         if (conv_i) {
             if (g.conv_src == nullptr || (g.conv_mode == 1 && g.conv_z == nullptr) || (reinterpret_cast<uintptr_t>(g.conv_src) & 15u) || (g.conv_ld % 4) ||
-                (g.conv_sb % 4) || (g.conv_cols % 8) || g.conv_rows != (g.a_mn ? g.K : g.M) || g.conv_cols != (g.a_mn ? g.M : g.K)) {
-                set_error("gemm_tc_grouped: bad conv operand (alignment / extents)");
+                (g.conv_sb % 4) || (g.conv_cols % 8) || g.conv_rows != (g.a_mn ? g.K : g.M) || g.conv_cols != (g.a_mn ? g.M : g.K) || !g.b_mn) {
+                set_error("gemm_tc_grouped: bad conv operand (alignment / extents; the B operand must be MN-major)");
                 return MB_ERR_INVALID;
+            }
+            // the fp32 score matrix, loaded as plain row-major tiles (no swizzle) into the raw ring
+            cuuint64_t dims[3] = {(cuuint64_t)g.conv_cols, (cuuint64_t)g.conv_rows, (cuuint64_t)g.batches};
+            cuuint64_t strides[2] = {(cuuint64_t)g.conv_ld * 4, (cuuint64_t)(g.batches == 1 ? (int64_t)g.conv_rows * g.conv_ld : g.conv_sb) * 4};
+            cuuint32_t box[3] = {g.a_mn ? (cuuint32_t)BLOCK_M : bk, g.a_mn ? bk : (cuuint32_t)BLOCK_M, 1};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = encode_fn()(&maps.m[i][0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.conv_src), dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled (score matrix) failed with CUresult " + std::to_string((int)r));
+                return MB_ERR_CUDA;
             }
         } else if (!g.a_mn) {
             MB_TRY(bf16_map(&maps.m[i][0], g.A_hi, g.K, g.M, g.batches, g.lda, g.sAb, BLOCK_M));
             MB_TRY(bf16_map(&maps.m[i][1], lo ? g.A_lo : g.A_hi, g.K, g.M, g.batches, g.lda, g.sAb, BLOCK_M));
         } else {
-            MB_TRY(bf16_map(&maps.m[i][0], g.A_hi, g.M, g.K, g.batches, g.lda, g.sAb, GBLOCK_K));
-            MB_TRY(bf16_map(&maps.m[i][1], lo ? g.A_lo : g.A_hi, g.M, g.K, g.batches, g.lda, g.sAb, GBLOCK_K));
+            MB_TRY(bf16_map(&maps.m[i][0], g.A_hi, g.M, g.K, g.batches, g.lda, g.sAb, bk));
+            MB_TRY(bf16_map(&maps.m[i][1], lo ? g.A_lo : g.A_hi, g.M, g.K, g.batches, g.lda, g.sAb, bk));
         }
         if (!g.b_mn) {
             MB_TRY(bf16_map(&maps.m[i][2], g.B_hi, g.K, g.N, g.batches, g.ldb, g.sBb, GHALF_N));
             MB_TRY(bf16_map(&maps.m[i][3], lo ? g.B_lo : g.B_hi, g.K, g.N, g.batches, g.ldb, g.sBb, GHALF_N));
         } else {
-            MB_TRY(bf16_map(&maps.m[i][2], g.B_hi, g.N, g.K, g.batches, g.ldb, g.sBb, GBLOCK_K));
-            MB_TRY(bf16_map(&maps.m[i][3], lo ? g.B_lo : g.B_hi, g.N, g.K, g.batches, g.ldb, g.sBb, GBLOCK_K));
+            MB_TRY(bf16_map(&maps.m[i][2], g.B_hi, g.N, g.K, g.batches, g.ldb, g.sBb, bk));
+            MB_TRY(bf16_map(&maps.m[i][3], lo ? g.B_lo : g.B_hi, g.N, g.K, g.batches, g.ldb, g.sBb, bk));
         }
         bool tma_store = ((reinterpret_cast<uintptr_t>(g.D) & 15u) == 0) && (g.ldd % 4 == 0) && (g.batches == 1 || g.sDb % 4 == 0);
         if (tma_store) {
@@ -585,21 +714,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
             if (r != CUDA_SUCCESS) tma_store = false;
         }
         if (!tma_store) maps.m[i][4] = maps.m[i][2];
-        if (conv_i) {
-            // the fp32 score matrix, loaded as plain row-major tiles (no swizzle) into the stage's A region
-            cuuint64_t dims[3] = {(cuuint64_t)g.conv_cols, (cuuint64_t)g.conv_rows, (cuuint64_t)g.batches};
-            cuuint64_t strides[2] = {(cuuint64_t)g.conv_ld * 4, (cuuint64_t)(g.batches == 1 ? (int64_t)g.conv_rows * g.conv_ld : g.conv_sb) * 4};
-            cuuint32_t box[3] = {g.a_mn ? 128u : 64u, g.a_mn ? 64u : 128u, 1};
-            cuuint32_t estr[3] = {1, 1, 1};
-            CUresult r = encode_fn()(&maps.m[i][0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.conv_src), dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) {
-                set_error("cuTensorMapEncodeTiled (score matrix) failed with CUresult " + std::to_string((int)r));
-                return MB_ERR_CUDA;
-            }
-            maps.m[i][1] = maps.m[i][2];  // (never used: a valid descriptor for prefetch.tensormap)
-        }
+        if (conv_i) maps.m[i][1] = maps.m[i][2];  // (never used: a valid descriptor for prefetch.tensormap)
         GProblem& q = p.prob[i];
         q.D = g.D;
         q.ldd = g.ldd;
@@ -737,14 +852,14 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     // function attributes are per device (one process may drive several: the reference's device_models_): opt in once on each
     static std::atomic<bool> attr_set[64];
     if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
-        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
-        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_TOTAL));
+        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM_TOTAL));
+        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM_TOTAL));
         if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
     if (conv)
-        gemm_tc_group_kernel<true><<<2 * clusters, kConvThreads, G_SMEM_TOTAL, st>>>(maps, p);
+        gemm_tc_group_kernel<true><<<2 * clusters, kConvThreads, Geo<true>::SMEM_TOTAL, st>>>(maps, p);
     else
-        gemm_tc_group_kernel<false><<<2 * clusters, kTcThreads, G_SMEM_TOTAL, st>>>(maps, p);
+        gemm_tc_group_kernel<false><<<2 * clusters, kTcThreads, Geo<false>::SMEM_TOTAL, st>>>(maps, p);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

@@ -196,6 +196,17 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
         ::"r"(bar), "r"(cta)
         : "memory");
 }
+// the same arrive with the default semantics (release at CTA scope): no GPU-scope memory barrier in front of it.  For signals whose
+// payload is already settled in the arriving CTA's shared memory (written by threads that fenced and synchronised before this thread
+// was told), which is what the 2-CTA pipelines of CUTLASS use for their cross-CTA barrier arrivals.
+__device__ __forceinline__ void mbar_arrive_remote_light(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(NCOLS) : "memory");

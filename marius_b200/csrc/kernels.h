@@ -42,7 +42,7 @@ mb_status launch_slot_keys(const int64_t* edges, int cols, int64_t B, const int6
 mb_status launch_rel_keys(const int64_t* edges, int cols, int64_t B, uint32_t* keys, cudaStream_t st);
 mb_status launch_segment_reduce(int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                                 const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                                const int64_t* ids, float lr, cudaStream_t st, const float* state_cache = nullptr);
+                                const int64_t* ids, float lr, cudaStream_t st);
 
 bool decoder_vec_ok(const float* emb, int64_t emb_ld, int d, bool has_rel, const float* rel, const float* inv_rel, int sides);
 mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float* const* row_ptrs, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
@@ -56,7 +56,7 @@ mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int6
                                    bool state_rows, cudaStream_t st);
 mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                             const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                            const int64_t* ids, float lr, cudaStream_t st, const float* state_cache = nullptr);
+                            const int64_t* ids, float lr, cudaStream_t st, const int64_t* owner_bounds = nullptr);
 
 mb_status launch_rel_reduce(const float* drel0, const float* drel1, float* out0, float* out1, const uint32_t* slots, const uint32_t* offsets, int64_t R,
                             int d, cudaStream_t st);
@@ -72,6 +72,14 @@ mb_status launch_split_mapped(const int64_t* mapped, const int64_t* edges, int64
 // eval_kernels.cu
 mb_status launch_score_filter(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, int* bad_flag, cudaStream_t st);
 mb_status launch_ranks(const float* pos, const float* neg, int64_t rows, int64_t N, int64_t ld, int64_t* ranks, cudaStream_t st);
+
+// shard_kernels.cu : exchange step of the sharded table (flag barriers, owner bounds, owner-side apply of received gradient rows)
+int64_t shard_exchange_bytes(int world, int64_t rows, int64_t d);
+mb_status launch_shard_barrier(const mb_shards* sh, cudaStream_t st);
+mb_status launch_owner_bounds(const mb_shards* sh, const int64_t* ids, int64_t n, int64_t d, int64_t* bounds, cudaStream_t st);
+void shard_inbox_ptrs(const mb_shards* sh, int64_t d, int64_t** ids_out, float** rows_out);
+mb_status launch_inbox_apply(const mb_shards* sh, int owner, int sender, int64_t ld, int d, float lr, int64_t max_rows, cudaStream_t st);
+mb_status shard_error_flag(const mb_shards* sh, int* out);
 
 // gemm_simt.cu
 mb_status gemm_simt(const float* A, int64_t sAm, int64_t sAk, int64_t sAb, const float* B, int64_t sBk, int64_t sBn, int64_t sBb, float* C, int64_t ldc,

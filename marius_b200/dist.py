@@ -180,7 +180,7 @@ class PeerShardedTable:
 
     One process per GPU; every process must see all GPUs of the box (torchrun's default)."""
 
-    def __init__(self, table: torch.Tensor, state: torch.Tensor, ctx, group=None):
+    def __init__(self, table: torch.Tensor, state: torch.Tensor, ctx, group=None, exchange_rows: int = 1 << 18):
         from . import ops
 
         self.ops, self.ctx, self.group = ops, ctx, group
@@ -190,21 +190,32 @@ class PeerShardedTable:
         self.d = table.size(1)
         self.ld = table.stride(0)
         self.table, self.state = table, state
-        tptr, sptr = [0] * self.world, [0] * self.world
+        tptr, sptr, eptr = [0] * self.world, [0] * self.world, [0] * self.world
         tptr[self.rank], sptr[self.rank] = table.data_ptr(), state.data_ptr()
+        self.exchange_rows = int(exchange_rows)
+        self.exchange = None
         if self.world > 1:
+            # this rank's exchange area: barrier flags + one inbox of gradient rows per sender (include/marius_b200.h: mb_shards)
+            self.exchange = torch.zeros(ops.shard_exchange_bytes(self.world, self.exchange_rows, self.d), dtype=torch.uint8, device=table.device)
+            eptr[self.rank] = self.exchange.data_ptr()
             handles = [None] * self.world
-            dist.all_gather_object(handles, (ops.ipc_export(table), ops.ipc_export(state), tuple(table.shape), table.stride(0)), group=group)
-            for r, (ht, hs, shape, ld) in enumerate(handles):
-                if shape != tuple(table.shape) or ld != self.ld:
-                    raise ValueError("all shards must have the same shape and stride")
+            dist.all_gather_object(handles, (ops.ipc_export(table), ops.ipc_export(state), ops.ipc_export(self.exchange), tuple(table.shape), table.stride(0),
+                                             self.exchange_rows), group=group)
+            for r, (ht, hs, he, shape, ld, er) in enumerate(handles):
+                if shape != tuple(table.shape) or ld != self.ld or er != self.exchange_rows:
+                    raise ValueError("all shards must have the same shape, stride and exchange capacity")
                 if r == self.rank:
                     continue
                 # opened with MY device current (mb_ipc_import): loads / stores from my kernels reach the peer's HBM over NVLink
                 tptr[r] = ops.ipc_import(ctx, *ht)
                 sptr[r] = ops.ipc_import(ctx, *hs)
+                eptr[r] = ops.ipc_import(ctx, *he)
             dist.barrier(group=group)
-        self.shards = ops.make_shards_raw(tptr, sptr, self.rows_per_rank, self.rank)
+        self.shards = ops.make_shards_raw(tptr, sptr, self.rows_per_rank, self.rank, eptr, self.exchange_rows if self.world > 1 else 0)
+
+    def error(self) -> int:
+        """non-zero once a cross-rank barrier of a sharded step timed out on this rank"""
+        return self.ops.shard_error(self.ctx, self.shards) if self.world > 1 else 0
 
     def train_step(self, kind, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr, reduction=1, precision=None, loss=None, rel_grad=None,
                    inv_rel_grad=None):

@@ -468,7 +468,15 @@ def ipc_import(ctx: Context, handle: bytes, offset: int) -> int:
     return int(out.value)
 
 
-def make_shards_raw(table_ptrs, state_ptrs, rows_per_rank: int, rank: int = 0):
+def shard_exchange_bytes(world: int, exchange_rows: int, d: int) -> int:
+    """bytes of one rank's exchange area (barrier flags + one inbox of `exchange_rows` gradient rows per sender)"""
+    n = int(lib.mb_shard_exchange_bytes(int(world), int(exchange_rows), int(d)))
+    if n < 0:
+        raise MariusB200Error(_INVALID, "bad exchange dimensions")
+    return n
+
+
+def make_shards_raw(table_ptrs, state_ptrs, rows_per_rank: int, rank: int = 0, exchange_ptrs=None, exchange_rows: int = 0, single_process: bool = False):
     sh = mb_shards()
     sh.rank = int(rank)
     for i, (t, s_) in enumerate(zip(table_ptrs, state_ptrs)):
@@ -476,14 +484,22 @@ def make_shards_raw(table_ptrs, state_ptrs, rows_per_rank: int, rank: int = 0):
         sh.states[i] = int(s_)
     sh.world = len(table_ptrs)
     sh.rows_per_rank = int(rows_per_rank)
+    if exchange_ptrs is not None:
+        for i, e in enumerate(exchange_ptrs):
+            sh.exchange[i] = int(e)
+    sh.exchange_rows = int(exchange_rows)
+    sh.single_process = int(bool(single_process))
     return sh
 
 
-def make_shards(tables, states, rows_per_rank: int, rank: int = 0):
-    """mb_shards from per-owner table / state tensors (this rank's own allocation + CUDA-IPC views of the peers')."""
+def make_shards(tables, states, rows_per_rank: int, rank: int = 0, exchange_rows: int = 1 << 14):
+    """mb_shards over per-owner table / state tensors that all live in THIS process (one GPU holding several shards: tests, or a
+    single-process driver): the exchange areas are allocated here and the call serves every owner (single_process).  The returned
+    structure keeps the exchange tensors alive through its `_keep` attribute."""
     if len(tables) != len(states) or not (1 <= len(tables) <= 8):
         raise MariusB200Error(_INVALID, "1..8 shards")
     sh = mb_shards()
+    keep = []
     for i, (t, s_) in enumerate(zip(tables, states)):
         _need_cuda(t, s_)
         if t.shape != tables[0].shape or s_.shape != t.shape or _rowmajor(t, "table") != _rowmajor(tables[0], "table"):
@@ -493,7 +509,23 @@ def make_shards(tables, states, rows_per_rank: int, rank: int = 0):
     sh.world = len(tables)
     sh.rows_per_rank = int(rows_per_rank)
     sh.rank = int(rank)
+    if sh.world > 1:
+        nbytes = shard_exchange_bytes(sh.world, exchange_rows, tables[0].size(1))
+        for i in range(sh.world):
+            ex = torch.zeros(nbytes, dtype=torch.uint8, device=tables[0].device)
+            keep.append(ex)
+            sh.exchange[i] = ex.data_ptr()
+        sh.exchange_rows = int(exchange_rows)
+    sh.single_process = 1
+    sh._keep = keep
     return sh
+
+
+def shard_error(ctx: Context, shards) -> int:
+    """non-zero once a cross-rank barrier of the sharded step timed out (sticky)"""
+    e = C.c_int(0)
+    check(lib.mb_shard_error(ctx.handle, C.byref(shards), C.byref(e)))
+    return int(e.value)
 
 
 def train_step_sharded(ctx: Context, kind: int, shards, ld: int, d: int, unique_ids, edges, rel, inv_rel, dst_negs, src_negs, lr: float,
