@@ -501,12 +501,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                             for (int j = 0; j < kPieces; j++) z[j] = col_ok ? zfix[j] : INFINITY;
                         } else {
                             // issued before the wait for the raw tile; a batch's shifts (4 KB) stay in L1
-                            const float* zk = zb + k0 + kr0;
+                            const float* zk = zb + k0 + kr0;  // (nothing consumes these loads before the raw tile has been read)
 #pragma unroll
-                            for (int j = 0; j < kPieces; j++) {
-                                const float zl = (k_interior || k0 + kr0 + 4 * j < rows_lim) ? __ldg(zk + 4 * j) : INFINITY;
-                                z[j] = fmaxf(zl, zfix[j]);
-                            }
+                            for (int j = 0; j < kPieces; j++) z[j] = (k_interior || k0 + kr0 + 4 * j < rows_lim) ? __ldg(zk + 4 * j) : INFINITY;
                         }
                     }
                     mbar_wait(raw_bar(slot), raw_phase);
@@ -518,6 +515,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                     mbar_wait(empty_bar(stage), phase ^ 1u);  // the tensor core is done with the operand stage's previous contents
                     const uint32_t sA = smem_base + stage * G::STAGE;
                     if (expo) {
+                        if (a_mn) {
+#pragma unroll
+                            for (int j = 0; j < kPieces; j++) z[j] = fmaxf(z[j], zfix[j]);
+                        }
 #pragma unroll
                         for (int j = 0; j < kPieces; j++) {
                             v[j].x = ex2_approx(fmaf(v[j].x, kLog2e, -z[j]));
