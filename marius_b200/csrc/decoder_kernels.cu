@@ -10,11 +10,15 @@
 // One warp per row everywhere: d=400 -> 100 float4 per row, 3.1 per lane; shuffles for the dots.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 #include "decoder_vec.cuh"
 #include "kernels.h"
+#include "row_bulk.cuh"
 
 namespace mb {
 
@@ -555,6 +559,18 @@ static vec::ShardPtrs make_sp(const mb_shards* sh) {
     return sp;
 }
 
+// opt a bulk-staged kernel in to its dynamic shared memory, once per (kernel, device)
+static mb_status bulk_attr(const void* fn, size_t smem, int slot) {
+    static std::atomic<size_t> done[8][64];
+    int dev = 0;
+    MB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || done[slot][dev].load(std::memory_order_acquire) < smem) {
+        MB_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) done[slot][dev].store(smem, std::memory_order_release);
+    }
+    return MB_OK;
+}
+
 mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float* const* row_ptrs, const float* emb, int64_t emb_ld, const int64_t* row_map, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int64_t Bp,
                       int64_t CN, int d, int decoder, int sides, const int64_t* dst_negs, const int64_t* src_negs, float* A /*[sides][Bp][d] or null*/,
                       float* pos /*[sides][Bp]*/, void* A_hi, void* A_lo /*[sides][Bp][d] or null*/, float* Neg /*[sides][CN][d] or null*/,
@@ -592,7 +608,24 @@ mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float
             a.Neg_lo[s] = (on && Neg_lo) ? (__nv_bfloat16*)Neg_lo + s * CN * d : nullptr;
         }
         // negative rows first (two in flight per warp): with a sharded table they run while the remote rows are still being fetched
-        if (CN > 0) {
+        // MB_ROW_BULK: bit 0 = negative rows through the bulk-copy staged kernel (default), bit 1 = edge rows too (measured slower: its
+        // four consumer warps per block are latency-bound), bit 2 = eight consumer warps in the negative-row kernel
+        static const int bulk_mode = [] { const char* e = getenv("MB_ROW_BULK"); return e ? atoi(e) : 1; }();
+        const bool use_bulk = (bulk_mode & 2) != 0;
+        if (CN > 0 && (bulk_mode & 1)) {
+            // bulk-copy staged version (row_bulk.cuh): one cp.async.bulk per row into a shared-memory ring, two blocks per SM
+            const size_t smem = bulk::smem_bytes(bulk::kNegRows, d);
+            const int64_t chunks = ((int64_t)sides * CN + bulk::kNegRows - 1) / bulk::kNegRows;
+            const int grid = (int)std::min<int64_t>(chunks, (int64_t)sm_count() * 2);
+            if (bulk_mode & 4) {
+                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::neg_rows_bulk_kernel<8>), smem, 4));
+                bulk::neg_rows_bulk_kernel<8><<<grid, 32 * 9, smem, st>>>(a);
+            } else {
+                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::neg_rows_bulk_kernel<4>), smem, 0));
+                bulk::neg_rows_bulk_kernel<4><<<grid, 32 * 5, smem, st>>>(a);
+            }
+            MB_LAUNCH_CHECK();
+        } else if (CN > 0) {
             const int grid = warp_grid((sides * CN + 1) / 2);
             if (d <= 128)
                 vec::neg_rows_kernel<1><<<grid, vec::kThreads, 0, st>>>(a);
@@ -601,7 +634,22 @@ mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float
             MB_LAUNCH_CHECK();
         }
         if (rows_fetched != nullptr) MB_CUDA_TRY(cudaStreamWaitEvent(st, rows_fetched, 0));
-        if (Bp > 0) {
+        if (Bp > 0 && use_bulk) {
+            const size_t smem = bulk::smem_bytes(bulk::kEdgeRows, d);
+            const int64_t chunks = (Bp + bulk::kEdgesPerStage - 1) / bulk::kEdgesPerStage;
+            const int grid = (int)std::min<int64_t>(chunks, (int64_t)sm_count() * 2);
+            if (dec == MB_DECODER_COMPLEX) {
+                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::edge_rows_bulk_kernel<MB_DECODER_COMPLEX>), smem, 1));
+                bulk::edge_rows_bulk_kernel<MB_DECODER_COMPLEX><<<grid, bulk::kThreads, smem, st>>>(a);
+            } else if (dec == MB_DECODER_DISTMULT) {
+                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::edge_rows_bulk_kernel<MB_DECODER_DISTMULT>), smem, 2));
+                bulk::edge_rows_bulk_kernel<MB_DECODER_DISTMULT><<<grid, bulk::kThreads, smem, st>>>(a);
+            } else {
+                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::edge_rows_bulk_kernel<MB_DECODER_DOT>), smem, 3));
+                bulk::edge_rows_bulk_kernel<MB_DECODER_DOT><<<grid, bulk::kThreads, smem, st>>>(a);
+            }
+            MB_LAUNCH_CHECK();
+        } else if (Bp > 0) {
             const int grid = warp_grid(Bp);
             const bool small = d <= 128;  // chunks per lane: full row <= 1 (d <= 128) / 4 (d <= 512); complex half <= 1 (d <= 256) / 2
             if (dec == MB_DECODER_COMPLEX) {

@@ -52,8 +52,9 @@ struct GMaps {
     CUtensorMap m[2][5];  // per problem: A_hi, A_lo, B_hi, B_lo, D
 };
 
-constexpr int kConvWarps = 8;
-constexpr int kConvThreads = kTcThreads + 32 * kConvWarps;  // 448: producer, MMA, 4 epilogue warps, 8 converter warps (2 per SM sub-partition)
+constexpr int kConvGroups = 3;                 // converter groups, each takes every kConvGroups-th k-block
+constexpr int kConvWarps = 4 * kConvGroups;    // one warp of every group per SM sub-partition
+constexpr int kConvThreads = kTcThreads + 32 * kConvWarps;  // 576: producer, MMA, 4 epilogue warps, 12 converter warps
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -90,7 +91,7 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads) { asm vo
 //   CONV = true  (backward contractions): the A operand of every problem is produced in the kernel from an fp32 matrix (the scores S):
 //                G = exp(S - z_row) (the SoftmaxCrossEntropy gradient, loss.cpp:50-67) or G = S.  k-blocks of 32: 4 operand stages of
 //                32 KB + a ring of 4 raw fp32 score tiles of 16 KB, so that the score tiles are in flight (TMA) several k-blocks ahead
-//                of their conversion, independently of the operand stages; 448 threads (8 converter warps).  The gradient matrix never
+//                of their conversion, independently of the operand stages; 576 threads (12 converter warps).  The gradient matrix never
 //                exists in global memory.
 template <bool CONV>
 struct Geo {
@@ -395,9 +396,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
         if (elect_one()) bulk_wait_all();
     } else {
         // ================= converter warps 6..13 (both CTAs, CONV only): fp32 scores -> G -> bf16 hi/lo operand tiles =================
-        // Two groups of four warps work on ALTERNATE k-blocks (group g takes the k-blocks whose running number is g mod 2), so the serial
-        // chain of one k-block (wait for the raw tile, load, synchronise, convert, fence, synchronise, arrive) may take two k-block periods
-        // of the tensor core: the groups pipeline against each other instead of splitting every k-block eight ways.
+        // kConvGroups groups of four warps work on INTERLEAVED k-blocks (group g takes the k-blocks whose running number is g mod
+        // kConvGroups), so the serial chain of one k-block (wait for the raw tile, load, synchronise, convert, fence, synchronise, arrive)
+        // may take kConvGroups k-block periods of the tensor core: the groups pipeline against each other instead of splitting every
+        // k-block twelve ways.  Measured (B = 50 000, both backward contractions): 2 groups 545 us, 3 groups 475 us, 4 groups (80
+        // registers per thread at 704 threads: spills) 516 us; the contraction alone, operands from global bf16 arrays, 369 us.
         // Raw ring: this CTA's fp32 score tile of k-block n (128 operand rows x 32 K, 16 KB, row-major, no swizzle) is loaded by TMA into
         // slot n % 4, RAW_SLOTS k-blocks ahead of its conversion; thread 0 of the group issues the load of k-block n + RAW_SLOTS as soon as
         // every thread of the group has read slot n % 4 (the load cursor walks the same tile table, across tile boundaries).
@@ -407,8 +410,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
         // hi tile then lo tile.  Thread mapping: consecutive threads take consecutive float4 of a raw row (conflict-free 128-bit loads);
         // their 8-byte stores cover whole operand rows (all 32 banks).
         constexpr int RS = G::RAW_SLOTS > 0 ? G::RAW_SLOTS : 2;
-        static_assert(RS % 2 == 0, "the two converter groups own alternate raw slots");
-        constexpr int kGroupThreads = 16 * kConvWarps;                       // 128
+        constexpr int kGroupThreads = 128;
         constexpr int kPieces = (BLOCK_M * BK / 4) / kGroupThreads;           // float4 pieces per thread per k-block (8)
         const int ct = (int)threadIdx.x - kTcThreads;
         const int grp = ct / kGroupThreads, gt = ct % kGroupThreads;
@@ -441,8 +443,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
         };
         if (gt == 0) {
             load_advance();
-            for (int s = 0; s < G::RAW_SLOTS; s++) {
-                if ((s & 1) == grp) load_issue(s);
+            for (int s = 0; s < G::RAW_SLOTS; s++) {  // k-block s goes to slot s; its load is issued by the group that will convert it
+                if (s % kConvGroups == grp) load_issue(s);
                 load_advance();
             }
         }
@@ -490,7 +492,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
             const int kcol = 4 * (gt & 7);  // K-major: first K column of this thread's pieces within the k-block
 #pragma unroll 1
             for (int kb = 0; kb < num_k_blocks; kb++, n++) {
-                if ((n & 1) == grp) {
+                if (n % kConvGroups == grp) {
                     const int k0 = kb * BK;
                     const bool k_interior = k0 + BK <= lim_k;  // (warp-uniform)
                     float z[kPieces];
