@@ -52,6 +52,7 @@ def test_sass_has_tcgen05_tma_and_system_reductions():
     assert re.search(r"UTC[A-Z]*MMA", sass), "no tcgen05.mma (UTC*MMA) in the SASS"
     assert "UTCHMMA.2CTA" in sass, "the grouped contraction is a cta_group::2 kernel"
     assert "UTMALDG" in sass and "UTMASTG" in sass, "no TMA tensor loads / stores in the SASS"
-    assert re.search(r"ST\.E\.64\.STRONG\.SYS|ST\.E\.64[.A-Z]*\.SYS", sass) and re.search(r"LD\.E\.64\.STRONG\.SYS|LD\.E\.64[.A-Z]*\.SYS", sass), \
+    assert re.search(r"STG\.E\.64\.STRONG\.SYS", sass) and re.search(r"LDG\.E\.64\.STRONG\.SYS", sass), \
         "the cross-rank barrier publishes / polls its epoch counters with system-scope release / acquire accesses"
+    assert "UBLKCP" in sass, "the negative-row kernel stages table rows with bulk asynchronous copies (cp.async.bulk)"
     assert "WGMMA" not in sass and "HMMA.16" not in sass  # neither Hopper wgmma nor legacy mma.sync anywhere
