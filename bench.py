@@ -248,6 +248,97 @@ def run_reference_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------------ the other shapes SURVEY.md 8d names
+def make_batches_shape(rng, num_nodes, n_batches, B, C, N, R):
+    out = []
+    for _ in range(n_batches):
+        src = rng.integers(0, num_nodes, size=B, dtype=np.int64)
+        dst = rng.integers(0, num_nodes, size=B, dtype=np.int64)
+        relid = rng.integers(0, R, size=B, dtype=np.int64)
+        sn = rng.integers(0, num_nodes, size=(C, N), dtype=np.int64)
+        dn = rng.integers(0, num_nodes, size=(C, N), dtype=np.int64)
+        out.append(synthetic_batch(rng, src, dst, relid, sn, dn))
+    return out
+
+
+def cpu_reference_shape(kind, d, R, batches, num_nodes, seed=3):
+    """The reference's CPU hot loop on the given batches (bounded sample); edges/s, or None when oracle/_ref is not built."""
+    from oracle import marius_oracle as O
+    from oracle import ref_lib as Rf
+
+    if not Rf.available():
+        return None
+    Rf.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(seed)
+    table = rng.uniform(-0.1, 0.1, (num_nodes, d)).astype(np.float32)
+    state = np.zeros((num_nodes, d), np.float32)
+    uniq = np.concatenate([b[0] for b in batches])
+    off = np.zeros(len(batches) + 1, np.int64)
+    off[1:] = np.cumsum([len(b[0]) for b in batches])
+    edges = np.ascontiguousarray(np.stack([b[1] for b in batches]))
+    dn = np.ascontiguousarray(np.stack([b[2] for b in batches]))
+    sn = np.ascontiguousarray(np.stack([b[3] for b in batches]))
+    okind = {"distmult": O.DISTMULT, "complex": O.COMPLEX}[kind]
+    secs = Rf.train_loop(okind, d, R, table, state, uniq, off, edges, dn, sn, LR, O.REDUCTION_SUM, warmup_batches=1)
+    B = edges.shape[1]
+    return dict(value=len(batches) * B / secs, unit=UNIT, cores=Rf.num_threads(), kind="reference", sample=f"{len(batches)} batches x {B} edges, host table {num_nodes} rows")
+
+
+EXTRA_SHAPES = [
+    # name, decoder, nodes (None = the bench table), R, d, B, C, N, cpu batches
+    ("FB15k-237 sizes: DistMult d=100, 100 negatives, batch 1000 (BASELINE configs[0])", "distmult", 14541, 237, 100, 1000, 1, 100, 20),
+    ("DistMult d=400, 1000 negatives, batch 50000", "distmult", None, NUM_REL, D, 50000, 50, NEG, 2),
+    ("ComplEx d=400, 1000 negatives, batch 1000 (Marius default batch)", "complex", None, NUM_REL, D, 1000, 1, NEG, 20),
+    ("ComplEx d=400, 1000 negatives, batch 10000", "complex", None, NUM_REL, D, 10000, 10, NEG, 6),
+]
+
+
+def run_extra_shapes(ops, ctx, dev, prec, table, state, steps, cpu_nodes, with_cpu):
+    """Device-timed edges/s of the fused step at the other shapes (indices resident in HBM, fresh random rows of a table >> L2 every
+    step -- the FB15k-237-sized table fits L2, as it does in the reference), each with its own bounded CPU-reference number."""
+    import torch
+
+    out = []
+    for name, kind, nodes, R, d, B, C, N, cpu_batches in EXTRA_SHAPES:
+        rng = np.random.default_rng(77)
+        if nodes is None:
+            t, st, n_nodes = table, state, table.size(0)
+        else:
+            n_nodes = nodes
+            t = torch.empty((n_nodes, d), dtype=torch.float32, device=dev).uniform_(-0.1, 0.1)
+            st = torch.zeros((n_nodes, d), dtype=torch.float32, device=dev)
+        okind = {"distmult": ops.DISTMULT, "complex": ops.COMPLEX}[kind]
+        rel = torch.ones((R, d), device=dev)
+        if kind == "complex":
+            rel[:, d // 2:] = 0
+        inv_rel = rel.clone()
+        rg, irg = torch.empty_like(rel), torch.empty_like(rel)
+        loss = torch.zeros(1, device=dev)
+        W = 3
+        batches = make_batches_shape(rng, n_nodes, W + steps, B, C, N, R)
+        res = [tuple(torch.from_numpy(x).to(dev) for x in b) for b in batches]
+        for i in range(W):
+            ops.train_step(ctx, okind, t, st, *res[i][:2], rel, inv_rel, res[i][2], res[i][3], LR, ops.REDUCTION_SUM, prec, loss=loss, rel_grad=rg, inv_rel_grad=irg)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(W, W + steps):
+            ops.train_step(ctx, okind, t, st, *res[i][:2], rel, inv_rel, res[i][2], res[i][3], LR, ops.REDUCTION_SUM, prec, loss=loss, rel_grad=rg, inv_rel_grad=irg)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        entry = dict(workload=name, value=B / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps, unique_rows_per_step=float(np.mean([len(b[0]) for b in batches])))
+        if with_cpu:
+            try:
+                cb = make_batches_shape(np.random.default_rng(78), min(cpu_nodes, n_nodes), cpu_batches, B, C, N, R)
+                entry["cpu_baseline"] = cpu_reference_shape(kind, d, R, cb, min(cpu_nodes, n_nodes))
+            except Exception as ex:
+                entry["cpu_baseline"] = dict(value=None, kind="unavailable", sample=str(ex)[:200])
+        out.append(entry)
+        del res
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------ parity (checker, never timed)
 PARITY_TOL = 1e-4
 
@@ -628,11 +719,48 @@ def run_ours(args):
     e2e_value = world * K * B / float(e2e_s.item())
     h2d = int(np.mean([sum(t.numel() * 8 for t in b) for b in pinned]))
 
+    # ---- e2e from RAW edges (N = 1): the host hands over only the positive edges with global ids (24 B / edge); negatives are sampled and
+    # the unique-id mapping is built on the device inside the call.  Reported next to `e2e` (whose inputs are the
+    # pre-mapped index tensors the reference's Batch::to moves), with the sampling + mapping time on its own.
+    e2e_raw = None
+    if world == 1:
+        raw_edges = []
+        for _ in range(min(K, 20) + 2):
+            raw_edges.append(torch.from_numpy(np.stack([rng.integers(0, rows, B), rng.integers(0, NUM_REL, B), rng.integers(0, rows, B)], axis=1).astype(np.int64)).pin_memory())
+        def raw_step(i):
+            return ops.train_step_edges_host_async(ctx, ops.COMPLEX, table, state, raw_edges[i], rows, C, NEG, 1234, i, rel, inv_rel, LR, ops.REDUCTION_SUM, prec,
+                                                   rel_grad=rg, inv_rel_grad=irg)
+        for i in range(2):
+            ops.train_step_host_wait(ctx, raw_step(i)[0])
+            dense_step()
+        barrier()
+        t0 = time.perf_counter()
+        prev = None
+        for i in range(2, len(raw_edges)):
+            cur = raw_step(i)
+            dense_step()
+            if prev is not None:
+                ops.train_step_host_wait(ctx, prev[0])
+            prev = cur
+        ops.train_step_host_wait(ctx, prev[0])
+        barrier()
+        raw_s = time.perf_counter() - t0
+        e2e_raw = dict(value=(len(raw_edges) - 2) * B / raw_s, unit=UNIT, h2d_bytes_per_step=int(raw_edges[0].numel() * 8), d2h_bytes_per_step=4,
+                       steps=len(raw_edges) - 2, note="positive edges only over PCIe; negative sampling (Philox) + unique-id mapping (radix sort) on the device inside the call")
+
     # ---- roofline: per-stage CUDA-event timing of the same steps (separate pass: events add launch gaps)
     ctx.profile(True)
     for i in range(W, W + K):
         step_resident(i)
     stages = ctx.profile_read()
+    sample_ms = None
+    if e2e_raw is not None:  # sampling + unique mapping, timed separately
+        for i in range(2, 6):
+            ops.train_step_host_wait(ctx, raw_step(i)[0])
+        st2 = ctx.profile_read()
+        if st2.get("negative_sampling+unique_mapping", (0, 0))[1] > 0:
+            sample_ms = st2["negative_sampling+unique_mapping"][0] / st2["negative_sampling+unique_mapping"][1]
+            e2e_raw["sampling_mapping_ms_per_step"] = sample_ms
     ctx.profile(False)
     pk = peaks()
     # per-STEP stage times (a stage may be several launches: the two corruption sides are pipelined on two streams)
@@ -683,6 +811,14 @@ def run_ours(args):
         except Exception as ex:  # the baseline is reported, never required
             cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="unavailable", sample=str(ex)[:200])
 
+    # ---- the other shapes (N = 1): device-timed value + bounded CPU-reference number each
+    extra = None
+    if world == 1 and not args.no_extra_shapes:
+        try:
+            extra = run_extra_shapes(ops, ctx, dev, prec, table, state, min(K, 20), args.ref_nodes, not args.no_cpu_baseline)
+        except Exception as ex:
+            extra = [dict(workload="extra shapes failed", error=f"{type(ex).__name__}: {ex}"[:300])]
+
     # ---- parity (outside every timed region): the measured path against the reference's CPU path, at the bench shape (N = 1) or through the
     # sharded protocol inside this process group (N > 1)
     parity = None
@@ -718,7 +854,7 @@ def run_ours(args):
                                    if world > 1 and peer is not None else {}),
                                 stage_ms={k: round(v, 4) for k, v in per_stage.items()}, stage_sum_ms=step_stage_ms, last_loss=last_loss),
                     clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4), gpu_launches=int(launches),
-                    roofline=roof, cpu_baseline=cpu, parity=parity, impl="marius_b200")
+                    roofline=roof, cpu_baseline=cpu, parity=parity, e2e_raw_edges=e2e_raw, configs=extra, impl="marius_b200")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -741,6 +877,7 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=24, help="--impl reference: upper bound on the timed CPU batches")
     ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-shapes", action="store_true", help="skip the other shapes (FB15k-237 sizes, DistMult d=400, batch 1000 / 10000)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (one bench-shape batch against the reference's CPU path, untimed)")
     ap.add_argument("--parity-disjoint", action="store_true", help="N > 1 parity: give every rank disjoint rows (no row updated by two ranks)")
     ap.add_argument("--gpu-sync-interval", type=int, default=16,

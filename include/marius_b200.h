@@ -265,6 +265,16 @@ mb_status mb_train_step_sharded_host_async(mb_context* ctx, const mb_batch* host
                                            const int64_t* unique_ids_host, float lr, int reduction, int precision, float* rel_grad,
                                            float* inv_rel_grad, int* ticket, void* stream);
 mb_status mb_train_step_host_wait(mb_context* ctx, int ticket, float* loss_host);
+/* The step from RAW positive edges (DataLoader::getBatch -> edgeSample -> loadGPUParameters -> train_batch -> updateEmbeddings,
+ * dataloader.cpp:389-564 with the table device-resident): `edges_host` [B,3] int64 (src, rel, dst) with GLOBAL node ids, pinned or
+ * pageable.  Negatives are sampled on the device (mb_sample_negatives, uniform, keyed by (seed, batch_index)), the unique-id mapping
+ * is mb_edge_sample, then the fused step.  Asynchronous like mb_train_step_host_async (ticket / mb_train_step_host_wait); at most one
+ * raw-edge step should be in flight per context (the staging block is single-buffered behind stream order).  inv_rel == NULL: no
+ * inverse side. */
+mb_status mb_train_step_edges_host_async(mb_context* ctx, int decoder, const int64_t* edges_host, int64_t B, int64_t num_nodes, int C, int N,
+                                         uint64_t seed, uint32_t batch_index, const float* rel, const float* inv_rel, int64_t R, int64_t d,
+                                         float* table, float* state_table, int64_t num_rows, int64_t ld, float lr, int reduction, int precision,
+                                         float* rel_grad, float* inv_rel_grad, int* ticket, void* stream);
 
 
 /* AdagradOptimizer::step on a dense parameter (nn/optim.cpp:114-145): state += g*g ; p -= lr * g / (sqrt(state) + eps) */

@@ -59,6 +59,8 @@ _SIGS = {
     "mb_train_step_host_async": [_vp, C.POINTER(mb_batch), _vp, _vp, _i64, _i64, _vp, _f, _i32, _i32, _vp, _vp, C.POINTER(C.c_int), _vp],
     "mb_train_step_sharded_host_async": [_vp, C.POINTER(mb_batch), C.POINTER(mb_shards), _i64, _vp, _f, _i32, _i32, _vp, _vp, C.POINTER(C.c_int), _vp],
     "mb_train_step_host_wait": [_vp, _i32, C.POINTER(C.c_float)],
+    "mb_train_step_edges_host_async": [_vp, _i32, _vp, _i64, _i64, _i32, _i32, C.c_uint64, C.c_uint32, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _i64, _f, _i32, _i32,
+                                       _vp, _vp, C.POINTER(C.c_int), _vp],
     "mb_dense_adagrad_step": [_vp, _vp, _vp, _i64, _f, _f, _vp],
     "mb_profile_enable": [_vp, _i32],
     "mb_graph_enable": [_vp, _i32],

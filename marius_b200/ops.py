@@ -435,6 +435,22 @@ def train_step_host_async(ctx: Context, kind: int, table, state_table, unique_id
     return int(ticket.value), (keep, uid)
 
 
+def train_step_edges_host_async(ctx: Context, kind: int, table, state_table, edges_h, num_nodes: int, C_: int, N: int, seed: int, batch_index: int, rel, inv_rel,
+                                lr: float, reduction: int = REDUCTION_SUM, precision: int = PREC_BF16X3, rel_grad=None, inv_rel_grad=None):
+    """The step from RAW positive edges ([B,3] int64 host tensor, global node ids): negatives and the unique-id mapping are produced on
+    the device.  Returns (ticket, keep-alive); train_step_host_wait(ctx, ticket) returns the loss."""
+    _need_cuda(table, state_table, rel, inv_rel)
+    if edges_h.is_cuda or edges_h.dim() != 2 or edges_h.size(1) != 3 or edges_h.dtype != torch.int64:
+        raise MariusB200Error(_INVALID, "edges must be a host int64 [B, 3] tensor")
+    e = edges_h.contiguous()
+    ticket = C.c_int(0)
+    check(lib.mb_train_step_edges_host_async(ctx.handle, int(kind), C.c_void_p(e.data_ptr()), e.size(0), int(num_nodes), int(C_), int(N), int(seed),
+                                             int(batch_index), _ptr(rel), _ptr(inv_rel), rel.size(0), table.size(1), _ptr(table), _ptr(state_table),
+                                             table.size(0), _rowmajor(table, "table"), float(lr), int(reduction), int(precision), _ptr(rel_grad),
+                                             _ptr(inv_rel_grad), C.byref(ticket), _stream()))
+    return int(ticket.value), (e,)
+
+
 def train_step_host_wait(ctx: Context, ticket: int) -> float:
     loss = C.c_float(0.0)
     check(lib.mb_train_step_host_wait(ctx.handle, int(ticket), C.byref(loss)))

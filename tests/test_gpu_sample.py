@@ -101,3 +101,33 @@ def test_sample_map_train_equals_oracle(ops, ctx):
     err = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
     assert err(tab.cpu().numpy(), ref_tab) < 1e-4 and err(st.cpu().numpy(), ref_st) < 1e-4
     assert abs(float(loss.item()) - float(res.loss)) < 1e-4 * abs(float(res.loss))
+
+
+def test_step_from_raw_edges_equals_the_assembled_step(ops):
+    """mb_train_step_edges_host_async (raw global edges from the host; negatives + unique mapping on the device) leaves exactly the
+    tables / losses of: sampler (oracle, bit-exact with the device sampler) -> map_tensors (oracle) -> mb_train_step."""
+    rng = np.random.default_rng(5)
+    num_nodes, R, B, C, N, d = 20000, 6, 1024, 2, 512, 64
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    rel, inv_rel = dev(rng.uniform(-1, 1, (R, d)).astype(np.float32)), dev(rng.uniform(-1, 1, (R, d)).astype(np.float32))
+    t1, s1 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    t2, s2 = dev(table), torch.zeros(num_nodes, d, device="cuda")
+    ctx_a, ctx_b = ops.Context(0), ops.Context(0)
+    seed = 99
+    losses_a, losses_b = [], []
+    for step in range(4):
+        edges = np.stack([rng.integers(0, num_nodes, B), rng.integers(0, R, B), rng.integers(0, num_nodes, B)], axis=1).astype(np.int64)
+        e_h = torch.from_numpy(edges).pin_memory()
+        ticket, keep = ops.train_step_edges_host_async(ctx_a, ops.COMPLEX, t1, s1, e_h, num_nodes, C, N, seed, step, rel, inv_rel, 0.1)
+        losses_a.append(ops.train_step_host_wait(ctx_a, ticket))
+        dn = O.sample_negatives(num_nodes, C, N, seed, step, False)
+        sn = O.sample_negatives(num_nodes, C, N, seed, step, True)
+        uniq, inv = O.map_tensors(np.concatenate([edges[:, 0], edges[:, 2], sn.reshape(-1), dn.reshape(-1)]))
+        e_loc = np.ascontiguousarray(np.stack([inv[:B], edges[:, 1], inv[B:2 * B]], axis=1))
+        sn_loc = np.ascontiguousarray(inv[2 * B:2 * B + C * N].reshape(C, N))
+        dn_loc = np.ascontiguousarray(inv[2 * B + C * N:].reshape(C, N))
+        loss = ops.train_step(ctx_b, ops.COMPLEX, t2, s2, dev(uniq), dev(e_loc), rel, inv_rel, dev(dn_loc), dev(sn_loc), 0.1)
+        losses_b.append(float(loss.item()))
+    torch.cuda.synchronize()
+    assert losses_a == losses_b
+    assert torch.equal(t1, t2) and torch.equal(s1, s2)
