@@ -339,6 +339,102 @@ def run_extra_shapes(ops, ctx, dev, prec, table, state, steps, cpu_nodes, with_c
     return out
 
 
+# ------------------------------------------------------------------------------------------------------ buffered table (BASELINE configs[2] shape)
+def run_buffered(ops, dev, prec, num_partitions=16, capacity=8, partition_rows=250_000, edges_per_bucket=200_000, B=50_000, seed=5, modes=(True, False)):
+    """One epoch over a table that does NOT fit the buffer: `num_partitions` partitions in a backing file, `capacity` of them resident in
+    an HBM slab (marius_b200.host.PartitionBuffer, embeddings + Adagrad state), BETA ordering (marius_b200.ordering), DistMult d=400,
+    1000 negatives drawn from the resident partitions, `edges_per_bucket` synthetic edges per edge bucket in batches of B through the
+    raw-edge step.  edges/s over the whole epoch INCLUDING every swap; with the asynchronous swap engine (LookaheadBlock /
+    AsyncWriteBlock) and with synchronous swaps."""
+    import shutil
+    import tempfile
+
+    import torch
+
+    from marius_b200 import host, ordering
+
+    d, C, N, R = D, max(B // CHUNK, 1), NEG, NUM_REL
+    total = num_partitions * partition_rows
+    need = 2 * total * d * 4
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need + (8 << 30) else tempfile.gettempdir()
+    if shutil.disk_usage(base).free < need + (2 << 30):
+        return dict(skipped=f"not enough space under {base} for {need / 1e9:.1f} GB of partition files")
+    tmp = tempfile.mkdtemp(prefix="mb_buffered_", dir=base)
+    out = dict(workload=f"BASELINE configs[2] shape, scaled: DistMult d={d}, {N} negatives, {num_partitions} partitions x {partition_rows} rows "
+                        f"({total * d * 4 / 1e9:.1f} GB embeddings + as much Adagrad state in backing files under {base}), buffer capacity {capacity} "
+                        f"partitions in HBM, BETA ordering, {edges_per_bucket} edges per edge bucket in batches of {B}", unit=UNIT)
+    try:
+        rng = np.random.default_rng(seed)
+        block = rng.uniform(-0.1, 0.1, (partition_rows, d)).astype(np.float32)
+        zeros = np.zeros((partition_rows, d), np.float32)
+        f_emb, f_state = os.path.join(tmp, "embeddings.bin"), os.path.join(tmp, "embeddings_state.bin")
+        with open(f_emb, "wb") as fe, open(f_state, "wb") as fs:
+            for _ in range(num_partitions):
+                fe.write(block.tobytes())
+                fs.write(zeros.tobytes())
+        del block, zeros
+        states, buckets = ordering.beta_ordering(num_partitions, capacity, seed)
+        out["buffer_states"] = len(states)
+        out["swaps"] = len(states) - 1
+        n_batches = max(1, edges_per_bucket // B)
+        edges_total = sum(len(b) for b in buckets) * n_batches * B
+        rel = torch.ones((R, d), device=dev)
+        inv_rel = rel.clone()
+        rels = torch.stack([rel, inv_rel])
+        rel_states, rel_grads = torch.zeros_like(rels), torch.empty_like(rels)
+        for prefetching in modes:
+            ctx = ops.Context(dev.index)
+            emb = host.storage.PartitionBuffer(capacity, num_partitions, 1, partition_rows, d, total, f_emb, prefetching, dev)
+            st = host.storage.PartitionBuffer(capacity, num_partitions, 1, partition_rows, d, total, f_state, prefetching, dev)
+            order = [torch.tensor(s_) for s_ in states]
+            emb.setBufferOrdering(order)
+            st.setBufferOrdering(order)
+            emb.load()
+            st.load()
+            torch.cuda.synchronize()
+            brng = np.random.default_rng(seed + 1)
+            bi = 0
+            prev = None
+            swap_s = 0.0
+            t0 = time.perf_counter()
+            for si, bks in enumerate(buckets):
+                m = emb.getGlobalToLocalMap(True)
+                slot_of = {p_: int(m[p_ * partition_rows].item()) // partition_rows for p_ in states[si]}
+                table, state = emb.bufferTensor(), st.bufferTensor()
+                for (ps, pd) in bks:
+                    for _ in range(n_batches):
+                        e = np.empty((B, 3), np.int64)
+                        e[:, 0] = slot_of[ps] * partition_rows + brng.integers(0, partition_rows, B)
+                        e[:, 1] = brng.integers(0, R, B)
+                        e[:, 2] = slot_of[pd] * partition_rows + brng.integers(0, partition_rows, B)
+                        cur = ops.train_step_edges_host_async(ctx, ops.DISTMULT, table, state, torch.from_numpy(e), capacity * partition_rows, C, N, 99, bi, rels[0],
+                                                              rels[1], LR, ops.REDUCTION_SUM, prec, rel_grad=rel_grads[0], inv_rel_grad=rel_grads[1])
+                        ops.dense_adagrad_step(rels, rel_states, rel_grads, LR)
+                        if prev is not None:
+                            ops.train_step_host_wait(ctx, prev[0])
+                        prev = cur
+                        bi += 1
+                if emb.hasSwap():
+                    ts = time.perf_counter()
+                    emb.performNextSwap()
+                    st.performNextSwap()
+                    swap_s += time.perf_counter() - ts
+            if prev is not None:
+                ops.train_step_host_wait(ctx, prev[0])
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - t0
+            emb.unload(True)
+            st.unload(True)
+            key = "async_swaps" if prefetching else "sync_swaps"
+            out[key] = dict(value=edges_total / secs, seconds=secs, host_seconds_blocked_in_swaps=swap_s, edges=edges_total, batches=bi)
+            del emb, st, ctx
+        if "async_swaps" in out:
+            out["value"] = out["async_swaps"]["value"]
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------------------------------ parity (checker, never timed)
 PARITY_TOL = 1e-4
 
@@ -819,6 +915,14 @@ def run_ours(args):
         except Exception as ex:
             extra = [dict(workload="extra shapes failed", error=f"{type(ex).__name__}: {ex}"[:300])]
 
+    # ---- buffered table: one BETA epoch over a partitioned table larger than its HBM buffer (swap engine included in the time)
+    buffered = None
+    if world == 1 and not args.no_buffered:
+        try:
+            buffered = run_buffered(ops, dev, prec, partition_rows=args.buffered_partition_rows, edges_per_bucket=args.buffered_edges_per_bucket, B=B)
+        except Exception as ex:
+            buffered = dict(error=f"{type(ex).__name__}: {ex}"[:300])
+
     # ---- parity (outside every timed region): the measured path against the reference's CPU path, at the bench shape (N = 1) or through the
     # sharded protocol inside this process group (N > 1)
     parity = None
@@ -854,7 +958,7 @@ def run_ours(args):
                                    if world > 1 and peer is not None else {}),
                                 stage_ms={k: round(v, 4) for k, v in per_stage.items()}, stage_sum_ms=step_stage_ms, last_loss=last_loss),
                     clocks=clocks, e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4), gpu_launches=int(launches),
-                    roofline=roof, cpu_baseline=cpu, parity=parity, e2e_raw_edges=e2e_raw, configs=extra, impl="marius_b200")
+                    roofline=roof, cpu_baseline=cpu, parity=parity, e2e_raw_edges=e2e_raw, configs=extra, buffered=buffered, impl="marius_b200")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -877,6 +981,9 @@ def main():
     ap.add_argument("--ref-max-steps", type=int, default=24, help="--impl reference: upper bound on the timed CPU batches")
     ap.add_argument("--cpu-steps", type=int, default=3, help="batches of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-buffered", action="store_true", help="skip the buffered-table epoch (16 partitions, capacity 8, BETA ordering, swaps included)")
+    ap.add_argument("--buffered-partition-rows", type=int, default=250_000)
+    ap.add_argument("--buffered-edges-per-bucket", type=int, default=200_000)
     ap.add_argument("--no-extra-shapes", action="store_true", help="skip the other shapes (FB15k-237 sizes, DistMult d=400, batch 1000 / 10000)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (one bench-shape batch against the reference's CPU path, untimed)")
     ap.add_argument("--parity-disjoint", action="store_true", help="N > 1 parity: give every rank disjoint rows (no row updated by two ranks)")
