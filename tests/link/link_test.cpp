@@ -120,6 +120,7 @@ int link_train_loop(float* table, float* state, int64_t num_nodes, int d, int nu
         GraphModelStoragePtrs ptrs;
         ptrs.node_embeddings = std::make_shared<B200Table>(emb_t);
         ptrs.node_optimizer_state = std::make_shared<B200Table>(st_t);
+        ptrs.edges = std::make_shared<InMemory>(i64(edges, {B, 3}));  // the reference's own host InMemory (graph_storage.cpp:76 reads its size)
         auto gms = std::make_shared<GraphModelStorage>(ptrs, false);  // the reference's facade, unmodified
         auto loader = make_loader(gms, C, N);                         // the reference's DataLoader, unmodified
         auto rel_d = f32(rel, {num_rel, d}).to(dev), inv_d = f32(inv_rel, {num_rel, d}).to(dev);
@@ -177,6 +178,7 @@ int link_error_conventions() {
         GraphModelStoragePtrs ptrs;
         ptrs.node_embeddings = std::make_shared<B200Table>(torch::zeros({16, 8}, torch::TensorOptions().device(dev)));
         ptrs.node_optimizer_state = std::make_shared<B200Table>(torch::zeros({16, 8}, torch::TensorOptions().device(dev)));
+        ptrs.edges = std::make_shared<InMemory>(torch::zeros({4, 3}, torch::kInt64));
         GraphModelStorage gms(ptrs, false);
         int caught = 0;
         try {
