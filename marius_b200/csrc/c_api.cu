@@ -529,8 +529,21 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         if (fused) {
             // barrier 2 (sharded): every rank has fetched the rows it needs -- from here on the tables may change
             if (p.sharded) MB_TRY(launch_shard_barrier(sh, st));
-            MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st,
-                                     p.sharded ? p.bounds : nullptr));
+            if (p.sharded && overlap && ctx->side2 != nullptr) {
+                // the gradient rows of remote rows cross NVLink (link-bound) on the second side stream while the rows this rank owns
+                // are updated (HBM-bound) on the main stream
+                MB_CUDA_TRY(cudaEventRecord(ctx->ev_fork2, st));
+                MB_CUDA_TRY(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork2, 0));
+                MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr,
+                                         ctx->side2, p.bounds, 2));
+                MB_CUDA_TRY(cudaEventRecord(ctx->ev_join2, ctx->side2));
+                MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st,
+                                         p.bounds, 1));
+                MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join2, 0));
+            } else {
+                MB_TRY(launch_seg_reduce(sh, 2, p.gcat, svals, p.offsets, p.U, d, nullptr, 0, nullptr, 0, nullptr, nullptr, table, state_table, ld, unique_ids, lr, st,
+                                         p.sharded ? p.bounds : nullptr));
+            }
         } else if (delta_e != nullptr || delta_s != nullptr) {
             MB_REQUIRE(state != nullptr && delta_e != nullptr && delta_s != nullptr, "delta_e/delta_s need state and both outputs");
             MB_TRY(launch_seg_reduce(nullptr, 1, p.gcat, svals, p.offsets, p.U, d, grad, d, state, state_ld, delta_e, delta_s, nullptr, nullptr, 0, nullptr, lr, st));
@@ -1287,7 +1300,7 @@ static mb_status train_step_any(mb_context* ctx, const mb_batch* ub, bool host_i
     MB_CUDA_TRY(cudaEventRecord(ctx->ev_out, ctx->gstream));
     MB_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out, 0));
     // kernels inside the replayed graph (mb_launch_count stays an honest kernel count); sharded: + fetch, bounds, 3 barriers, world-1 applies
-    count_launch(sh != nullptr && sh->world > 1 ? 29 + 2 + (sh->single_process ? 0 : 3) + (sh->world - 1) : 29);
+    count_launch(sh != nullptr && sh->world > 1 ? 29 + 3 + (sh->single_process ? 0 : 3) + (sh->world - 1) : 29);
     return MB_OK;
 }
 

@@ -779,6 +779,19 @@ mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int6
         return MB_ERR_INVALID;
     }
     vec::FetchArgs a{ids, U, make_sp(sh), ld, d, cache, row_ptrs};
+    // MB_FETCH_BULK=1: remote rows as bulk asynchronous copies through a shared-memory ring (row_bulk.cuh).  Verified in one process
+    // (shards on one GPU, compute-sanitizer clean) and across two GPUs at the check shape; at the bench shape across real peers it
+    // ended in a launch failure that has not been root-caused, so the register-staged kernel stays the default.
+    static const bool fetch_bulk = [] { const char* e = getenv("MB_FETCH_BULK"); return e ? atoi(e) != 0 : false; }();
+    if (!state_rows && fetch_bulk) {
+        const size_t smem = bulk::fetch_smem_bytes(d);
+        MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::fetch_remote_rows_bulk_kernel), smem, 5));
+        const int64_t chunks = (U + bulk::kFetchRows - 1) / bulk::kFetchRows;
+        const int grid_b = (int)std::min<int64_t>(chunks, (int64_t)sm_count());
+        bulk::fetch_remote_rows_bulk_kernel<<<grid_b, bulk::kFetchThreads, smem, st>>>(a);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
     const int grid = warp_grid(U);
     if (state_rows) {
         if (d <= 128)
@@ -797,7 +810,7 @@ mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int6
 
 mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                             const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                            const int64_t* ids, float lr, cudaStream_t st, const int64_t* owner_bounds) {
+                            const int64_t* ids, float lr, cudaStream_t st, const int64_t* owner_bounds, int part) {
     if (n_seg == 0) return MB_OK;
     const bool vec_ok = (d % 4 == 0) && d <= 512 && al16(rows) && (!out || (al16(out) && out_ld % 4 == 0)) && (!state || (al16(state) && state_ld % 4 == 0)) &&
                         (!delta_e || (al16(delta_e) && al16(delta_s))) && (!table || (al16(table) && al16(state_table) && ld % 4 == 0));
@@ -813,6 +826,7 @@ mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, co
         a.inbox_rows[i] = nullptr;
     }
     a.inbox_cap = 0;
+    a.part = part;
     if (sh != nullptr && sh->world > 1) {
         if (mode == 2 && owner_bounds == nullptr) {
             set_error("sharded update needs the owner bounds of the batch");

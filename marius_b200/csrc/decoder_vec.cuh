@@ -582,6 +582,7 @@ struct SegVArgs {
     int64_t* inbox_ids[8];
     float* inbox_rows[8];
     int64_t inbox_cap;
+    int part;  // sharded update: 0 = every row, 1 = only the rows this rank owns, 2 = only remote rows (their gradient rows cross NVLink)
 };
 
 __device__ __forceinline__ void adagrad4(const float4& g, const float4& s, float neg_lr, float4& de, float4& ds, float4& sn) {
@@ -616,9 +617,11 @@ __global__ void __launch_bounds__(kThreads) segment_reduce_kernel(SegVArgs a) {
                     } else {  // the owner's HBM: peer-mapped over NVLink when the owner is another rank
                         const int64_t o = r / a.sp.rows_per_rank, lr_ = r - o * a.sp.rows_per_rank;
                         if (o == a.sp.rank) {
-                            my_e = a.sp.table[o] + lr_ * a.ld;
-                            my_s = a.sp.state[o] + lr_ * a.ld;
-                        } else {
+                            if (a.part != 2) {
+                                my_e = a.sp.table[o] + lr_ * a.ld;
+                                my_s = a.sp.state[o] + lr_ * a.ld;
+                            }
+                        } else if (a.part != 1) {
                             // remote row: only its gradient row crosses NVLink, into this rank's inbox at the owner (the owner applies Adagrad)
                             const int64_t slot = u - __ldg(a.owner_bounds + o);
                             my_remote = 1;

@@ -56,7 +56,7 @@ mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int6
                                    bool state_rows, cudaStream_t st);
 mb_status launch_seg_reduce(const mb_shards* sh, int mode, const float* rows, const uint32_t* slots, const uint32_t* offsets, int64_t n_seg, int d, float* out, int64_t out_ld,
                             const float* state, int64_t state_ld, float* delta_e, float* delta_s, float* table, float* state_table, int64_t ld,
-                            const int64_t* ids, float lr, cudaStream_t st, const int64_t* owner_bounds = nullptr);
+                            const int64_t* ids, float lr, cudaStream_t st, const int64_t* owner_bounds = nullptr, int part = 0);
 
 mb_status launch_rel_reduce(const float* drel0, const float* drel1, float* out0, float* out1, const uint32_t* slots, const uint32_t* offsets, int64_t R,
                             int d, cudaStream_t st);

@@ -299,5 +299,87 @@ __global__ void __launch_bounds__(kThreads) edge_rows_bulk_kernel(vec::PrepArgs 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded table: resolve every unique row of the batch to an address and fetch the remote ones into the batch cache (see
+// vec::fetch_remote_rows_kernel).  Remote rows travel  peer HBM --NVLink--> shared memory --> local HBM  as bulk asynchronous copies in
+// both directions (cp.async.bulk global -> shared with mbarrier completion, then shared -> global as a bulk group): the bytes in flight
+// per SM are bounded by the ring (3 stages x 32 rows), not by what a warp can hold in registers across a multi-microsecond NVLink round trip.
+constexpr int kFetchRows = 32;    // ids resolved per chunk (one per lane) = row slots per stage
+constexpr int kFetchStages = 3;
+constexpr int kFetchThreads = 64;  // warp 0: resolve + load, warp 1: store
+
+inline size_t fetch_smem_bytes(int d) { return (size_t)kFetchStages * kFetchRows * d * 4 + 128 + 64 + kFetchStages * kFetchRows * 8; }
+
+__device__ __forceinline__ void bulk_store_row(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kFetchThreads) fetch_remote_rows_bulk_kernel(vec::FetchArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const int d = a.d;
+    const uint32_t row_bytes = (uint32_t)d * 4u;
+    const uint32_t bar0 = base + kFetchStages * kFetchRows * row_bytes;
+    const uint32_t dst0 = bar0 + 64u;  // per stage and slot: destination address of the staged row (0 = slot unused)
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (kFetchStages + s); };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kFetchStages; s++) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        tcptx::fence_barrier_init();
+    }
+    __syncthreads();
+    const int64_t chunks = (a.U + kFetchRows - 1) / kFetchRows;
+    int it = 0;
+    if (warp == 0) {
+        for (int64_t c = blockIdx.x; c < chunks; c += gridDim.x, it++) {
+            const int s = it % kFetchStages;
+            const uint32_t ph = (uint32_t)((it / kFetchStages) & 1);
+            const int64_t u = c * kFetchRows + lane;
+            const float* src = nullptr;
+            float* dst = nullptr;
+            if (u < a.U) {
+                const int64_t g = __ldg(a.ids + u);
+                const float* where = a.sp.table[a.sp.rank];  // padding entries point at something valid
+                if (g >= 0) {
+                    const int64_t o = g / a.sp.rows_per_rank, l = g - o * a.sp.rows_per_rank;
+                    if (o == a.sp.rank) {
+                        where = a.sp.table[o] + l * a.ld;
+                    } else {
+                        src = a.sp.table[o] + l * a.ld;
+                        dst = a.cache + u * d;
+                        where = dst;
+                    }
+                }
+                a.row_ptrs[u] = where;
+            }
+            mbar_wait(empty(s), ph ^ 1u);
+            const unsigned remote = __ballot_sync(0xffffffffu, src != nullptr);
+            asm volatile("st.shared.u64 [%0], %1;" ::"r"(dst0 + (uint32_t)(s * kFetchRows + lane) * 8u), "l"(reinterpret_cast<unsigned long long>(dst)) : "memory");
+            __syncwarp();
+            if (lane == 0) mbar_expect_tx(full(s), (uint32_t)__popc(remote) * row_bytes);  // (arrives even when the chunk has no remote row)
+            __syncwarp();
+            if (src != nullptr) bulk_load_row(base + (uint32_t)(s * kFetchRows + lane) * row_bytes, src, row_bytes, full(s));
+        }
+    } else {
+        for (int64_t c = blockIdx.x; c < chunks; c += gridDim.x, it++) {
+            const int s = it % kFetchStages;
+            const uint32_t ph = (uint32_t)((it / kFetchStages) & 1);
+            mbar_wait(full(s), ph);
+            unsigned long long dst;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(dst) : "r"(dst0 + (uint32_t)(s * kFetchRows + lane) * 8u) : "memory");
+            if (dst != 0ull) bulk_store_row(reinterpret_cast<void*>(dst), base + (uint32_t)(s * kFetchRows + lane) * row_bytes, row_bytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage's shared memory has been read: it may be refilled
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty(s));
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the rows are in the cache before the kernel ends
+    }
+}
+
 }  // namespace bulk
 }  // namespace mb

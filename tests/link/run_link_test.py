@@ -24,7 +24,8 @@ def main():
     rng = np.random.default_rng(3)
     num_nodes, R, B, Cc, N, d, steps = 6000, 5, 512, 2, 256, 64, 3
     table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
-    state = np.zeros((num_nodes, d), np.float32)
+    state = rng.uniform(0.01, 0.1, (num_nodes, d)).astype(np.float32)  # (a trained table: at state 0 the first Adagrad step is -lr * sign(g),
+    #                                                                       which is not a continuous function of the gradient)
     rel = rng.uniform(-1, 1, (R, d)).astype(np.float32)
     inv = rng.uniform(-1, 1, (R, d)).astype(np.float32)
     batches = [O.make_batch(rng, num_nodes, R, B, Cc, N) for _ in range(steps)]
@@ -49,7 +50,7 @@ def main():
     et, es = err(got_t, exp_t), err(got_s, exp_s)
     el = max(abs(float(a) - b) / abs(b) for a, b in zip(losses, exp_losses))
     conv = lib.link_error_conventions()
-    ok = et < 3e-4 and es < 1e-4 and el < 1e-4 and conv == 3  # (table: a first-step Adagrad sign flip on a near-zero gradient is lr-sized, see bench.parity_single)
+    ok = et < 1e-4 and es < 1e-4 and el < 1e-4 and conv == 3
     print(f"LINK_TEST {'OK' if ok else 'FAIL'} table_err={et:.2e} state_err={es:.2e} loss_err={el:.2e} runtime_errors_through_the_reference_facade={conv}/3")
     return 0 if ok else 1
 
