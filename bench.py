@@ -766,9 +766,12 @@ def run_ours(args):
         sampler.start()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(K)] if world > 1 else []
     e0.record()
     for i in range(W, W + K):
         step_resident(i)
+        if marks:
+            marks[i - W].record()  # per-step device times (N > 1: shows which steps carry the relation all-reduce / rank skew)
     e1.record()
     barrier()
     launches = _lib.launch_count() - launches0
@@ -777,6 +780,10 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     value = world * K * B / (total_ms / 1e3)
+    step_trace = None
+    if marks:
+        ts = [e0.elapsed_time(m) for m in marks]
+        step_trace = [round(b_ - a_, 3) for a_, b_ in zip([0.0] + ts[:-1], ts)]
 
     # ---- e2e: host (pinned) index buffers in, loss out, every step; wall clock bracketed by barriers.  The steps go through the
     # asynchronous host entry point (mb_train_step_host_async): batch i+1 is enqueued -- its H2D copies queue behind batch i's kernels on
@@ -952,6 +959,7 @@ def run_ours(args):
                                              + f"; relation grads all-reduced (NCCL) every {args.gpu_sync_interval} batches (reference gpu_sync_interval)") if world > 1 else "single GPU, fused gather+score+update step",
                                 l2="inputs larger than L2: every step gathers/updates a fresh uniform-random row set of a table >> 126 MB",
                                 unique_rows_per_step=U_mean, step_hbm_gbs_algorithmic=step_hbm, step_hbm_frac=step_hbm / pk["hbm_gbs"],
+                                **(dict(step_ms_trace_rank0=step_trace) if step_trace else {}),
                                 **(dict(remote_rows_per_step_rank0=remote_mean, remote_fraction=remote_mean / U_mean,
                                         nvlink_gbs_per_gpu_each_direction=remote_mean * (D * 4 + 8) / (step_ms * 1e-3) / 1e9,
                                         nvlink_note="per remote row: 1 embedding row in (fetch) and 1 gradient row + id out (inbox); measured peer-copy peak 770 GB/s per direction")

@@ -277,6 +277,26 @@ mb_status mb_train_step_edges_host_async(mb_context* ctx, int decoder, const int
                                          float* rel_grad, float* inv_rel_grad, int* ticket, void* stream);
 
 
+/* ---- filtered evaluation over ALL nodes ----------------------------------------------------------------------
+ * mb_filter_sort_edges   the graph's edge list ([E, cols] int64, device) sorted stably by the endpoint a corruption KEEPS (source for
+ *   destination corruption, destination when inverse != 0): the pool compute_filter_corruption searches (negative.cpp:62-112).  Done
+ *   once per evaluation, not per batch.
+ * mb_compute_filter      compute_filter_corruption with all nodes as negatives (negative.cpp:152-163, `filtered` evaluation): for batch
+ *   edge i every pool edge with the same kept endpoint and relation yields (i, id of its other endpoint).  filter_out [cap, 2] receives
+ *   the pairs ordered by batch edge, then pool order; *count_dev (device) the number of pairs (pairs beyond cap are not written).
+ * mb_evaluate_all_nodes  Model::evaluate_batch with negatives = arange(num_nodes) (negative.cpp:321-325,355) WITHOUT materialising the
+ *   [B, num_nodes] score matrix: the table streams through the score contraction in tiles of `tile_rows` rows, each tile is filtered
+ *   and its (score >= positive) counts are added to the ranks.  `edges` hold GLOBAL node ids (rows of `table`), `table` is dense
+ *   (ld == d).  ranks / inv_ranks [B] int64, pos_out / inv_pos_out [B] optional. */
+mb_status mb_filter_sort_edges(mb_context* ctx, const int64_t* graph_edges, int64_t E, int edge_cols, int inverse, int64_t max_id, int64_t* sorted_out,
+                               void* stream);
+mb_status mb_compute_filter(mb_context* ctx, const int64_t* sorted_edges, int64_t E, int edge_cols, int inverse, const int64_t* batch_edges, int64_t B,
+                            int64_t* filter_out, int64_t cap, int64_t* count_dev, void* stream);
+mb_status mb_evaluate_all_nodes(mb_context* ctx, int decoder, const float* table, int64_t num_nodes, int64_t ld, int64_t d, const int64_t* edges, int64_t B,
+                                int edge_cols, const float* rel, const float* inv_rel, int64_t R, const int64_t* dst_filter, int64_t Fd,
+                                const int64_t* src_filter, int64_t Fs, int precision, int64_t tile_rows, int64_t* ranks, int64_t* inv_ranks, float* pos_out,
+                                float* inv_pos_out, void* stream);
+
 /* AdagradOptimizer::step on a dense parameter (nn/optim.cpp:114-145): state += g*g ; p -= lr * g / (sqrt(state) + eps) */
 mb_status mb_dense_adagrad_step(float* param, float* state_sum, const float* grad, int64_t n, float lr, float eps, void* stream);
 

@@ -69,6 +69,9 @@ _SIGS = {
     "mb_ipc_import": [_vp, _vp, _i64, C.POINTER(_vp)],
     "mb_profile_read": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "mb_profile_timeline": [_vp, _i32, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)],
+    "mb_filter_sort_edges": [_vp, _vp, _i64, _i32, _i32, _i64, _vp, _vp],
+    "mb_compute_filter": [_vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp],
+    "mb_evaluate_all_nodes": [_vp, _i32, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "mb_shard_error": [_vp, C.POINTER(mb_shards), C.POINTER(C.c_int)],
     "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }

@@ -1098,6 +1098,146 @@ mb_status mb_evaluate_batch(mb_context* ctx, const mb_batch* batch, const float*
     return MB_OK;
 }
 
+// ---- score-filter construction + streaming all-node evaluation ------------------------------------------------
+mb_status mb_filter_sort_edges(mb_context* ctx, const int64_t* graph_edges, int64_t E, int edge_cols, int inverse, int64_t max_id, int64_t* sorted_out,
+                               void* stream) {
+    MB_REQUIRE(ctx != nullptr && E >= 0 && max_id >= 0, "bad arguments");
+    MB_REQUIRE(edge_cols == 2 || edge_cols == 3, "Edge list must be a 3 or 2 column tensor");
+    MB_REQUIRE(E == 0 || (graph_edges != nullptr && sorted_out != nullptr), "null pointer");
+    MB_REQUIRE(E < ((int64_t)1 << 32), "too many edges for 32-bit sort payloads");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    uint64_t *ka, *kb;
+    uint32_t *va, *vb, *hist;
+    auto lay = [&](Arena& ar) {
+        ka = ar.take<uint64_t>(E);
+        kb = ar.take<uint64_t>(E);
+        va = ar.take<uint32_t>(E);
+        vb = ar.take<uint32_t>(E);
+        hist = reinterpret_cast<uint32_t*>(ar.take<char>(sort_scratch_bytes(E)));
+    };
+    Arena sizing(nullptr);
+    lay(sizing);
+    MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+    Arena place(ctx->ws);
+    lay(place);
+    // the kept endpoint: the source for destination corruption, the destination for source corruption (negative.cpp:70-78)
+    const int key_col = inverse ? edge_cols - 1 : 0;
+    return launch_filter_sort(graph_edges, E, edge_cols, key_col, ka, kb, va, vb, hist, bits_for((uint64_t)max_id), sorted_out, st);
+}
+
+mb_status mb_compute_filter(mb_context* ctx, const int64_t* sorted_edges, int64_t E, int edge_cols, int inverse, const int64_t* batch_edges, int64_t B,
+                            int64_t* filter_out, int64_t cap, int64_t* count_dev, void* stream) {
+    MB_REQUIRE(ctx != nullptr && E >= 0 && B >= 0 && cap >= 0 && count_dev != nullptr, "bad arguments");
+    MB_REQUIRE(edge_cols == 2 || edge_cols == 3, "Edge list must be a 3 or 2 column tensor");
+    MB_REQUIRE((E == 0 || sorted_edges != nullptr) && (B == 0 || batch_edges != nullptr) && (cap == 0 || filter_out != nullptr), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    int64_t *counts, *offsets;
+    auto lay = [&](Arena& ar) {
+        counts = ar.take<int64_t>(B + 1);
+        offsets = ar.take<int64_t>(B + 1);
+    };
+    Arena sizing(nullptr);
+    lay(sizing);
+    MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+    Arena place(ctx->ws);
+    lay(place);
+    const int key_col = inverse ? edge_cols - 1 : 0, cor_col = inverse ? 0 : edge_cols - 1;
+    return launch_filter_match(sorted_edges, E, edge_cols, key_col, cor_col, batch_edges, B, counts, offsets, filter_out, cap, count_dev, st);
+}
+
+mb_status mb_evaluate_all_nodes(mb_context* ctx, int decoder, const float* table, int64_t num_nodes, int64_t ld, int64_t d, const int64_t* edges, int64_t B,
+                                int edge_cols, const float* rel, const float* inv_rel, int64_t R, const int64_t* dst_filter, int64_t Fd,
+                                const int64_t* src_filter, int64_t Fs, int precision, int64_t tile_rows, int64_t* ranks, int64_t* inv_ranks, float* pos_out,
+                                float* inv_pos_out, void* stream) {
+    MB_REQUIRE(ctx != nullptr && table != nullptr && ranks != nullptr, "UndefinedTensor");
+    MB_REQUIRE(num_nodes > 0 && d > 0 && ld == d && B >= 0 && Fd >= 0 && Fs >= 0, "bad dimensions (the table must be dense: ld == d)");
+    MB_REQUIRE(precision >= MB_PREC_FP32 && precision <= MB_PREC_BF16, "unknown precision");
+    cudaStream_t st = (cudaStream_t)stream;
+    MB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (B == 0) return MB_OK;
+    // the positives as one chunk (C = 1); the "negatives" are the table itself, tile by tile
+    mb_batch b;
+    std::memset(&b, 0, sizeof(b));
+    b.decoder = decoder;
+    b.U = num_nodes;
+    b.d = d;
+    b.B = B;
+    b.R = R;
+    b.C = 1;
+    b.N = 8;
+    b.edges = edges;
+    b.edge_cols = edge_cols;
+    b.dst_negs = edges;  // (placeholder: no negative rows are gathered, CN = 0 below)
+    b.src_negs = inv_rel != nullptr ? edges : nullptr;
+    b.rel = rel;
+    b.inv_rel = inv_rel;
+    MB_TRY(validate_batch(&b));
+    Plan p;
+    fill_plan_dims(p, &b, precision);
+    const int sides = p.sides;
+    if (sides == 2) MB_REQUIRE(inv_ranks != nullptr, "inverse outputs required when inverse relations are used");
+    MB_REQUIRE(p.use_tc || precision == MB_PREC_FP32, "all-node evaluation needs d % 8 == 0 for the tensor-core path");
+    int64_t T = tile_rows > 0 ? tile_rows : 32768;
+    T = std::min<int64_t>((T + 7) / 8 * 8, (num_nodes + 7) / 8 * 8);
+    float *A, *pos, *S, *NegF;
+    __nv_bfloat16 *A_hl, *Neg_hl;
+    auto lay = [&](Arena& ar) {
+        A = ar.take<float>(sides * B * d);
+        pos = ar.take<float>(sides * B);
+        A_hl = p.use_tc ? ar.take<__nv_bfloat16>(2 * sides * B * d) : nullptr;
+        Neg_hl = p.use_tc ? ar.take<__nv_bfloat16>(2 * T * d) : nullptr;
+        NegF = nullptr;
+        S = ar.take<float>(sides * B * T);
+    };
+    Arena sizing(nullptr);
+    lay(sizing);
+    MB_TRY(ensure_ws(ctx, sizing.off + 256, st));
+    Arena place(ctx->ws);
+    lay(place);
+    const int64_t a_half = sides * B * d;
+    const bool need_A = !p.use_tc || !decoder_vec_ok(table, ld, (int)d, p.has_rel, rel, sides == 2 ? inv_rel : nullptr, sides);
+    MB_TRY(launch_prep(nullptr, nullptr, nullptr, table, ld, nullptr, edges, edge_cols, rel, sides == 2 ? inv_rel : nullptr, B, B, 0, (int)d, decoder, sides, nullptr,
+                       nullptr, need_A ? A : nullptr, pos, p.use_tc ? (void*)A_hl : nullptr, p.use_tc ? (void*)(A_hl + a_half) : nullptr, nullptr, nullptr,
+                       nullptr, st));
+    MB_TRY(launch_fill_i64(ranks, B, 1, st));
+    if (sides == 2) MB_TRY(launch_fill_i64(inv_ranks, B, 1, st));
+    const bool any_filter = Fd > 0 || (sides == 2 && Fs > 0);
+    if (any_filter) MB_CUDA_TRY(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
+    const int passes = precision == MB_PREC_BF16 ? 1 : 3;
+    for (int64_t t0 = 0; t0 < num_nodes; t0 += T) {
+        const int64_t Tc = std::min<int64_t>(T, num_nodes - t0);
+        if (p.use_tc) {
+            MB_TRY(launch_split(table + t0 * ld, Tc * d, Neg_hl, Neg_hl + T * d, st));
+            // S[side] = A[side] . tile^T : both sides score against the same tile (one launch per side, or both sides grouped in one)
+            TcGroupProblem g[2];
+            for (int sd = 0; sd < sides; sd++)
+                g[sd] = TcGroupProblem{A_hl + sd * B * d, A_hl + a_half + sd * B * d, d, B * d, 0, Neg_hl, Neg_hl + T * d, d, T * d, 0, S + sd * B * T, T, B * T,
+                                       (int)B, (int)Tc, (int)d, 1};
+            MB_TRY(gemm_tc_grouped(g, sides, passes, st));
+        } else {
+            MB_TRY(gemm_simt(A, d, 1, B * d, table + t0 * ld, 1, d, 0, S, T, B * T, (int)B, (int)Tc, (int)d, sides, st));
+        }
+        if (Fd > 0) MB_TRY(launch_filter_tile(S, B, T, t0, Tc, dst_filter, Fd, num_nodes, ctx->d_flag, st));
+        MB_TRY(launch_rank_accumulate(pos, S, B, Tc, T, ranks, st));
+        if (sides == 2) {
+            if (Fs > 0) MB_TRY(launch_filter_tile(S + B * T, B, T, t0, Tc, src_filter, Fs, num_nodes, ctx->d_flag, st));
+            MB_TRY(launch_rank_accumulate(pos + B, S + B * T, B, Tc, T, inv_ranks, st));
+        }
+    }
+    if (pos_out) MB_CUDA_TRY(cudaMemcpyAsync(pos_out, pos, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    if (inv_pos_out && sides == 2) MB_CUDA_TRY(cudaMemcpyAsync(inv_pos_out, pos + B, sizeof(float) * B, cudaMemcpyDeviceToDevice, st));
+    if (any_filter) {
+        int host_flag = 0;
+        MB_CUDA_TRY(cudaMemcpyAsync(&host_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        MB_CUDA_TRY(cudaStreamSynchronize(st));
+        MB_REQUIRE(host_flag == 0, "score filter index out of range");
+    }
+    (void)NegF;
+    return MB_OK;
+}
+
 mb_status mb_train_batch(mb_context* ctx, const mb_batch* batch, const float* emb, int64_t emb_ld, const float* state, int64_t state_ld, float lr,
                          int reduction, int precision, float* loss, float* grad, float* delta_e, float* delta_s, float* rel_grad, float* inv_rel_grad,
                          void* stream) {

@@ -306,3 +306,43 @@ void Model::evaluate_batch(shared_ptr<Batch> batch) {  // model.cpp:335-349
     reporter_->addRanks(ranks);
     if (inverse) reporter_->addRanks(inv_ranks);
 }
+
+// ---- compute stage ---------------------------------------------------------------------------------------------------------------
+ComputeWorkerGPU::ComputeWorkerGPU(shared_ptr<Model> model, shared_ptr<InMemory> embeddings, shared_ptr<InMemory> state, size_t queue_size)
+    : model_(model), embeddings_(embeddings), state_(state) {
+    device_loaded_batches_ = std::make_shared<Queue<shared_ptr<Batch>>>(queue_size);
+    device_update_batches_ = std::make_shared<Queue<shared_ptr<Batch>>>(1 << 20);
+}
+
+ComputeWorkerGPU::~ComputeWorkerGPU() { stop(); }
+
+void ComputeWorkerGPU::run() {
+    while (!done_) {
+        auto tup = device_loaded_batches_->blocking_pop();
+        if (!std::get<0>(tup)) break;  // queue closed and drained
+        shared_ptr<Batch> batch = std::get<1>(tup);
+        try {
+            // loadGPUParameters + train_batch + updateEmbeddings(gpu) (pipeline_gpu.cpp:49-91) in one fused call on this device's tables
+            batch->loss_ = model_->train_batch_fused(batch, *embeddings_, *state_, true);
+            edges_processed_ += batch->edges_.size(0);
+            batches_processed_ += 1;
+        } catch (const std::exception& e) {
+            error_ = e.what();
+            done_ = true;
+        }
+        device_update_batches_->blocking_push(batch);
+    }
+}
+
+void ComputeWorkerGPU::start() {
+    if (thread_ == nullptr) thread_ = new std::thread(&ComputeWorkerGPU::run, this);
+}
+
+void ComputeWorkerGPU::stop() {
+    if (thread_ != nullptr) {
+        device_loaded_batches_->close();
+        if (thread_->joinable()) thread_->join();
+        delete thread_;
+        thread_ = nullptr;
+    }
+}

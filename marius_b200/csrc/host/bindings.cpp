@@ -174,10 +174,29 @@ PYBIND11_MODULE(_host, m) {
         .def_readwrite("edges", &Batch::edges_)
         .def_readwrite("src_neg_filter", &Batch::src_neg_filter_)
         .def_readwrite("dst_neg_filter", &Batch::dst_neg_filter_)
+        .def_readwrite("loss", &Batch::loss_)
         .def("to", &Batch::to, py::arg("device"))
         .def("accumulateGradients", &Batch::accumulateGradients, py::arg("learning_rate"))
         .def("embeddingsToHost", &Batch::embeddingsToHost)
         .def("clear", &Batch::clear);
+
+    // the compute stage of the GPU pipeline (pipeline/pipeline_gpu.cpp:33-104) for device-resident tables
+    py::class_<ComputeWorkerGPU, shared_ptr<ComputeWorkerGPU>>(m, "ComputeWorkerGPU")
+        .def(py::init<shared_ptr<Model>, shared_ptr<InMemory>, shared_ptr<InMemory>, size_t>(), py::arg("model"), py::arg("embeddings"), py::arg("state"),
+             py::arg("queue_size") = 4)
+        .def("start", &ComputeWorkerGPU::start)
+        .def("stop", &ComputeWorkerGPU::stop, py::call_guard<py::gil_scoped_release>())
+        .def("push", [](ComputeWorkerGPU& w, shared_ptr<Batch> b) { w.device_loaded_batches_->blocking_push(b); }, py::arg("batch"),
+             py::call_guard<py::gil_scoped_release>())
+        .def("pop_finished",
+             [](ComputeWorkerGPU& w) {
+                 auto t = w.device_update_batches_->blocking_pop();
+                 return std::get<1>(t);
+             },
+             py::call_guard<py::gil_scoped_release>())
+        .def_property_readonly("edges_processed", [](ComputeWorkerGPU& w) { return (int64_t)w.edges_processed_; })
+        .def_property_readonly("batches_processed", [](ComputeWorkerGPU& w) { return (int64_t)w.batches_processed_; })
+        .def_property_readonly("error", [](ComputeWorkerGPU& w) { return w.error(); });
 
     // reporting_wrap.cpp
     py::class_<RankingMetric, shared_ptr<RankingMetric>>(m, "RankingMetric")

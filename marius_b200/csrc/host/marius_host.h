@@ -15,6 +15,7 @@
 #pragma once
 #include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
 
@@ -377,6 +378,7 @@ class Batch {
     Indices dst_neg_indices_;
     torch::Tensor src_neg_filter_;
     torch::Tensor dst_neg_filter_;
+    float loss_ = 0.f;  // (adapter: the batch's loss, recorded by the compute stage)
 
     explicit Batch(bool train);
     void to(torch::Device device);
@@ -454,4 +456,70 @@ class Model : public torch::nn::Module {
     void evaluate_batch(shared_ptr<Batch> batch);
     void clear_grad();
     void step();
+};
+
+// ---- compute stage (pipeline/pipeline_gpu.cpp:33-104, pipeline/queue.h) ----------------------------------------------------------
+/** pipeline/queue.h: bounded blocking queue between pipeline stages */
+template <class T>
+class Queue {
+    std::deque<T> q_;
+    size_t max_size_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool open_ = true;
+
+   public:
+    explicit Queue(size_t max_size) : max_size_(max_size) {}
+    void blocking_push(T item) {
+        std::unique_lock<std::mutex> lock(m_);
+        cv_.wait(lock, [this] { return q_.size() < max_size_ || !open_; });
+        q_.push_back(std::move(item));
+        lock.unlock();
+        cv_.notify_all();
+    }
+    std::tuple<bool, T> blocking_pop() {
+        std::unique_lock<std::mutex> lock(m_);
+        cv_.wait(lock, [this] { return !q_.empty() || !open_; });
+        if (q_.empty()) return std::forward_as_tuple(false, T());
+        T item = std::move(q_.front());
+        q_.pop_front();
+        lock.unlock();
+        cv_.notify_all();
+        return std::forward_as_tuple(true, std::move(item));
+    }
+    void close() {  // wake every waiter; pops drain what is left, then report "not popped"
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            open_ = false;
+        }
+        cv_.notify_all();
+    }
+    size_t size() {
+        std::lock_guard<std::mutex> lock(m_);
+        return q_.size();
+    }
+};
+
+/** ComputeWorkerGPU::run with device-resident embeddings (pipeline_gpu.cpp:49-91): a worker thread pops loaded batches, and for each
+ *  does loadGPUParameters -> Model::train_batch -> updateEmbeddings(batch, gpu = true) as ONE fused C-ABI call
+ *  (Model::train_batch_fused) on its device's tables, then hands the batch (its loss recorded) to the update-batches queue.  The
+ *  reference's transfer / host-update stages have nothing left to do when the table lives in HBM. */
+class ComputeWorkerGPU {
+    shared_ptr<Model> model_;
+    shared_ptr<InMemory> embeddings_, state_;
+    std::thread* thread_ = nullptr;
+    std::atomic<bool> done_{false};
+    string error_;
+    void run();
+
+   public:
+    shared_ptr<Queue<shared_ptr<Batch>>> device_loaded_batches_;
+    shared_ptr<Queue<shared_ptr<Batch>>> device_update_batches_;
+    std::atomic<int64_t> edges_processed_{0};
+    std::atomic<int64_t> batches_processed_{0};
+    ComputeWorkerGPU(shared_ptr<Model> model, shared_ptr<InMemory> embeddings, shared_ptr<InMemory> state, size_t queue_size = 4);
+    ~ComputeWorkerGPU();
+    void start();
+    void stop();  // closes the input queue, lets the worker drain it, joins
+    const string& error() const { return error_; }
 };

@@ -72,6 +72,14 @@ mb_status launch_split_mapped(const int64_t* mapped, const int64_t* edges, int64
 // eval_kernels.cu
 mb_status launch_score_filter(float* scores, int64_t rows, int64_t N, int64_t ld, const int64_t* filter, int64_t F, int* bad_flag, cudaStream_t st);
 mb_status launch_ranks(const float* pos, const float* neg, int64_t rows, int64_t N, int64_t ld, int64_t* ranks, cudaStream_t st);
+mb_status launch_filter_sort(const int64_t* edges, int64_t E, int cols, int key_col, uint64_t* ka, uint64_t* kb, uint32_t* va, uint32_t* vb, uint32_t* hist,
+                             int key_bits, int64_t* sorted_out, cudaStream_t st);
+mb_status launch_filter_match(const int64_t* pool, int64_t E, int cols, int key_col, int cor_col, const int64_t* batch, int64_t B, int64_t* counts,
+                              int64_t* offsets, int64_t* out, int64_t cap, int64_t* total_dev, cudaStream_t st);
+mb_status launch_filter_tile(float* scores, int64_t rows, int64_t ld, int64_t t0, int64_t T, const int64_t* filter, int64_t F, int64_t num_nodes, int* bad,
+                             cudaStream_t st);
+mb_status launch_rank_accumulate(const float* pos, const float* neg, int64_t rows, int64_t T, int64_t ld, int64_t* ranks, cudaStream_t st);
+mb_status launch_fill_i64(int64_t* p, int64_t n, int64_t v, cudaStream_t st);
 
 // shard_kernels.cu : exchange step of the sharded table (flag barriers, owner bounds, owner-side apply of received gradient rows)
 int64_t shard_exchange_bytes(int world, int64_t rows, int64_t d);

@@ -30,11 +30,13 @@ EdgeDecoder, DistMult, ComplEx = _host.EdgeDecoder, _host.DistMult, _host.ComplE
 Batch, Model, LossFunction, SoftmaxCrossEntropy = _host.Batch, _host.Model, _host.LossFunction, _host.SoftmaxCrossEntropy
 node_corrupt_forward, only_pos_forward = _host.node_corrupt_forward, _host.only_pos_forward
 LinkPredictionReporter, Hitsk, MeanRank, MeanReciprocalRank = _host.LinkPredictionReporter, _host.Hitsk, _host.MeanRank, _host.MeanReciprocalRank
+ComputeWorkerGPU = _host.ComputeWorkerGPU
 MariusRuntimeException = _host.MariusRuntimeException
 set_default_precision, default_precision = _host.set_default_precision, _host.default_precision
 
 storage = SimpleNamespace(Storage=Storage, InMemory=InMemory, PartitionBuffer=PartitionBuffer, PartitionBufferStorage=PartitionBufferStorage)
 data = SimpleNamespace(Batch=Batch)
+pipeline = SimpleNamespace(ComputeWorkerGPU=ComputeWorkerGPU)
 report = SimpleNamespace(LinkPredictionReporter=LinkPredictionReporter, Hitsk=Hitsk, MeanRank=MeanRank, MeanReciprocalRank=MeanReciprocalRank)
 nn = SimpleNamespace(Model=Model, SoftmaxCrossEntropy=SoftmaxCrossEntropy, LossFunction=LossFunction,
                      decoders=SimpleNamespace(edge=SimpleNamespace(DistMult=DistMult, ComplEx=ComplEx, EdgeDecoder=EdgeDecoder,

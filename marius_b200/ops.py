@@ -357,6 +357,53 @@ def evaluate_batch(ctx: Context, kind: int, emb: torch.Tensor, edges, rel, inv_r
     return ranks, inv_ranks, pos, inv_pos
 
 
+def filter_sort_edges(ctx: Context, graph_edges: torch.Tensor, inverse: bool, max_id: Optional[int] = None) -> torch.Tensor:
+    """The graph's edges sorted stably by the endpoint a corruption keeps (done once per evaluation; negative.cpp:62-112)."""
+    _need_cuda(graph_edges)
+    g = graph_edges.contiguous()
+    if max_id is None:
+        max_id = int(g.max().item()) if g.numel() else 0
+    out = torch.empty_like(g)
+    check(lib.mb_filter_sort_edges(ctx.handle, _ptr(g), g.size(0), g.size(1), int(bool(inverse)), int(max_id), _ptr(out), _stream()))
+    return out
+
+
+def compute_filter(ctx: Context, sorted_edges: torch.Tensor, batch_edges: torch.Tensor, inverse: bool, cap: Optional[int] = None) -> torch.Tensor:
+    """compute_filter_corruption against the whole graph with all nodes as negatives (negative.cpp:152-163): [F, 2] (row, node id)."""
+    _need_cuda(sorted_edges, batch_edges)
+    e = batch_edges.contiguous()
+    cnt = torch.zeros(1, dtype=torch.int64, device=e.device)
+    cap = int(cap) if cap is not None else max(1024, 64 * e.size(0))
+    while True:
+        out = torch.empty((cap, 2), dtype=torch.int64, device=e.device)
+        check(lib.mb_compute_filter(ctx.handle, _ptr(sorted_edges), sorted_edges.size(0), sorted_edges.size(1), int(bool(inverse)), _ptr(e), e.size(0),
+                                    _ptr(out), cap, _ptr(cnt), _stream()))
+        n = int(cnt.item())
+        if n <= cap:
+            return out[:n]
+        cap = n
+
+
+def evaluate_all_nodes(ctx: Context, kind: int, table: torch.Tensor, edges: torch.Tensor, rel, inv_rel, dst_filter=None, src_filter=None,
+                       precision: int = PREC_BF16X3, tile_rows: int = 32768):
+    """Model::evaluate_batch with every node as a negative (filtered evaluation), streamed over the table in tiles: (ranks, inv_ranks, pos, inv_pos)."""
+    _need_cuda(table, edges, rel, inv_rel, dst_filter, src_filter)
+    e = edges.contiguous()
+    B = e.size(0)
+    inverse = inv_rel is not None and rel is not None and kind != DOT and e.size(1) == 3
+    df, Fd = _check_filter(dst_filter)
+    sf, Fs = _check_filter(src_filter)
+    dev = table.device
+    ranks = torch.empty(B, dtype=torch.int64, device=dev)
+    inv_ranks = torch.empty(B, dtype=torch.int64, device=dev) if inverse else None
+    pos = torch.empty(B, dtype=torch.float32, device=dev)
+    inv_pos = torch.empty(B, dtype=torch.float32, device=dev) if inverse else None
+    check(lib.mb_evaluate_all_nodes(ctx.handle, int(kind), _ptr(table), table.size(0), _rowmajor(table, "table"), table.size(1), _ptr(e), B, e.size(1), _ptr(rel),
+                                    _ptr(inv_rel) if inverse else None, rel.size(0) if rel is not None else 0, _ptr(df), Fd, _ptr(sf), Fs, int(precision),
+                                    int(tile_rows), _ptr(ranks), _ptr(inv_ranks), _ptr(pos), _ptr(inv_pos), _stream()))
+    return ranks, inv_ranks, pos, inv_pos
+
+
 def ranking_metrics(ranks: torch.Tensor, ks=(1, 3, 10)) -> dict:
     """MeanRankMetric / MeanReciprocalRankMetric / HitskMetric (reporting.cpp:17-31) on a rank vector."""
     out = {"mean_rank": float(ranks.to(torch.float64).mean().item()), "mrr": float(ranks.to(torch.float32).reciprocal().mean().item())}

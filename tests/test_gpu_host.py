@@ -385,3 +385,41 @@ def test_evaluate_batch_needs_reporter(host):
     batch.dst_neg_indices_mapping = torch.tensor([[2, 0], [0, 1], [1, 0]]).to(CUDA)
     with pytest.raises(RuntimeError):
         model.evaluate_batch(batch)
+
+
+def test_compute_worker_gpu_stage(host):
+    """ComputeWorkerGPU adapter (pipeline_gpu.cpp:33-104 for device-resident tables): batches pushed into its loaded-batches queue are
+    trained by its worker thread (load -> train -> update fused) in order, and come out of the update-batches queue with their loss;
+    tables equal the same batches applied by direct Model::train_batch_fused calls."""
+    rng = np.random.default_rng(17)
+    num_nodes, R, B, C, N, d = 4000, 4, 256, 2, 128, 64
+    table = rng.uniform(-0.3, 0.3, (num_nodes, d)).astype(np.float32)
+    batches = [O.make_batch(rng, num_nodes, R, B, C, N) for _ in range(6)]
+
+    def mk():
+        emb = host.storage.InMemory(torch.from_numpy(table).to(CUDA))
+        st = host.storage.InMemory(torch.zeros(num_nodes, d).to(CUDA))
+        dec = host.nn.decoders.edge.ComplEx(num_relations=R, embedding_dim=d, use_inverse_relations=True, device=CUDA, mode="train")
+        return emb, st, host.nn.Model(dec, host.nn.SoftmaxCrossEntropy(reduction="sum"), CUDA)
+
+    def mkbatch(b):
+        uniq, edges, dn, sn = b
+        x = host.data.Batch(True)
+        x.unique_node_indices = torch.from_numpy(uniq)
+        x.edges = torch.from_numpy(edges)
+        x.dst_neg_indices_mapping = torch.from_numpy(dn)
+        x.src_neg_indices_mapping = torch.from_numpy(sn)
+        return x
+
+    e1, s1, m1 = mk()
+    direct = [m1.train_batch_fused(mkbatch(b), e1, s1, True) for b in batches]
+    e2, s2, m2 = mk()
+    w = host.pipeline.ComputeWorkerGPU(m2, e2, s2, 2)
+    w.start()
+    for b in batches:
+        w.push(mkbatch(b))
+    got = [w.pop_finished().loss for _ in batches]
+    w.stop()
+    assert w.error == "" and w.batches_processed == len(batches) and w.edges_processed == len(batches) * B
+    assert got == direct
+    assert torch.equal(e1.data, e2.data) and torch.equal(s1.data, s2.data)
