@@ -200,6 +200,7 @@ struct Plan {
     __nv_bfloat16 *A_hl, *Neg_hl;
     float2* stats = nullptr;  // [sides*Bp][stat_slots] (max, sum exp) per score-row slot, written by the forward contraction's epilogue
     float* zw = nullptr;      // [sides*Bp] log-partition of every score row (minus log of the loss weight): G = exp(S - zw)
+    float* block_loss = nullptr;  // [ceil(sides*Bp / 16)] per-block sums of the row losses (loss_merge_kernel)
     uint32_t *keys_a, *keys_b, *vals_a, *vals_b, *offsets, *hist;
     uint32_t *rkeys_a, *rkeys_b, *rvals_a, *rvals_b, *roffsets, *rhist;
 
@@ -225,6 +226,7 @@ struct Plan {
             gcat = ar.take<float>(n_slots * d);
             stats = use_tc ? ar.take<float2>(sides * Bp * stat_slots) : nullptr;
             zw = use_tc ? ar.take<float>(sides * Bp) : nullptr;
+            block_loss = use_tc ? ar.take<float>(loss_merge_blocks(sides * Bp) + 1) : nullptr;
             keys_a = ar.take<uint32_t>(n_slots);
             keys_b = ar.take<uint32_t>(n_slots);
             vals_a = ar.take<uint32_t>(n_slots);
@@ -435,6 +437,7 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
     // SoftmaxCrossEntropy forward + gradient (loss.cpp:50-67); both sides in one launch (rows = sides*Bp)
     const int64_t rows = p.sides * p.Bp;
     const float w = reduction == MB_REDUCTION_SUM ? 1.0f : (p.Bp > 0 ? 1.0f / (float)p.Bp : 0.f);
+    bool merged_loss = false;
     if (rows > 0 && ext != nullptr) {
         // generic autograd path: the caller's loss produced d loss / d (pos, neg, inv_pos, inv_neg); the backward contractions read the
         // fp32 gradient matrix directly (converter warps, conv_mode 2)
@@ -448,13 +451,16 @@ static mb_status run_train(mb_context* ctx, const mb_batch* b, const float* emb_
         // log-partition z of every row (-> row loss, d loss / d pos); the gradient matrix G = exp(S - z) itself is produced inside the
         // backward contractions and never written to memory
         StageTimer tm(ctx, ST_LOSS, st);
-        MB_TRY(launch_loss_merge(p.stats, p.stat_slots, p.pos, p.gpos, p.row_loss, p.zw, rows, w, st));
+        MB_TRY(launch_loss_merge(p.stats, p.stat_slots, p.pos, p.gpos, p.row_loss, p.zw, rows, w, p.block_loss, st));
+        merged_loss = true;
     } else if (rows > 0) {
         StageTimer tm(ctx, ST_LOSS, st);
         MB_TRY(launch_loss(p.S, p.S, p.pos, p.gpos, p.row_loss, nullptr, nullptr, rows, p.N, w, st, p.N));
     }
     if (loss && ext == nullptr) {
-        if (rows > 0)
+        if (rows > 0 && merged_loss)
+            MB_TRY(launch_loss_reduce(p.block_loss, loss_merge_blocks(rows), loss, st));  // (rows / 16 terms, fixed order)
+        else if (rows > 0)
             MB_TRY(launch_loss_reduce(p.row_loss, rows, loss, st));
         else
             MB_CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));

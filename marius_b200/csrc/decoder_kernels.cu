@@ -456,33 +456,68 @@ mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_l
 // Fused SoftmaxCrossEntropy, second half (the first half is the epilogue of the score contraction, gemm_tc_group.cu): merge the
 // per-slot (max, sum exp) statistics of a score row with its positive score into z = log(e^pos + sum_j e^neg_j)  (loss.cpp:57-66),
 // then  row_loss = (z - pos) w ,  d loss / d pos = (e^(pos - z) - 1) w ,  zw = (z - log w) log2 e  so that  d loss / d neg_j = exp2(neg_j log2 e - zw).
+// 16 lanes per score row (one statistics slot each, coalesced 128-byte reads), 16 rows per block; the block also leaves the sum of
+// its rows' losses in block_loss[blockIdx.x] (fixed order: deterministic), so the final loss reduction only has rows / 16 terms.
 __global__ void __launch_bounds__(256) loss_merge_kernel(const float2* __restrict__ stats, int slots, const float* __restrict__ pos,
                                                           float* __restrict__ gpos, float* __restrict__ row_loss, float* __restrict__ zw, int64_t rows,
-                                                          float w, float log_w) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    const float p = pos[i];
-    const float2* st = stats + i * slots;
-    float m = p;
-    for (int t = 0; t < slots; t++) {
-        const float2 x = st[t];
-        if (x.y > 0.f) m = fmaxf(m, x.x);  // a slot no tile wrote has sum == 0
+                                                          float w, float log_w, float* __restrict__ block_loss) {
+    __shared__ float part[16];
+    const int sub = threadIdx.x & 15, rib = threadIdx.x >> 4;
+    const int64_t i = (int64_t)blockIdx.x * 16 + rib;
+    const bool on = i < rows;
+    const float p = on ? pos[i] : 0.f;
+    float m = p, lsum = 0.f;
+    float2 x[2];  // up to 32 slots (N <= 2048) in registers, more in a second pass
+    const float2* st = stats + (on ? i : 0) * slots;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int t = sub + 16 * k;
+        x[k] = (on && t < slots) ? st[t] : make_float2(0.f, 0.f);
+        if (x[k].y > 0.f) m = fmaxf(m, x[k].x);  // a slot no tile wrote has sum == 0
     }
-    float sum = expf(p - m);
-    for (int t = 0; t < slots; t++) {
-        const float2 x = st[t];
-        if (x.y > 0.f) sum += x.y * expf(x.x - m);
+    for (int t = sub + 32; on && t < slots; t += 16) {
+        const float2 y = st[t];
+        if (y.y > 0.f) m = fmaxf(m, y.x);
     }
-    const float z = m + logf(sum);
-    gpos[i] = (expf(p - z) - 1.0f) * w;
-    row_loss[i] = (z - p) * w;
-    zw[i] = (z - log_w) * 1.4426950408889634f;  // pre-scaled by log2(e): the converter warps evaluate exp2(S * log2 e - zw)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+        if (x[k].y > 0.f) lsum += x[k].y * expf(x[k].x - m);
+    for (int t = sub + 32; on && t < slots; t += 16) {
+        const float2 y = st[t];
+        if (y.y > 0.f) lsum += y.y * expf(y.x - m);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);  // (xor butterfly: every lane holds the same sum)
+    float rl = 0.f;
+    if (on) {
+        const float sum = lsum + expf(p - m);
+        const float z = m + logf(sum);
+        rl = (z - p) * w;
+        if (sub == 0) {
+            gpos[i] = (expf(p - z) - 1.0f) * w;
+            row_loss[i] = rl;
+            zw[i] = (z - log_w) * 1.4426950408889634f;  // pre-scaled by log2(e): the converter warps evaluate exp2(S * log2 e - zw)
+        }
+    }
+    if (sub == 0) part[rib] = rl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc += part[k];
+        block_loss[blockIdx.x] = acc;
+    }
 }
 
+// rows / 16 partial sums, written by loss_merge_kernel into `block_loss`; returns how many
+int64_t loss_merge_blocks(int64_t rows) { return (rows + 15) / 16; }
+
 mb_status launch_loss_merge(const float2* stats, int slots, const float* pos, float* gpos, float* row_loss, float* zw, int64_t rows, float w,
-                            cudaStream_t st) {
+                            float* block_loss, cudaStream_t st) {
     if (rows == 0) return MB_OK;
-    loss_merge_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(stats, slots, pos, gpos, row_loss, zw, rows, w, logf(w));
+    loss_merge_kernel<<<(unsigned)loss_merge_blocks(rows), 256, 0, st>>>(stats, slots, pos, gpos, row_loss, zw, rows, w, logf(w), block_loss);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

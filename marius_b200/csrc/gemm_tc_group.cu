@@ -400,7 +400,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
         // kConvGroups), so the serial chain of one k-block (wait for the raw tile, load, synchronise, convert, fence, synchronise, arrive)
         // may take kConvGroups k-block periods of the tensor core: the groups pipeline against each other instead of splitting every
         // k-block twelve ways.  Measured (B = 50 000, both backward contractions): 2 groups 545 us, 3 groups 475 us, 4 groups (80
-        // registers per thread at 704 threads: spills) 516 us; the contraction alone, operands from global bf16 arrays, 369 us.
+        // registers per thread at 704 threads: spills) 516 us; 3 groups reading the scores straight from global memory into registers
+        // one own k-block ahead (no raw ring, 6 operand stages) 673 us -- L2 latency under this load exceeds the slack; the contraction
+        // alone, operands from global bf16 arrays, 369 us.  At 3 groups the kernel sits at ~75 % of the shared-memory bandwidth (operand
+        // reads 34 %, converter loads / stores 42 %) and 65 % tensor-pipe utilisation (profiles/r2_ncu.md).
         // Raw ring: this CTA's fp32 score tile of k-block n (128 operand rows x 32 K, 16 KB, row-major, no swizzle) is loaded by TMA into
         // slot n % 4, RAW_SLOTS k-blocks ahead of its conversion; thread 0 of the group issues the load of k-block n + RAW_SLOTS as soon as
         // every thread of the group has read slot n % 4 (the load cursor walks the same tile table, across tile boundaries).

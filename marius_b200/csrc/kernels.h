@@ -33,7 +33,9 @@ mb_status launch_split(const float* x, int64_t n, void* hi, void* lo, cudaStream
 mb_status launch_loss_grad(float* S, const float* pos, float* gpos, float* row_loss, void* G_hi, void* G_lo, int64_t rows, int N, float w, cudaStream_t st,
                            int64_t ldg = 0);
 mb_status launch_loss_reduce(const float* row_loss, int64_t n, float* loss, cudaStream_t st);
-mb_status launch_loss_merge(const float2* stats, int slots, const float* pos, float* gpos, float* row_loss, float* zw, int64_t rows, float w, cudaStream_t st);
+int64_t loss_merge_blocks(int64_t rows);
+mb_status launch_loss_merge(const float2* stats, int slots, const float* pos, float* gpos, float* row_loss, float* zw, int64_t rows, float w,
+                            float* block_loss, cudaStream_t st);
 mb_status launch_edge_backward(const float* emb, int64_t emb_ld, const int64_t* edges, int cols, const float* rel, const float* inv_rel, int64_t B, int d,
                                int decoder, const float* A0, const float* A1, const float* dA0, const float* dA1, const float* gpos0,
                                const float* gpos1, float* gcat, float* drel0, float* drel1, cudaStream_t st);
