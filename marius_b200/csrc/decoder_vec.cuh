@@ -127,26 +127,33 @@ __global__ void __launch_bounds__(kThreads) fetch_remote_rows_kernel(FetchArgs a
             }
         }
         unsigned todo = __ballot_sync(0xffffffffu, my_src != nullptr);
-        while (todo != 0) {  // remote rows of this round, two at a time
-            const int k0 = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int k1 = todo != 0 ? __ffs(todo) - 1 : k0;
-            todo &= todo - 1;  // (no-op when todo is already 0)
-            const float *r0 = shfl_ptr(my_src, k0), *r1 = shfl_ptr(my_src, k1);
-            float *w0 = shfl_ptr(my_dst, k0), *w1 = shfl_ptr(my_dst, k1);
-            float4 x0[CH], x1[CH];
+        while (todo != 0) {  // remote rows of this round, four at a time (an NVLink round trip is several microseconds: keep bytes in flight)
+            int k[4];
+            const float* r[4];
+            float* w[4];
+            int n = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                k[q] = todo != 0 ? __ffs(todo) - 1 : k[0];
+                if (todo != 0) n++;
+                todo &= todo - 1;  // (no-op once todo is 0)
+                r[q] = shfl_ptr(my_src, k[q]);
+                w[q] = shfl_ptr(my_dst, k[q]);
+            }
+            float4 x[4][CH];
 #pragma unroll
             for (int c = 0; c < CH; c++) {
                 const int vc = min(lane + 32 * c, dv - 1);
-                x0[c] = ldg_nc4(r0, vc);
-                x1[c] = ldg_nc4(r1, vc);
+#pragma unroll
+                for (int q = 0; q < 4; q++) x[q][c] = ldg4(r[q], vc);  // (plain loads: the peer may have rewritten the row in an earlier step)
             }
 #pragma unroll
             for (int c = 0; c < CH; c++) {
                 const int v = lane + 32 * c;
                 if (v < dv) {
-                    st4(w0, v, x0[c]);
-                    if (k1 != k0) st4(w1, v, x1[c]);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (q < n) st4(w[q], v, x[q][c]);
                 }
             }
         }
