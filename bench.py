@@ -761,6 +761,10 @@ def run_ours(args):
         # longer than the warm-up that one-time cost would otherwise land inside the timed steps
         dist.all_reduce(rel_grads)
     barrier()
+    if world > 1:
+        # The ranks leave the host barrier up to a few ms apart.  One more untimed step: its device-side flag barriers line the GPUs up, so
+        # that every rank's start event marks (nearly) the same instant and the max over ranks is not inflated by host skew.
+        step_resident(W - 1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
