@@ -301,9 +301,15 @@ mb_status mb_evaluate_all_nodes(mb_context* ctx, int decoder, const float* table
 mb_status mb_dense_adagrad_step(float* param, float* state_sum, const float* grad, int64_t n, float lr, float eps, void* stream);
 
 /* Diagnostic entry point for the contraction kernels (tests/, profiling): D[b] (MxN) = A[b] . B[b] over K, fp32 in/out.
- * a_mn == 0: A is [batches][M][K]; a_mn == 1: A is [batches][K][M].  b_mn likewise with N.  block_n in {128, 256}. */
+ * a_mn == 0: A is [batches][M][K]; a_mn == 1: A is [batches][K][M].  b_mn likewise with N.  block_n: 2 = run the backward
+ * contraction kernel (A operand converted in the kernel from the fp32 matrix, through tensor memory; b_mn must be 1), 3 = the same with
+ * the A operand staged in shared memory; any other value = the plain kernel on pre-split bf16 operands. */
 mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* B, int b_mn, float* D, int M, int N, int K, int batches,
                         int precision, int block_n, void* stream);
+/* Diagnostics (MB_TC_WAITLOG=1 in the environment): the contraction kernels bound every barrier wait and trap instead of hanging; with the
+ * log enabled a waiter that gives up first leaves (block << 32 | thread, barrier shared address << 32 | parity) in host-mapped memory.
+ * Copies up to cap / 2 records into out and returns their number; readable even after the failed launch poisoned the context. */
+int mb_debug_wait_log(uint64_t* out, int cap);
 
 /* mb_train_step / mb_train_step_host replay the step as one CUDA graph from the second call with the same signature on (same shapes,
  * tables, relation tables, output pointers, stream); index tensors and the unique-row count may change freely.  MB_GRAPH=0 in the

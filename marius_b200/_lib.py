@@ -73,6 +73,7 @@ _SIGS = {
     "mb_compute_filter": [_vp, _vp, _i64, _i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp],
     "mb_evaluate_all_nodes": [_vp, _i32, _vp, _i64, _i64, _i64, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "mb_shard_error": [_vp, C.POINTER(mb_shards), C.POINTER(C.c_int)],
+    "mb_debug_wait_log": [C.POINTER(C.c_uint64), _i32],
     "mb_debug_gemm": [_vp, _vp, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp],
 }
 EXPORTS = list(_SIGS) + ["mb_profile_num_stages", "mb_profile_stage_name", "mb_destroy", "mb_last_error", "mb_version", "mb_launch_count", "mb_build_info", "mb_workspace_bytes", "mb_shard_exchange_bytes"]

@@ -37,7 +37,7 @@ def build_cuda(force: bool = False, verbose: bool = True) -> str:
         objdir = os.path.join(LIBDIR, "obj")
         os.makedirs(objdir, exist_ok=True)
         hdrs = deps[len(srcs):]
-        flags = [f for f in NVCC_FLAGS if f != "-shared"]
+        flags = [f for f in NVCC_FLAGS if f != "-shared"] + os.environ.get("MB_NVCC_EXTRA", "").split()
         objs, procs = [], []
         for s in srcs:
             o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")

@@ -1665,12 +1665,53 @@ mb_status mb_debug_gemm(mb_context* ctx, const float* A, int a_mn, const float* 
     Arena place(ctx->ws);
     __nv_bfloat16* a_hl = place.take<__nv_bfloat16>(2 * na);
     __nv_bfloat16* b_hl = place.take<__nv_bfloat16>(2 * nb);
-    MB_TRY(launch_split(A, na, a_hl, a_hl + na, st));
     MB_TRY(launch_split(B, nb, b_hl, b_hl + nb, st));
-    (void)block_n;  // (kept in the ABI; there is one tensor-core kernel)
+    if (block_n == 2 || block_n == 3) {
+        // diagnostics of the backward kernels: the A operand is converted inside the kernel from the fp32 matrix (conv_mode 2: identity);
+        // block_n == 3 additionally forces the shared-memory-A kernel
+        MB_REQUIRE(b_mn, "the converting kernels take an MN-major B operand");
+        TcGroupProblem g{nullptr, nullptr, 0, 0, a_mn ? 1 : 0, b_hl, b_hl + nb, N, (int64_t)N * K, 1, D, N, (int64_t)M * N, M, N, K, batches};
+        g.conv_src = A;
+        g.conv_ld = a_mn ? M : K;
+        g.conv_sb = (int64_t)M * K;
+        g.conv_rows = a_mn ? K : M;
+        g.conv_cols = a_mn ? M : K;
+        g.conv_mode = 2;
+        return gemm_tc_grouped(&g, 1, precision == MB_PREC_BF16 ? 1 : 3, st, block_n == 3);
+    }
+    if (block_n == 4 || block_n == 5) {
+        // diagnostics: BOTH backward problems in one grouped launch, from one square fp32 matrix S [batches][M][M] (K == M):
+        //   D[b] = f(S[b]) . B[b]   and   D[batches + b] = f(S[b])^T . B[batches + b],   f = identity (4) or exp (5, zero shifts)
+        // B is [2 * batches][K][N] (MN-major), D is [2 * batches][M][N].
+        MB_REQUIRE(b_mn && !a_mn && M == K, "grouped diagnostics: square A, MN-major B");
+        Arena sz2(nullptr);
+        sz2.take<__nv_bfloat16>(4 * nb);
+        sz2.take<float>((int64_t)batches * M);
+        MB_TRY(ensure_ws(ctx, sz2.off + 256, st));
+        Arena pl2(ctx->ws);
+        __nv_bfloat16* b2 = pl2.take<__nv_bfloat16>(4 * nb);
+        float* z = pl2.take<float>((int64_t)batches * M);
+        MB_TRY(launch_split(B, 2 * nb, b2, b2 + 2 * nb, st));
+        MB_CUDA_TRY(cudaMemsetAsync(z, 0, sizeof(float) * batches * M, st));
+        TcGroupProblem g[2];
+        for (int q = 0; q < 2; q++) {
+            g[q] = TcGroupProblem{nullptr, nullptr, 0, 0, q, b2 + q * nb, b2 + 2 * nb + q * nb, N, (int64_t)N * K, 1, D + (int64_t)q * batches * M * N, N, (int64_t)M * N, M, N, K, batches};
+            g[q].conv_src = A;
+            g[q].conv_ld = M;
+            g[q].conv_sb = (int64_t)M * M;
+            g[q].conv_rows = M;
+            g[q].conv_cols = M;
+            g[q].conv_mode = block_n == 5 ? 1 : 2;
+            g[q].conv_z = z;
+        }
+        return gemm_tc_grouped(g, 2, precision == MB_PREC_BF16 ? 1 : 3, st);
+    }
+    MB_TRY(launch_split(A, na, a_hl, a_hl + na, st));
     return tc_contract(a_hl, a_hl + na, a_mn ? M : K, (int64_t)M * K, a_mn != 0, b_hl, b_hl + nb, b_mn ? N : K, (int64_t)N * K, b_mn != 0, D, N,
                        (int64_t)M * N, M, N, K, batches, precision == MB_PREC_BF16 ? 1 : 3, st);
 }
+
+int mb_debug_wait_log(uint64_t* out, int cap) { return gemm_tc_wait_log(reinterpret_cast<unsigned long long*>(out), cap); }
 
 static mb_status grow_i64(int64_t** p, size_t* cap, size_t need) {
     if (need <= *cap) return MB_OK;

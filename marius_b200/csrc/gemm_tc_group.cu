@@ -100,7 +100,7 @@ struct Geo {
     static constexpr int A_TILE = BLOCK_M * BK * 2;           // one of hi / lo: this CTA's 128 rows
     static constexpr int B_TILE = GHALF_N * BK * 2;           // one of hi / lo: this CTA's half of the tile columns
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int RAW_SLOTS = CONV ? 4 : 0;
+    static constexpr int RAW_SLOTS = CONV ? kConvGroups : 0;  // one private slot per converter group
     static constexpr int RAW_TILE = BLOCK_M * BK * 4;         // fp32 score tile of one k-block (this CTA's part)
     static constexpr int RAW_OFFSET = STAGES * STAGE;
     static constexpr int EPI_OFFSET = RAW_OFFSET + RAW_SLOTS * RAW_TILE;
@@ -404,54 +404,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
         // one own k-block ahead (no raw ring, 6 operand stages) 673 us -- L2 latency under this load exceeds the slack; the contraction
         // alone, operands from global bf16 arrays, 369 us.  At 3 groups the kernel sits at ~75 % of the shared-memory bandwidth (operand
         // reads 34 %, converter loads / stores 42 %) and 65 % tensor-pipe utilisation (profiles/r2_ncu.md).
-        // Raw ring: this CTA's fp32 score tile of k-block n (128 operand rows x 32 K, 16 KB, row-major, no swizzle) is loaded by TMA into
-        // slot n % 4, RAW_SLOTS k-blocks ahead of its conversion; thread 0 of the group issues the load of k-block n + RAW_SLOTS as soon as
-        // every thread of the group has read slot n % 4 (the load cursor walks the same tile table, across tile boundaries).
+        // Raw ring: this CTA's fp32 score tile of a k-block (128 operand rows x 32 K, 16 KB, row-major, no swizzle) is loaded by TMA into
+        // the private slot of the group that converts it; thread 0 of the group issues the load of the group's next k-block as soon as
+        // every thread of the group has read the current one (the load cursor walks the same tile table, across tile boundaries).
         // Operand stage: the A region gets what the TMA loads of the non-CONV kernel would produce for BK = 32:
         //   K-major A (dA = G . Neg):    128 rows (M row m0 + i) of 64 bytes (32 K), SWIZZLE_64B: 16-byte chunk index XOR ((row >> 1) & 3)
         //   MN-major A (dNeg = G^T . A): two slabs (64 M columns each) of 32 rows (K row k0 + r) of 128 bytes, SWIZZLE_128B
         // hi tile then lo tile.  Thread mapping: consecutive threads take consecutive float4 of a raw row (conflict-free 128-bit loads);
         // their 8-byte stores cover whole operand rows (all 32 banks).
-        constexpr int RS = G::RAW_SLOTS > 0 ? G::RAW_SLOTS : 2;
         constexpr int kGroupThreads = 128;
         constexpr int kPieces = (BLOCK_M * BK / 4) / kGroupThreads;           // float4 pieces per thread per k-block (8)
         const int ct = (int)threadIdx.x - kTcThreads;
         const int grp = ct / kGroupThreads, gt = ct % kGroupThreads;
         const int bar_read = 1 + 2 * grp, bar_done = 2 + 2 * grp;             // named barriers of the group
         const uint32_t raw_base = smem_base + G::RAW_OFFSET;
-        // ---- load cursor (thread 0 of each group): walks every (tile, k-block), RAW_SLOTS ahead of the conversion
+        // ---- load cursor (thread 0 of each group): the group's own k-blocks, one ahead (see gemm_tc_ts_kernel on why the slot is private)
         int lr = -1, lkb = 0, lnkb = 0;  // table round, k-block, k-blocks of that tile
         int4 le = make_int4(-1, 0, 0, 0);
-        auto load_advance = [&]() {      // move to the next (tile, k-block); lr >= p.rounds when the table is exhausted
-            if (lr >= 0 && lr < p.rounds && ++lkb < lnkb) return;
-            lkb = 0;
+        auto next_tile = [&]() {
             while (++lr < p.rounds) {
                 le = p.table[lr * num_clusters + cluster_id];
                 if (le.x >= 0) {
                     lnkb = (p.prob[le.x & 0xff].K + BK - 1) / BK;
+                    lkb = 0;
                     return;
                 }
             }
         };
-        auto load_issue = [&](int slot) {  // TMA of the score tile at the load cursor into raw slot `slot`
+        auto load_seek = [&](int steps) {  // the cursor moves `steps` k-blocks forward, across tiles; lr >= p.rounds: past the end
+            while (lr < p.rounds) {
+                if (lkb + steps < lnkb) {
+                    lkb += steps;
+                    return;
+                }
+                steps -= lnkb - lkb;
+                next_tile();
+            }
+        };
+        auto load_issue = [&]() {  // TMA of the score tile at the load cursor into the group's raw slot
             if (lr >= p.rounds) return;
             const int pi = le.x & 0xff;
             const GProblem& lp = p.prob[pi];
             const int lm = le.z + (int)rank * BLOCK_M;
-            mbar_expect_tx(raw_bar(slot), G::RAW_TILE);
+            mbar_expect_tx(raw_bar(grp), G::RAW_TILE);
             if (lp.a_mn == 0)
-                tma_load_3d(raw_base + slot * G::RAW_TILE, &maps.m[pi][0], raw_bar(slot), lkb * BK, lm, le.y);  // box {32 K columns, 128 M rows}
+                tma_load_3d(raw_base + grp * G::RAW_TILE, &maps.m[pi][0], raw_bar(grp), lkb * BK, lm, le.y);  // box {32 K columns, 128 M rows}
             else
-                tma_load_3d(raw_base + slot * G::RAW_TILE, &maps.m[pi][0], raw_bar(slot), lm, lkb * BK, le.y);  // box {128 M columns, 32 K rows}
+                tma_load_3d(raw_base + grp * G::RAW_TILE, &maps.m[pi][0], raw_bar(grp), lm, lkb * BK, le.y);  // box {128 M columns, 32 K rows}
         };
         if (gt == 0) {
-            load_advance();
-            for (int s = 0; s < G::RAW_SLOTS; s++) {  // k-block s goes to slot s; its load is issued by the group that will convert it
-                if (s % kConvGroups == grp) load_issue(s);
-                load_advance();
-            }
+            next_tile();
+            load_seek(grp);
+            load_issue();
         }
-        int stage = 0, slot = 0;
+        int stage = 0;
         uint32_t phase = 0, raw_phase = 0;
         int n = 0;  // running k-block number
         int4 e_next = p.table[cluster_id];
@@ -511,12 +517,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                             for (int j = 0; j < kPieces; j++) z[j] = (k_interior || k0 + kr0 + 4 * j < rows_lim) ? __ldg(zk + 4 * j) : INFINITY;
                         }
                     }
-                    mbar_wait(raw_bar(slot), raw_phase);
+                    mbar_wait(raw_bar(grp), raw_phase);
+                    raw_phase ^= 1u;
                     float4 v[kPieces];
 #pragma unroll
-                    for (int j = 0; j < kPieces; j++) v[j] = lds_f4(raw_base + slot * G::RAW_TILE + (uint32_t)(gt + kGroupThreads * j) * 16u);
+                    for (int j = 0; j < kPieces; j++) v[j] = lds_f4(raw_base + grp * G::RAW_TILE + (uint32_t)(gt + kGroupThreads * j) * 16u);
                     named_barrier_sync(bar_read, kGroupThreads);  // every thread of the group holds its part of the raw tile: the slot is free
-                    if (gt == 0) load_issue(slot);
+                    if (gt == 0) {
+                        load_seek(kConvGroups);
+                        load_issue();
+                    }
                     mbar_wait(empty_bar(stage), phase ^ 1u);  // the tensor core is done with the operand stage's previous contents
                     const uint32_t sA = smem_base + stage * G::STAGE;
                     if (expo) {
@@ -549,14 +559,440 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
                     named_barrier_sync(bar_done, kGroupThreads);  // the CTA's A tiles are complete: one CTA-local arrival (the non-leader's is
                     if (gt == 32) mbar_arrive(leader ? full_bar(stage) : afull_bar(stage));  // forwarded to the leader's full barrier by its warp 1)
                 }
-                if (gt == 0) load_advance();  // the cursor stays RAW_SLOTS k-blocks ahead of n
                 if (++stage == NST) {
                     stage = 0;
                     phase ^= 1u;
                 }
-                if (++slot == RS) {
-                    slot = 0;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+    }
+}
+
+
+// =====================================================================================================================================
+// TS variant of the backward contractions: the A operand (G, or G^T) is written by the converter warps straight into TENSOR MEMORY and
+// read from there by tcgen05.mma ([a_tmem] operand), instead of going through shared memory.  Two consequences:
+//   * the operand stages in shared memory hold only B, so the shared-memory traffic per k-block drops from ~112 KB to ~96 KB *for a tile
+//     1.6x as wide* (the smem-A kernel above is bound by shared-memory bandwidth, not by the tensor core);
+//   * one tile covers ALL output columns of a 256-row block (N <= 416: accumulator columns [0, 224) and [224, 416), two MMAs per k-step
+//     with the same A): every score element is converted once per problem instead of once per column tile, and read once.
+// Tensor memory: accumulator 416 columns (single-buffered: the epilogue of a tile is not overlapped with the next tile's MMAs, ~10 % of
+// a tile at K = 1000) + 3 A stages of 32 columns (bf16 hi: 16 columns = 32 K, bf16 lo: 16 columns), one per converter group.
+// A from tensor memory cannot be transposed: for dNeg = G^T . A the converter thread of operand row m reads COLUMN m of the fp32 score
+// tile (conflict-free: consecutive threads, consecutive addresses); for dA = G . Neg it reads row m of a SWIZZLE_128B tile.
+struct GeoTS {
+    static constexpr int BK = 32;
+    static constexpr int STAGES = 4;                    // B operand stages (shared memory)
+    static constexpr int A_STAGES = kConvGroups;        // A operand stages (tensor memory)
+    static constexpr int PIECE0 = 224;                  // accumulator columns of the first column piece
+    static constexpr int ACC_COLS = 416;                // 224 + 192
+    static constexpr int A_COLS = 32;                   // per A stage: hi 16 columns, lo 16 columns
+    static constexpr int B_TILE = GHALF_N * BK * 2;     // one of hi / lo of one column piece: this CTA's half (8 KB)
+    static constexpr int STAGE = 4 * B_TILE;            // piece 0 hi, piece 0 lo, piece 1 hi, piece 1 lo
+    static constexpr int RAW_SLOTS = kConvGroups;       // fp32 score tiles in flight: one private slot per converter group
+    static constexpr int RAW_TILE = BLOCK_M * BK * 4;
+    static constexpr int RAW_OFFSET = STAGES * STAGE;
+    static constexpr int EPI_OFFSET = RAW_OFFSET + RAW_SLOTS * RAW_TILE;
+    static constexpr int BAR_OFFSET = EPI_OFFSET + kEpilogueSmemBytes;
+    static constexpr int SMEM_TOTAL = BAR_OFFSET + 256 + 1024;
+    static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+    static_assert(ACC_COLS + A_STAGES * A_COLS <= 512, "tensor memory budget");
+};
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+// 32 fp32 -> 16 columns of packed bf16 hi + 16 columns of packed bf16 lo (x ~= hi + lo; even k in the low half of a column)
+__device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+        const float h0 = __uint_as_float(h[j] << 16), h1 = __uint_as_float(h[j] & 0xffff0000u);
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l[j]) : "f"(v[2 * j + 1] - h1), "f"(v[2 * j] - h0));
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1) gemm_tc_ts_kernel(const __grid_constant__ GMaps maps, const GParams p) {
+    using G = GeoTS;
+    constexpr int BK = G::BK, NST = G::STAGES, NA = G::A_STAGES;
+    constexpr int TMEM_COLS = 512;
+    constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + G::BAR_OFFSET;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };                 // leader: the B tiles of stage s have landed (both CTAs' loads)
+    auto empty_bar = [&](int s) { return bar_base + 8u * (NST + s); };        // both: the tensor core is done with B stage s
+    const uint32_t tfull_bar = bar_base + 8u * (2 * NST);                     // both: the tile's accumulator is complete
+    const uint32_t tempty_bar = bar_base + 8u * (2 * NST + 1);                // leader: all eight epilogue warps have drained it
+    const uint32_t tmem_holder = bar_base + 8u * (2 * NST + 2);
+    auto raw_bar = [&](int s) { return bar_base + 8u * (2 * NST + 3 + s); };  // this CTA's fp32 score tile in raw slot s has landed
+    auto afull_bar = [&](int a) { return bar_base + 8u * (2 * NST + 3 + G::RAW_SLOTS + a); };           // leader: both CTAs wrote A stage a
+    auto aloc_bar = [&](int a) { return bar_base + 8u * (2 * NST + 3 + G::RAW_SLOTS + NA + a); };       // non-leader: its part of A stage a is written
+    auto aempty_bar = [&](int a) { return bar_base + 8u * (2 * NST + 3 + G::RAW_SLOTS + 2 * NA + a); }; // both: the tensor core is done with A stage a
+    static_assert(8 * (2 * NST + 3 + G::RAW_SLOTS + 3 * NA) <= 256, "barrier area");
+    volatile uint32_t* tmem_holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_holder - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int lo_mult = p.passes == 3 ? 2 : 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int q = 0; q < 2; q++)
+            for (int j = 0; j < 5; j++) prefetch_tmap(&maps.m[q][j]);
+        for (int s = 0; s < NST; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < G::RAW_SLOTS; s++) mbar_init(raw_bar(s), 1);
+        for (int a = 0; a < NA; a++) {
+            mbar_init(afull_bar(a), 2);
+            mbar_init(aloc_bar(a), 1);
+            mbar_init(aempty_bar(a), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 8);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder_ptr;
+    auto ceil32 = [](int x) { return (x + 31) & ~31; };
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs): the B tiles (MN-major, SWIZZLE_128B: 64-column slabs of BK rows of 128 bytes) =================
+        int stage = 0;
+        uint32_t phase = 0;
+        int4 e_next = p.table[cluster_id];
+        for (int r = 0; r < p.rounds; r++) {
+            const int4 e = e_next;
+            if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+            if (e.x < 0) continue;
+            const int pi = e.x & 0xff;
+            const GProblem& pr = p.prob[pi];
+            const CUtensorMap* mB_hi = &maps.m[pi][2];
+            const CUtensorMap* mB_lo = &maps.m[pi][3];
+            const int b = e.y;
+            const int w0 = min(pr.N, G::PIECE0), w1 = pr.N - w0;
+            const int nc0 = (int)rank * (ceil32(w0) / 2), nc1 = G::PIECE0 + (int)rank * (ceil32(w1) / 2);
+            const uint32_t tx_pair = (uint32_t)(2 * lo_mult * (w1 > 0 ? 2 : 1) * G::B_TILE);
+            const int num_k_blocks = (pr.K + BK - 1) / BK;
+            const bool three = p.passes == 3;
+            for (int kb = 0; kb < num_k_blocks; kb++) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t sB = smem_base + stage * G::STAGE;
+                const uint32_t lbar = full_bar(stage) & kPeerMask;
+                const int k0 = kb * BK;
+                if (elect_one() && (p.debug_flags & 16)) {
+                    if (leader) mbar_arrive(full_bar(stage));
+                } else if (elect_one()) {
+                    if (leader) mbar_expect_tx(full_bar(stage), tx_pair);
+#pragma unroll
+                    for (int j = 0; j < GHALF_N / 64; j++) {
+                        tma_load_3d_2sm(sB + j * (BK * 128), mB_hi, lbar, nc0 + 64 * j, k0, b);
+                        if (three) tma_load_3d_2sm(sB + G::B_TILE + j * (BK * 128), mB_lo, lbar, nc0 + 64 * j, k0, b);
+                    }
+                    if (w1 > 0) {
+#pragma unroll
+                        for (int j = 0; j < GHALF_N / 64; j++) {
+                            tma_load_3d_2sm(sB + 2 * G::B_TILE + j * (BK * 128), mB_hi, lbar, nc1 + 64 * j, k0, b);
+                            if (three) tma_load_3d_2sm(sB + 3 * G::B_TILE + j * (BK * 128), mB_lo, lbar, nc1 + 64 * j, k0, b);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (++stage == NST) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            // ================= MMA issuer: A from tensor memory, B from shared memory, two column pieces per k-step =================
+            int stage = 0, astage = 0;
+            uint32_t phase = 0, aphase = 0, tile_phase = 0;
+            constexpr uint32_t kDescHiMN = ((1024u >> 4) & 0x3fffu) | (1u << 14) | (2u << 29);
+            constexpr uint32_t b_lbo = ((uint32_t)(BK * 128) >> 4) << 16, b_kstep = 2048u >> 4;
+            const uint32_t npass = (p.debug_flags & 1) ? 0u : (uint32_t)p.passes;
+            int4 e_next = p.table[cluster_id];
+            for (int r = 0; r < p.rounds; r++) {
+                const int4 e = e_next;
+                if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+                if (e.x < 0) continue;
+                const GProblem& pr = p.prob[e.x & 0xff];
+                const int w0 = min(pr.N, G::PIECE0), w1 = pr.N - w0;
+                const uint32_t idesc0 = make_idesc(GTILE_M, ceil32(w0), false, true);
+                const uint32_t idesc1 = make_idesc(GTILE_M, ceil32(max(w1, 1)), false, true);
+                const int num_k_blocks = (pr.K + BK - 1) / BK;
+                mbar_wait(tempty_bar, tile_phase ^ 1u);  // the epilogue has drained the previous tile
+                tile_phase ^= 1u;
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(full_bar(stage), phase);
+                    mbar_wait(afull_bar(astage), aphase);
+                    tc_fence_after();
+                    const uint32_t sB = (smem_base + stage * G::STAGE) >> 4;  // 16-byte units
+                    const uint32_t tA = tmem_base + (uint32_t)(G::ACC_COLS + astage * G::A_COLS);
+                    const int k_valid = min(BK, pr.K - kb * BK);
+                    const int ksteps = (k_valid + UMMA_K - 1) / UMMA_K;
+                    if (elect_one()) {
+#pragma unroll
+                        for (uint32_t prod = 0; prod < 3; prod++) {  // hi.hi, hi.lo, lo.hi
+                            if (prod < npass) {
+                                const uint32_t ta = tA + ((prod == 2) ? 16u : 0u);
+                                const uint32_t sb0 = b_lbo | (sB + ((prod == 1) ? (uint32_t)(G::B_TILE >> 4) : 0u));
+                                const uint32_t sb1 = sb0 + (uint32_t)((2 * G::B_TILE) >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < BK / UMMA_K; ks++) {
+                                    if (ks < ksteps) {
+                                        umma_bf16_2sm_ts(tmem_base, ta + 8u * ks, ((uint64_t)kDescHiMN << 32) | (uint64_t)(sb0 + ks * b_kstep), idesc0, accumulate);
+                                        if (w1 > 0)
+                                            umma_bf16_2sm_ts(tmem_base + (uint32_t)G::PIECE0, ta + 8u * ks, ((uint64_t)kDescHiMN << 32) | (uint64_t)(sb1 + ks * b_kstep),
+                                                             idesc1, accumulate);
+                                        accumulate = 1;
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit_2sm(empty_bar(stage));
+                        umma_commit_2sm(aempty_bar(astage));
+                        if (kb == num_k_blocks - 1) umma_commit_2sm(tfull_bar);
+                    }
+                    __syncwarp();
+                    if (p.debug_flags & 64) mbar_wait(aempty_bar(astage), aphase);  // ablation: one k-block in flight at a time
+                    if (++stage == NST) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                    if (++astage == NA) {
+                        astage = 0;
+                        aphase ^= 1u;
+                    }
+                }
+            }
+        } else {
+            // Non-leader CTA: forward "this CTA's part of A stage a is written" to the leader's barrier (see the smem-A kernel above)
+            int astage = 0;
+            uint32_t aphase = 0;
+            int4 e_next = p.table[cluster_id];
+            for (int r = 0; r < p.rounds; r++) {
+                const int4 e = e_next;
+                if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+                if (e.x < 0) continue;
+                const int num_k_blocks = (p.prob[e.x & 0xff].K + BK - 1) / BK;
+                for (int kb = 0; kb < num_k_blocks; kb++) {
+                    mbar_wait(aloc_bar(astage), aphase);
+                    if (elect_one()) {
+                        if (p.debug_flags & 32) mbar_arrive_remote(afull_bar(astage), 0);
+                        else mbar_arrive_remote_light(afull_bar(astage), 0);
+                    }
+                    __syncwarp();
+                    if (++astage == NA) {
+                        astage = 0;
+                        aphase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ================= epilogue warps 2..5 (both CTAs): 32-column chunks of the 416-column accumulator -> TMA store =================
+        const int q = warp & 3;
+        uint32_t tile_phase = 0;
+        uint32_t epi_chunk = 0;
+        int4 e_next = p.table[cluster_id];
+        for (int r = 0; r < p.rounds; r++) {
+            const int4 e = e_next;
+            if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+            if (e.x < 0) continue;
+            const GProblem& pr = p.prob[e.x & 0xff];
+            const CUtensorMap* mD = &maps.m[e.x & 0xff][4];
+            const int b = e.y;
+            const int m0 = e.z + (int)rank * BLOCK_M;
+            mbar_wait(tfull_bar, tile_phase);
+            tile_phase ^= 1u;
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            float* drow = pr.D + (int64_t)b * pr.sDb + (int64_t)row * pr.ldd;
+            const bool row_ok = row < pr.M;
+            const int n_chunks = (p.debug_flags & 4) ? 0 : (pr.N + 31) / 32;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            uint32_t ra[32], rb[32];
+            auto emit = [&](const uint32_t (&rg)[32], int c) {
+                const int col0 = c * 32;
+                if (pr.tma_store) {
+                    stage_and_store(rg, smem_base + G::EPI_OFFSET + (uint32_t)((warp - 2) * 2 + (epi_chunk & 1)) * kStageTileBytes, lane, mD, col0, m0 + q * 32, b);
+                    epi_chunk++;
+                } else if (row_ok) {
+#pragma unroll
+                    for (int v = 0; v < 32; v++)
+                        if (col0 + v < pr.N) drow[col0 + v] = __uint_as_float(rg[v]);
+                }
+            };
+            if (n_chunks > 0) tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll 1
+            for (int c = 0; c < n_chunks; c += 2) {
+                tmem_ld_wait();
+                if (c + 1 < n_chunks) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 1) * 32), rb);
+                emit(ra, c);
+                if (c + 1 < n_chunks) {
+                    tmem_ld_wait();
+                    if (c + 2 < n_chunks) tmem_ld_32x32b_x32(taddr + (uint32_t)((c + 2) * 32), ra);
+                    emit(rb, c + 1);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty_bar, 0);
+        }
+        if (elect_one()) bulk_wait_all();
+    } else {
+        // ================= converter warps 6..17 (both CTAs): fp32 scores -> G -> bf16 hi / lo in tensor memory =================
+        // Three groups of four warps on interleaved k-blocks (group g: running k-block numbers g mod 3, A stage g).  Thread (sub-partition
+        // q = warp mod 4, lane) owns operand row i = 32 q + lane = TMEM lane i, and produces that row's 32 K values of the k-block.
+        constexpr int kGroupThreads = 128;
+        const int ct = (int)threadIdx.x - kTcThreads;
+        const int grp = ct / kGroupThreads, gt = ct % kGroupThreads;
+        const int bar_read = 1 + 2 * grp, bar_done = 2 + 2 * grp;
+        const int i = (warp & 3) * 32 + lane;
+        const uint32_t raw_base = smem_base + G::RAW_OFFSET;
+        const uint32_t tA = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(G::ACC_COLS + grp * G::A_COLS);
+        // Raw ring: one slot per converter group.  A barrier that several groups polled in turn would be unsafe: a group returns to a
+        // given slot only every 12 k-blocks, so it can start polling two phases ahead of the barrier, and a parity wait cannot tell
+        // "two phases behind" from "complete" (seen as a corrupted tile followed by an arrive on a phase that is still waiting for
+        // its bytes).  With a private slot the group that waits for use j is the one that consumed use j - 1.  The load of the group's
+        // next k-block (3 ahead) is issued as soon as the group holds the current tile in registers: one group period (~3 k-block
+        // periods of the tensor core) of lookahead.
+        int lr = -1, lkb = 0, lnkb = 0;  // load cursor of thread 0 of the group: table round, k-block, k-blocks of that tile
+        int4 le = make_int4(-1, 0, 0, 0);
+        auto next_tile = [&]() {
+            while (++lr < p.rounds) {
+                le = p.table[lr * num_clusters + cluster_id];
+                if (le.x >= 0) {
+                    lnkb = (p.prob[le.x & 0xff].K + BK - 1) / BK;
+                    lkb = 0;
+                    return;
+                }
+            }
+        };
+        auto load_seek = [&](int steps) {  // the cursor moves `steps` k-blocks forward, across tiles; lr >= p.rounds: past the end
+            while (lr < p.rounds) {
+                if (lkb + steps < lnkb) {
+                    lkb += steps;
+                    return;
+                }
+                steps -= lnkb - lkb;
+                next_tile();
+            }
+        };
+        auto load_issue = [&]() {  // TMA of the score tile at the cursor into the group's raw slot
+            if (lr >= p.rounds) return;
+            const int pi = le.x & 0xff;
+            const GProblem& lp = p.prob[pi];
+            const int lm = le.z + (int)rank * BLOCK_M;
+            mbar_expect_tx(raw_bar(grp), G::RAW_TILE);
+            if (lp.a_mn == 0)
+                tma_load_3d(raw_base + grp * G::RAW_TILE, &maps.m[pi][0], raw_bar(grp), lkb * BK, lm, le.y);  // box {32 K columns, 128 M rows}, SWIZZLE_128B
+            else
+                tma_load_3d(raw_base + grp * G::RAW_TILE, &maps.m[pi][0], raw_bar(grp), lm, lkb * BK, le.y);  // box {128 M columns, 32 K rows}, no swizzle
+        };
+        if (gt == 0) {
+            next_tile();
+            load_seek(grp);  // the group's first k-block
+            load_issue();
+        }
+        uint32_t raw_phase = 0, aphase = 0;
+        int n = 0;
+        int4 e_next = p.table[cluster_id];
+        for (int r = 0; r < p.rounds; r++) {
+            const int4 e = e_next;
+            if (r + 1 < p.rounds) e_next = p.table[(r + 1) * num_clusters + cluster_id];
+            if (e.x < 0) continue;
+            const GProblem& pr = p.prob[e.x & 0xff];
+            const int b = e.y;
+            const int m_base = e.z + (int)rank * BLOCK_M;
+            const int num_k_blocks = (pr.K + BK - 1) / BK;
+            const bool a_mn = pr.a_mn != 0, want_lo = p.passes == 3, expo = pr.conv_mode == 1;
+            const int rows_lim = pr.conv_rows, cols_lim = pr.conv_cols;
+            const float* zb = expo ? pr.conv_z + (int64_t)b * rows_lim : nullptr;
+            // the operand row's position in the score matrix: K-major (dA): score row m_base + i; MN-major (dNeg): score column m_base + i
+            const bool m_ok = m_base + i < (a_mn ? cols_lim : rows_lim);
+            // K-major: the shift of the thread's score row, fixed for the tile; a +inf shift turns a value into exp2(-inf) = 0
+            const float zrow = (expo && !a_mn && m_ok) ? __ldg(zb + m_base + i) : INFINITY;
+            const int lim_k = a_mn ? rows_lim : cols_lim;
+#pragma unroll 1
+            for (int kb = 0; kb < num_k_blocks; kb++, n++) {
+                if (n % kConvGroups == grp) {
+                    const int k0 = kb * BK;
+                    const bool k_interior = k0 + BK <= lim_k;
+                    // MN-major: lane l holds the shift of score row k0 + l (all lanes use it: it must not depend on this lane's own column;
+                    // operand rows beyond the matrix only feed output rows that the store clips)
+                    float zl = INFINITY;
+                    if (expo && a_mn && k0 + lane < rows_lim) zl = __ldg(zb + k0 + lane);
+                    mbar_wait(raw_bar(grp), raw_phase);
                     raw_phase ^= 1u;
+                    const uint32_t raw = raw_base + grp * G::RAW_TILE;
+                    float v[32];
+                    if (!a_mn) {
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            const float4 t = lds_f4(raw + (uint32_t)i * 128u + (uint32_t)((c ^ (i & 7)) << 4));
+                            v[4 * c] = t.x, v[4 * c + 1] = t.y, v[4 * c + 2] = t.z, v[4 * c + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) v[k] = lds_f32(raw + (uint32_t)k * 512u + (uint32_t)i * 4u);
+                    }
+                    named_barrier_sync(bar_read, kGroupThreads);  // every thread of the group holds its part of the raw tile: the slot is free
+                    if (gt == 0) {
+                        load_seek(kConvGroups);
+                        load_issue();
+                    }
+                    if (expo) {
+                        if (!a_mn) {
+                            const float zs = -zrow;
+#pragma unroll
+                            for (int k = 0; k < 32; k++) v[k] = ex2_approx(fmaf(v[k], kLog2e, zs));
+                            if (!k_interior) {
+#pragma unroll
+                                for (int k = 0; k < 32; k++)
+                                    if (k0 + k >= cols_lim) v[k] = 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 32; k++) v[k] = ex2_approx(fmaf(v[k], kLog2e, -__shfl_sync(0xffffffffu, zl, k)));
+                        }
+                    }
+                    uint32_t h[16], l[16];
+                    split32(v, h, l);
+                    mbar_wait(aempty_bar(grp), aphase ^ 1u);  // the tensor core is done with the stage's previous contents
+                    tc_fence_after();
+                    if (!(p.debug_flags & 2)) {
+                        tmem_st_32x32b_x16(tA, h);
+                        if (want_lo) tmem_st_32x32b_x16(tA + 16u, l);
+                        tmem_st_wait();
+                    }
+                    tc_fence_before();
+                    named_barrier_sync(bar_done, kGroupThreads);
+                    if (gt == 32) mbar_arrive(leader ? afull_bar(grp) : aloc_bar(grp));
+                    aphase ^= 1u;
                 }
             }
         }
@@ -631,12 +1067,37 @@ std::mutex& table_mutex() {
 
 }  // namespace
 
+// MB_TC_WAITLOG=1: bounded waits that give up leave a record in mapped host memory before the kernel traps (diagnostics)
+static unsigned long long* g_wait_log_host = nullptr;
+static void wait_log_setup() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+#ifdef MB_WAITLOG
+        const char* e = getenv("MB_TC_WAITLOG");
+        if (e == nullptr || atoi(e) == 0) return;
+        unsigned long long* h = nullptr;
+        if (cudaHostAlloc(&h, 1001 * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) return;
+        std::memset(h, 0, 1001 * sizeof(unsigned long long));
+        unsigned long long* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return;
+        if (cudaMemcpyToSymbol(tcptx::g_wait_log, &d, sizeof(d)) != cudaSuccess) return;
+        g_wait_log_host = h;
+#endif
+    });
+}
+int gemm_tc_wait_log(unsigned long long* out, int cap) {
+    if (g_wait_log_host == nullptr) return 0;
+    const int n = (int)std::min<unsigned long long>(g_wait_log_host[0], 500ull);
+    for (int i = 0; i < 2 * n && i < cap; i++) out[i] = g_wait_log_host[1 + i];
+    return n;
+}
+
 bool gemm_tc_supported(int64_t a_inner, int64_t b_inner) {
     // TMA: 16-byte global strides => inner extents (bf16) multiples of 8
     return (a_inner % 8 == 0) && (b_inner % 8 == 0) && encode_fn() != nullptr;
 }
 
-mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st) {
+mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st, bool force_smem_a) {
     if (n < 1 || n > 2) {
         set_error("gemm_tc_grouped: 1 or 2 problems");
         return MB_ERR_INVALID;
@@ -647,6 +1108,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     }
     int dev = 0;
     MB_CUDA_TRY(cudaGetDevice(&dev));
+    wait_log_setup();
     const int clusters_max = sm_count() / 2;
     GMaps maps;
     std::memset(&maps, 0, sizeof(maps));
@@ -663,6 +1125,11 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     key.dev = dev;
     key.n = n;
     int64_t total_tiles = 0;
+    // backward contractions: A operand through tensor memory, one tile per 256-row block over all columns (gemm_tc_ts_kernel), when
+    // every problem's output fits the 416 accumulator columns; MB_CONV_TS=0 keeps the shared-memory-A kernel
+    const char* ts_env = getenv("MB_CONV_TS");  // (read per call: tests switch it inside one process)
+    bool ts = (ts_env == nullptr || atoi(ts_env) != 0) && !force_smem_a;
+    for (int i = 0; i < n; i++) ts = ts && probs[i].conv_mode != 0 && probs[i].N <= GeoTS::ACC_COLS && probs[i].b_mn;
     for (int i = 0; i < n; i++) {
         const TcGroupProblem& g = probs[i];
         if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batches <= 0) {
@@ -688,9 +1155,10 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
             cuuint64_t strides[2] = {(cuuint64_t)g.conv_ld * 4, (cuuint64_t)(g.batches == 1 ? (int64_t)g.conv_rows * g.conv_ld : g.conv_sb) * 4};
             cuuint32_t box[3] = {g.a_mn ? (cuuint32_t)BLOCK_M : bk, g.a_mn ? bk : (cuuint32_t)BLOCK_M, 1};
             cuuint32_t estr[3] = {1, 1, 1};
+            // (TS kernel, K-major: rows of 32 floats = 128 bytes, SWIZZLE_128B, so that a thread per row reads them without bank conflicts)
             CUresult r = encode_fn()(&maps.m[i][0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g.conv_src), dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, (ts && !g.a_mn) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 set_error("cuTensorMapEncodeTiled (score matrix) failed with CUresult " + std::to_string((int)r));
                 return MB_ERR_CUDA;
@@ -750,7 +1218,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
         key.N[i] = g.N;
         key.K[i] = g.K;
         key.batches[i] = g.batches;
-        total_tiles += (int64_t)((g.M + GTILE_M - 1) / GTILE_M) * ((g.N + GTILE_N - 1) / GTILE_N) * g.batches;
+        total_tiles += (int64_t)((g.M + GTILE_M - 1) / GTILE_M) * (ts ? 1 : (g.N + GTILE_N - 1) / GTILE_N) * g.batches;
     }
     if (n == 1) {
         p.prob[1] = p.prob[0];
@@ -758,7 +1226,7 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     }
     int clusters = (int)std::min<int64_t>(clusters_max, total_tiles);
     key.clusters = clusters;
-    key.slot64 = with_stats ? 1 : 0;  // statistics slots are 64 columns wide: column pieces of the tail tiles must start on multiples of 64
+    key.slot64 = ts ? 2 : (with_stats ? 1 : 0);  // statistics slots are 64 columns wide: column pieces of the tail tiles must start on multiples of 64
     TableVal tv;
     {
         std::lock_guard<std::mutex> lk(table_mutex());
@@ -778,16 +1246,18 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
                 max_batches = std::max(max_batches, probs[i].batches);
             }
             auto cost_of = [&](int prob, int width) {  // MMA time ~ n_eff per k-step; + pipeline fill / epilogue drain per tile
-                return (int64_t)(((width + 31) / 32) * 32) * ksteps[prob] + 1024;
+                const int w0 = ts ? std::min(width, (int)GeoTS::PIECE0) : width;
+                return (int64_t)(((w0 + 31) / 32) * 32 + ((width - w0 + 31) / 32) * 32) * ksteps[prob] + 1024;
             };
             std::vector<Tile> base;
             for (int b = 0; b < max_batches; b++)
                 for (int i = 0; i < n; i++) {
                     const TcGroupProblem& g = probs[i];
                     if (b >= g.batches) continue;
+                    const int tile_n = ts ? (int)GeoTS::ACC_COLS : GTILE_N;  // TS kernel: one tile covers all columns
                     for (int m0 = 0; m0 < g.M; m0 += GTILE_M)
-                        for (int n0 = 0; n0 < g.N; n0 += GTILE_N) {
-                            const int w = std::min(GTILE_N, g.N - n0);
+                        for (int n0 = 0; n0 < g.N; n0 += tile_n) {
+                            const int w = std::min(tile_n, g.N - n0);
                             base.push_back({i, b, m0, n0, w, cost_of(i, w)});
                         }
                 }
@@ -819,9 +1289,10 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
                 }
                 return *std::max_element(load.begin(), load.end());
             };
-            int best_tail = 0, best_piece = GTILE_N;
+            int best_tail = 0, best_piece = ts ? (int)GeoTS::ACC_COLS : GTILE_N;
             int64_t best_span = schedule(base, nullptr);
             for (int piece : {192, 128, 96, 64}) {
+                if (ts) break;  // (full-width tiles are not split)
                 if (with_stats && piece % kTcStatSlotCols != 0) continue;
                 for (int k = 1; k <= 16; k++) {
                     const int tail = clusters * k / 4;
@@ -860,9 +1331,12 @@ mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaSt
     if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
         MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<false>::SMEM_TOTAL));
         MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_group_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<true>::SMEM_TOTAL));
+        MB_CUDA_TRY(cudaFuncSetAttribute(gemm_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GeoTS::SMEM_TOTAL));
         if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
-    if (conv)
+    if (ts)
+        gemm_tc_ts_kernel<<<2 * clusters, kConvThreads, GeoTS::SMEM_TOTAL, st>>>(maps, p);
+    else if (conv)
         gemm_tc_group_kernel<true><<<2 * clusters, kConvThreads, Geo<true>::SMEM_TOTAL, st>>>(maps, p);
     else
         gemm_tc_group_kernel<false><<<2 * clusters, kTcThreads, Geo<false>::SMEM_TOTAL, st>>>(maps, p);

@@ -25,6 +25,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Diagnostics (debug builds: MB_NVCC_EXTRA=-DMB_WAITLOG; the out-of-line call costs the kernels a stack frame): where a bounded wait gave
+// up.  When set (MB_TC_WAITLOG=1) the pointer refers to mapped host memory, which survives the trap:
+// [0] = number of records, then pairs (block << 32 | thread, shared address of the barrier << 32 | parity).
+#ifdef MB_WAITLOG
+static __device__ unsigned long long* g_wait_log = nullptr;
+static __device__ __noinline__ void wait_timed_out(uint32_t bar, uint32_t parity) {
+    unsigned long long* d = g_wait_log;
+    if (d != nullptr) {
+        const unsigned long long s = atomicAdd(d, 1ull);
+        if (s < 500) {
+            d[1 + 2 * s] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+            d[2 + 2 * s] = ((unsigned long long)bar << 32) | parity;
+        }
+        __threadfence_system();
+        const long long t0 = clock64();
+        while (clock64() - t0 < 200000000ll) {}  // let the other stuck waiters record theirs before the kernel dies
+    }
+    __trap();
+}
+#else
+__device__ __forceinline__ void wait_timed_out(uint32_t, uint32_t) { __trap(); }
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     long long t0 = clock64();
@@ -37,7 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
-        if (clock64() - t0 > kWaitTimeoutCycles) __trap();
+        if (clock64() - t0 > kWaitTimeoutCycles) wait_timed_out(bar, parity);
     }
 }
 // one lane of a converged warp (always the same one for the full mask): lets loops and address arithmetic stay warp-uniform, so
@@ -216,6 +238,28 @@ template <int NCOLS>
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
 }
+
+// ---- A operand from tensor memory (tcgen05.mma with [a_tmem]) -----------------------------------------------------------------
+// Layout (cute/atom/mma_traits_sm100.hpp, tmem_frg for a 16-bit value type, M = 128 rows per CTA): operand row m = TMEM lane m of the
+// CTA that owns the row, K runs along the columns, two bf16 per 32-bit column (even k in the low half): one K = 16 step is 8 columns.
+// The A operand cannot be transposed (a_major must be K).
+__device__ __forceinline__ void umma_bf16_2sm_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane (a warp covers the 32 lanes of its sub-partition: warp index mod 4)
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+          "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 
 }  // namespace tcptx

@@ -97,6 +97,7 @@ mb_status gemm_simt(const float* A, int64_t sAm, int64_t sAk, int64_t sAb, const
 
 // gemm_tc_group.cu : up to two contractions in one table-scheduled persistent 2-CTA launch
 bool gemm_tc_supported(int64_t a_inner, int64_t b_inner);
+int gemm_tc_wait_log(unsigned long long* out, int cap);  // diagnostics (MB_TC_WAITLOG=1): records of bounded waits that gave up
 struct TcGroupProblem {
     const void *A_hi, *A_lo;
     int64_t lda, sAb;
@@ -121,6 +122,6 @@ struct TcGroupProblem {
     int conv_rows = 0, conv_cols = 0, conv_mode = 0;
 };
 constexpr int kTcStatSlotCols = 64;
-mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st);
+mb_status gemm_tc_grouped(const TcGroupProblem* probs, int n, int passes, cudaStream_t st, bool force_smem_a = false);
 
 }  // namespace mb

@@ -625,3 +625,12 @@ def debug_gemm(ctx: Context, A: torch.Tensor, a_mn: bool, B: torch.Tensor, b_mn:
     D = torch.empty((batches, M, N), dtype=torch.float32, device=A.device)
     check(lib.mb_debug_gemm(ctx.handle, _ptr(A), int(a_mn), _ptr(B), int(b_mn), _ptr(D), M, N, K, batches, int(precision), int(block_n), _stream()))
     return D
+
+
+def debug_wait_log():
+    """Diagnostics (MB_TC_WAITLOG=1): [(block, thread, barrier shared address, parity)] of the bounded waits that gave up (see mb_debug_wait_log)."""
+    import ctypes as C
+
+    buf = (C.c_uint64 * 1000)()
+    n = lib.mb_debug_wait_log(buf, 1000)
+    return [(int(buf[2 * i] >> 32), int(buf[2 * i] & 0xFFFFFFFF), int(buf[2 * i + 1] >> 32), int(buf[2 * i + 1] & 0xFFFFFFFF)) for i in range(n)]

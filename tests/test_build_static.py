@@ -30,7 +30,7 @@ def test_built_for_sm_100a():
 
 
 def test_hot_kernels_exist_and_do_not_spill(resources):
-    hot = ["gemm_tc_group_kernel", "neg_rows_kernelILi4E", "edge_rows_kernelILi2ELi2E", "edge_backward_kernelILi2ELi2E", "loss_kernelILi8E",
+    hot = ["gemm_tc_group_kernelILb0E", "neg_rows_kernelILi4E", "edge_rows_kernelILi2ELi2E", "edge_backward_kernelILi2ELi2E", "loss_kernelILi8E",
            "segment_reduce_kernelILi2ELi4E", "fetch_remote_rows_kernelILi4ELb0E", "gather_rows_kernel", "rank_kernel", "sample_negatives_kernel",
            "loss_merge_kernel", "inbox_apply_kernelILi4E", "neg_rows_bulk_kernelILi4E"]
     for name in hot:
@@ -40,11 +40,15 @@ def test_hot_kernels_exist_and_do_not_spill(resources):
             assert v["local"] == 0 and v["stack"] == 0, f"{k} spills: {v}"
     for name in ("shard_barrier_kernel", "owner_bounds_kernel"):  # one-warp control kernels of the sharded step (dynamic indexing of their
         assert any(name in k for k in resources), name                # parameter arrays costs them a few bytes of stack: not hot)
-    # both instantiations of the persistent contraction: plain (192 threads) and with converter warps (576 threads); one CTA per SM
-    gemms = {k: v for k, v in resources.items() if "gemm_tc_group_kernel" in k}
-    assert len(gemms) == 2
+    # the persistent contractions: plain (192 threads), and the two backward kernels with converter warps (576 threads: A operand through
+    # shared memory / through tensor memory); one CTA per SM.  The 576-thread kernels are capped at 96 registers and keep one table entry
+    # (16 bytes, touched once per tile, not per k-block) on the stack.
+    gemms = {k: v for k, v in resources.items() if "gemm_tc_group_kernel" in k or "gemm_tc_ts_kernel" in k}
+    assert len(gemms) == 3
     for k, v in gemms.items():
-        assert v["reg"] * (640 if "ILb1E" in k else 192) <= 65536
+        conv = "ILb0E" not in k
+        assert v["reg"] * (640 if conv else 192) <= 65536
+        assert v["local"] == 0 and v["stack"] <= (16 if conv else 0), f"{k} spills: {v}"
 
 
 def test_sass_has_tcgen05_tma_and_system_reductions():
@@ -55,4 +59,5 @@ def test_sass_has_tcgen05_tma_and_system_reductions():
     assert re.search(r"STG\.E\.64\.STRONG\.SYS", sass) and re.search(r"LDG\.E\.64\.STRONG\.SYS", sass), \
         "the cross-rank barrier publishes / polls its epoch counters with system-scope release / acquire accesses"
     assert "UBLKCP" in sass, "the negative-row kernel stages table rows with bulk asynchronous copies (cp.async.bulk)"
+    assert "STTM" in sass and re.search(r"UTCHMMA\.2CTA tmem\[\w+\], gdesc", sass), "the backward contraction takes its A operand from tensor memory (tcgen05.st + [a_tmem])"
     assert "WGMMA" not in sass and "HMMA.16" not in sass  # neither Hopper wgmma nor legacy mma.sync anywhere
