@@ -616,13 +616,18 @@ def train_step_sharded_host(ctx: Context, kind: int, shards, ld: int, d: int, un
 
 
 def debug_gemm(ctx: Context, A: torch.Tensor, a_mn: bool, B: torch.Tensor, b_mn: bool, precision: int = PREC_BF16X3, block_n: int = 256):
-    """Diagnostic: batched D = A . B over K through the contraction kernels (see mb_debug_gemm)."""
+    """Diagnostic: batched D = A . B over K through the contraction kernels (see mb_debug_gemm).  block_n 2 / 3: the backward kernels
+    (A converted in the kernel; tensor-memory A / shared-memory A); 4 / 5: both backward problems in one grouped launch (identity / exp)."""
     _need_cuda(A, B)
     A, B = A.contiguous(), B.contiguous()
     batches = A.size(0)
     M, K = (A.size(2), A.size(1)) if a_mn else (A.size(1), A.size(2))
     N = B.size(2) if b_mn else B.size(1)
-    D = torch.empty((batches, M, N), dtype=torch.float32, device=A.device)
+    if block_n in (4, 5):  # both backward problems from one square matrix: B holds [2 * batches][K][N], D gets [2 * batches][M][N]
+        batches = A.size(0)
+        D = torch.empty((2 * batches, M, N), dtype=torch.float32, device=A.device)
+    else:
+        D = torch.empty((batches, M, N), dtype=torch.float32, device=A.device)
     check(lib.mb_debug_gemm(ctx.handle, _ptr(A), int(a_mn), _ptr(B), int(b_mn), _ptr(D), M, N, K, batches, int(precision), int(block_n), _stream()))
     return D
 

@@ -83,7 +83,7 @@ def _random_problem(seed, kind, B, C, N, d, num_nodes, R, scale=0.3, with_rel=Tr
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("kind,B,C,N,d", [(1, 100, 1, 64, 32), (2, 333, 4, 200, 64), (2, 1000, 1, 1000, 400), (1, 2000, 2, 1000, 400),
-                                          (1, 17, 5, 24, 16), (2, 130, 3, 136, 72)])
+                                          (1, 17, 5, 24, 16), (2, 130, 3, 136, 72), (2, 96, 2, 72, 432)])
 def test_train_batch_vs_oracle(ops, ctx, prec, kind, B, C, N, d):
     p = ops.PREC_FP32 if prec == "fp32" else ops.PREC_BF16X3
     uniq, edges, dn, sn, emb, state, rel, inv_rel = _random_problem(B + d, kind, B, C, N, d, 50000, 11)
@@ -201,6 +201,42 @@ def test_contraction_kernel_layouts(ops, ctx, a_mn, b_mn, block_n):
         assert err1 < 2e-2
         D0 = ops.debug_gemm(ctx, Ain, a_mn, Bin, b_mn, ops.PREC_FP32, block_n)
         assert float((D0.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("which", [2, 3])
+@pytest.mark.parametrize("a_mn", [False, True])
+def test_backward_contraction_kernels_vs_fp64(ops, ctx, which, a_mn):
+    """The backward contraction kernels (A operand converted inside the kernel from an fp32 matrix; which = 2: through tensor memory,
+    one full-width tile per 256-row block; 3: through shared memory), identity conversion, ragged shapes, vs an fp64 matmul."""
+    torch.manual_seed(3)
+    for (bt, M, N, K) in [(1, 256, 64, 32), (1, 256, 416, 64), (3, 232, 104, 40), (2, 1000, 400, 1000), (2, 300, 224, 72), (2, 520, 8, 200), (3, 77, 232, 1000),
+                          (2, 200, 424, 136)]:  # N = 424 > 416 accumulator columns: falls back to the shared-memory-A kernel
+        A = torch.randn(bt, K, M, device="cuda") if a_mn else torch.randn(bt, M, K, device="cuda")
+        Bm = torch.randn(bt, K, N, device="cuda")
+        ref = (A.double().transpose(1, 2) if a_mn else A.double()) @ Bm.double()
+        D = ops.debug_gemm(ctx, A, a_mn, Bm, True, ops.PREC_BF16X3, which)
+        err = float((D.double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-5, (which, a_mn, bt, M, N, K, err)
+
+
+@pytest.mark.parametrize("which", [4, 5])
+def test_backward_contractions_back_to_back(ops, ctx, which, monkeypatch):
+    """Both backward problems in one grouped launch, several tiles per CTA pair, launched back to back without a synchronisation in
+    between (how they run inside the step's CUDA graph): guards the raw-tile ring against waiting on a barrier two phases ahead, which
+    showed up only under this timing as corrupted tiles / a trapped arrive.  which = 4: G = S, 5: G = exp(S)."""
+    torch.manual_seed(4)
+    bt, M, N = 60, 1000, 400
+    S = torch.randn(bt, M, M, device="cuda") * 0.5
+    Bm = torch.randn(2 * bt, M, N, device="cuda")
+    f = S.double() if which == 4 else torch.exp(S.double())
+    ref = torch.cat([f @ Bm[:bt].double(), f.transpose(1, 2) @ Bm[bt:].double()], 0)
+    for ts in ("1", "0"):
+        monkeypatch.setenv("MB_CONV_TS", ts)
+        for _ in range(10):
+            D = ops.debug_gemm(ctx, S, False, Bm, True, ops.PREC_BF16X3, which)
+        torch.cuda.synchronize()
+        err = float((D.double() - ref).abs().max() / ref.abs().max())
+        assert err < 3e-5, (which, ts, err)
 
 
 def test_full_shape_property_checks(ops, ctx):
