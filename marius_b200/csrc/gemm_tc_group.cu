@@ -1,4 +1,6 @@
-// gemm_tc_group.cu -- grouped, table-scheduled 2-CTA tcgen05 GEMM (the only tensor-core contraction kernel of the library).
+// gemm_tc_group.cu -- grouped, table-scheduled 2-CTA tcgen05 GEMMs (the tensor-core contraction kernels of the library):
+// gemm_tc_group_kernel<false> (operands from bf16 hi/lo arrays; forward scores), gemm_tc_group_kernel<true> and gemm_tc_ts_kernel (backward:
+// the A operand is produced inside the kernel from the fp32 scores, staged in shared memory / in tensor memory).
 //
 // One persistent CTA pair per two SMs (cta_group::2), warp-specialised (TMA producer / MMA issuer / 4 epilogue warps), with two
 // properties that matter at the named shape (ComplEx d=400, 1000 negatives: each backward contraction has few cluster tiles per
@@ -90,9 +92,9 @@ __device__ __forceinline__ void named_barrier_sync(int id, int threads) { asm vo
 //   CONV = false (forward scores, diagnostics): k-blocks of 64, 3 operand stages of 64 KB (A hi/lo + B hi/lo), 192 threads.
 //   CONV = true  (backward contractions): the A operand of every problem is produced in the kernel from an fp32 matrix (the scores S):
 //                G = exp(S - z_row) (the SoftmaxCrossEntropy gradient, loss.cpp:50-67) or G = S.  k-blocks of 32: 4 operand stages of
-//                32 KB + a ring of 4 raw fp32 score tiles of 16 KB, so that the score tiles are in flight (TMA) several k-blocks ahead
+//                32 KB + 3 raw fp32 score tiles of 16 KB (one per converter group), so that the score tiles are in flight (TMA) ahead
 //                of their conversion, independently of the operand stages; 576 threads (12 converter warps).  The gradient matrix never
-//                exists in global memory.
+//                exists in global memory.  Used when the output is wider than the tensor-memory-A kernel below can hold (N > 416).
 template <bool CONV>
 struct Geo {
     static constexpr int BK = CONV ? 32 : 64;                 // k-block (bf16 elements)
