@@ -897,9 +897,9 @@ def run_ours(args):
         ach = flops[dom] / (per_stage[dom] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         roof = dict(bound="tensor", kernel=dom, achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=ncu_traffic(dom),
-                    launches_per_step=stage_launches.get(dom),
+                    launches_per_step=stage_launches.get(dom), issued_bf16_tflops=3 * ach, issued_frac=3 * ach / peak,
                     note=f"algorithmic fp32 flops (2MNK summed over the stage's launches in one step) / the stage's time per step; the kernel issues 3 bf16 "
-                         f"products per fp32 product (bf16x3, needed for the 1e-4 parity bar), so frac <= 1/3; peak = {pk['source']} sustained cuBLAS bf16")
+                         f"products per fp32 product (bf16x3, needed for the 1e-4 parity bar), so frac <= 1/3 and issued_frac = 3 frac is the fraction of the peak the tensor cores actually deliver; peak = {pk['source']} sustained cuBLAS bf16")
     elif dom in byts:
         ach = byts[dom] / (per_stage[dom] * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel=dom, achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"], traffic=None,
