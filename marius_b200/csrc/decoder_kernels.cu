@@ -643,10 +643,9 @@ mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float
             a.Neg_lo[s] = (on && Neg_lo) ? (__nv_bfloat16*)Neg_lo + s * CN * d : nullptr;
         }
         // negative rows first (two in flight per warp): with a sharded table they run while the remote rows are still being fetched
-        // MB_ROW_BULK: bit 0 = negative rows through the bulk-copy staged kernel (default), bit 1 = edge rows too (measured slower: its
-        // four consumer warps per block are latency-bound), bit 2 = eight consumer warps in the negative-row kernel
+        // MB_ROW_BULK: bit 0 = negative rows through the bulk-copy staged kernel (default; 0 = the register-staged kernel),
+        // bit 2 = eight consumer warps per block instead of four
         static const int bulk_mode = [] { const char* e = getenv("MB_ROW_BULK"); return e ? atoi(e) : 1; }();
-        const bool use_bulk = (bulk_mode & 2) != 0;
         if (CN > 0 && (bulk_mode & 1)) {
             // bulk-copy staged version (row_bulk.cuh): one cp.async.bulk per row into a shared-memory ring, two blocks per SM
             const size_t smem = bulk::smem_bytes(bulk::kNegRows, d);
@@ -669,22 +668,7 @@ mb_status launch_prep(const mb_shards* sh, cudaEvent_t rows_fetched, const float
             MB_LAUNCH_CHECK();
         }
         if (rows_fetched != nullptr) MB_CUDA_TRY(cudaStreamWaitEvent(st, rows_fetched, 0));
-        if (Bp > 0 && use_bulk) {
-            const size_t smem = bulk::smem_bytes(bulk::kEdgeRows, d);
-            const int64_t chunks = (Bp + bulk::kEdgesPerStage - 1) / bulk::kEdgesPerStage;
-            const int grid = (int)std::min<int64_t>(chunks, (int64_t)sm_count() * 2);
-            if (dec == MB_DECODER_COMPLEX) {
-                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::edge_rows_bulk_kernel<MB_DECODER_COMPLEX>), smem, 1));
-                bulk::edge_rows_bulk_kernel<MB_DECODER_COMPLEX><<<grid, bulk::kThreads, smem, st>>>(a);
-            } else if (dec == MB_DECODER_DISTMULT) {
-                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::edge_rows_bulk_kernel<MB_DECODER_DISTMULT>), smem, 2));
-                bulk::edge_rows_bulk_kernel<MB_DECODER_DISTMULT><<<grid, bulk::kThreads, smem, st>>>(a);
-            } else {
-                MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::edge_rows_bulk_kernel<MB_DECODER_DOT>), smem, 3));
-                bulk::edge_rows_bulk_kernel<MB_DECODER_DOT><<<grid, bulk::kThreads, smem, st>>>(a);
-            }
-            MB_LAUNCH_CHECK();
-        } else if (Bp > 0) {
+        if (Bp > 0) {
             const int grid = warp_grid(Bp);
             const bool small = d <= 128;  // chunks per lane: full row <= 1 (d <= 128) / 4 (d <= 512); complex half <= 1 (d <= 256) / 2
             if (dec == MB_DECODER_COMPLEX) {
@@ -814,19 +798,6 @@ mb_status launch_fetch_remote_rows(const mb_shards* sh, const int64_t* ids, int6
         return MB_ERR_INVALID;
     }
     vec::FetchArgs a{ids, U, make_sp(sh), ld, d, cache, row_ptrs};
-    // MB_FETCH_BULK=1: remote rows as bulk asynchronous copies through a shared-memory ring (row_bulk.cuh).  Verified in one process
-    // (shards on one GPU, compute-sanitizer clean) and across two GPUs at the check shape; at the bench shape across real peers it
-    // ended in a launch failure that has not been root-caused, so the register-staged kernel stays the default.
-    static const bool fetch_bulk = [] { const char* e = getenv("MB_FETCH_BULK"); return e ? atoi(e) != 0 : false; }();
-    if (!state_rows && fetch_bulk) {
-        const size_t smem = bulk::fetch_smem_bytes(d);
-        MB_TRY(bulk_attr(reinterpret_cast<const void*>(bulk::fetch_remote_rows_bulk_kernel), smem, 5));
-        const int64_t chunks = (U + bulk::kFetchRows - 1) / bulk::kFetchRows;
-        const int grid_b = (int)std::min<int64_t>(chunks, (int64_t)sm_count());
-        bulk::fetch_remote_rows_bulk_kernel<<<grid_b, bulk::kFetchThreads, smem, st>>>(a);
-        MB_LAUNCH_CHECK();
-        return MB_OK;
-    }
     const int grid = warp_grid(U);
     if (state_rows) {
         if (d <= 128)
