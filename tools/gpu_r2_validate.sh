@@ -1,4 +1,5 @@
 #!/bin/bash
+# validation pass: all GPU tests, the default bench line, ncu --set full of the backward contraction, eager timeline of one step
 mkdir -p gpurun_out
 timeout 1700 python -m pytest tests -m gpu -x -q > gpurun_out/f1_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/f1_pytest.log
 timeout 900 python bench.py > gpurun_out/f1_bench.json 2> gpurun_out/f1_bench.err; echo "bench rc=$?"
