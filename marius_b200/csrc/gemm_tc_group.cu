@@ -405,7 +405,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV ? kConvThreads 
         // registers per thread at 704 threads: spills) 516 us; 3 groups reading the scores straight from global memory into registers
         // one own k-block ahead (no raw ring, 6 operand stages) 673 us -- L2 latency under this load exceeds the slack; the contraction
         // alone, operands from global bf16 arrays, 369 us.  At 3 groups the kernel sits at ~75 % of the shared-memory bandwidth (operand
-        // reads 34 %, converter loads / stores 42 %) and 65 % tensor-pipe utilisation (profiles/r2_ncu.md).
+        // reads 34 %, converter loads / stores 42 %) and 65 % tensor-pipe utilisation (profiles/r2_ncu_step_mid.csv); with private raw slots
+        // 460 us.  gemm_tc_ts_kernel below (A through tensor memory, full-width tiles) does the same work in 374 us and is the one used
+        // whenever the output fits its 416 accumulator columns.
         // Raw ring: this CTA's fp32 score tile of a k-block (128 operand rows x 32 K, 16 KB, row-major, no swizzle) is loaded by TMA into
         // the private slot of the group that converts it; thread 0 of the group issues the load of the group's next k-block as soon as
         // every thread of the group has read the current one (the load cursor walks the same tile table, across tile boundaries).
