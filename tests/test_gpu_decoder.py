@@ -221,6 +221,25 @@ def test_backward_contraction_kernels_vs_fp64(ops, ctx, which, a_mn):
         assert err < 3e-5, (which, a_mn, bt, M, N, K, err)
 
 
+def test_single_bf16_product_mode(ops, ctx):
+    """MB_PREC_BF16 (one bf16 product, never the default: it misses the 1e-4 bar) through the backward kernels and the whole batch:
+    the error is what bf16 operands give (~1e-3 .. 1e-2), not garbage."""
+    torch.manual_seed(5)
+    for which in (2, 3):
+        for a_mn in (False, True):
+            A = torch.randn(2, 1000, 1000, device="cuda")
+            Bm = torch.randn(2, 1000, 400, device="cuda")
+            ref = (A.double().transpose(1, 2) if a_mn else A.double()) @ Bm.double()
+            D = ops.debug_gemm(ctx, A, a_mn, Bm, True, ops.PREC_BF16, which)
+            err = float((D.double() - ref).abs().max() / ref.abs().max())
+            assert 1e-5 < err < 2e-2, (which, a_mn, err)
+    uniq, edges, dn, sn, emb, state, rel, inv_rel = _random_problem(77, 2, 333, 4, 200, 64, 50000, 11)
+    ref = O.train_batch(2, emb, state, edges, rel, inv_rel, dn, sn, 0.1, O.REDUCTION_SUM, acc=np.float64)
+    out = ops.train_batch(ctx, 2, dev(emb), dev(state), dev(edges), dev(rel), dev(inv_rel), dev(dn), dev(sn), 0.1, ops.REDUCTION_SUM, ops.PREC_BF16)
+    assert abs(float(out["loss"].item()) - float(ref.loss)) <= 2e-2 * abs(float(ref.loss))
+    assert rel_err(out["grad"], ref.grad) < 5e-2
+
+
 @pytest.mark.parametrize("which", [4, 5])
 def test_backward_contractions_back_to_back(ops, ctx, which, monkeypatch):
     """Both backward problems in one grouped launch, several tiles per CTA pair, launched back to back without a synchronisation in
