@@ -1,4 +1,4 @@
-"""tools/ncu_step_table.py <launches.csv> <first_id> <last_id> -- per-kernel table (markdown) + traffic summary (json) of one bench step
+"""tools/ncu_step_table.py <launches.csv> <first_id> <last_id> [summary.json] -- per-kernel table (markdown) + traffic summary (json) of one bench step
 from the long-format CSV of `ncu --replay-mode application --metrics ... --csv` (tools/gpu_r2_prof.sh)."""
 import collections
 import csv
@@ -6,6 +6,7 @@ import json
 import sys
 
 path, first, last = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+json_out = sys.argv[4] if len(sys.argv) > 4 else "/tmp/step_table.json"
 rows = list(csv.reader(open(path)))
 h = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
 hdr = rows[h]
@@ -46,4 +47,4 @@ for i, d in data.items():
     kernels.append(dict(kernel=d["name"], us=round(us, 1), dram_read_mb=round(rd / 1e6, 1), dram_write_mb=round(wr / 1e6, 1), gbs=round(gbs), warps_active_pct=round(wa, 1),
                         regs=regs, tensor_pct=round(tp, 1), grid=int(d.get("launch__grid_size", 0))))
 print(f"\nSum: {tot_us:.0f} us of kernel time (main stream {tot_main:.0f} us), {tot_b / 1e9:.3f} GB of DRAM traffic")
-json.dump(dict(step_dram_bytes=tot_b, step_kernel_us_serialised=tot_us, kernels=kernels), open("/tmp/step_table.json", "w"), indent=1)
+json.dump(dict(step_dram_bytes=tot_b, step_kernel_us_serialised=tot_us, kernels=kernels), open(json_out, "w"), indent=1)
